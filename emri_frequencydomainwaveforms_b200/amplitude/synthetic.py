@@ -1,0 +1,55 @@
+"""Synthetic Teukolsky-amplitude producer with FEW's mode-index layout.
+
+The reference evaluates ``few.amplitude.romannet.RomanAmplitude`` (ROMAN network; weights are a
+Zenodo download, absent offline).  This stand-in keeps what the hot path depends
+on: the (l, m, n) layout -- l = 2..10, m = 0..l, n = -30..30, 3843 modes -- a ``[L, 3843]``
+complex128 return, smooth dependence on (p, e) and >= 6 decades of dynamic range across modes.
+It is an input producer, not part of the accelerated path.
+"""
+import numpy as np
+
+LMAX, NMAX = 10, 30
+
+
+def mode_index_arrays(lmax=LMAX, nmax=NMAX):
+    l_arr, m_arr, n_arr = [], [], []
+    for l in range(2, lmax + 1):
+        for m in range(0, l + 1):
+            for n in range(-nmax, nmax + 1):
+                l_arr.append(l), m_arr.append(m), n_arr.append(n)
+    return (np.asarray(l_arr, dtype=np.int32), np.asarray(m_arr, dtype=np.int32),
+            np.asarray(n_arr, dtype=np.int32))
+
+
+class SyntheticAmplitude:
+    """``amp(p, e)`` -> ``teuk_modes[L, num_modes]`` complex128 (call shape of RomanAmplitude)."""
+
+    def __init__(self, lmax=LMAX, nmax=NMAX, **kwargs):
+        self.lmax, self.nmax = lmax, nmax
+        self.l_arr, self.m_arr, self.n_arr = mode_index_arrays(lmax, nmax)
+        self.num_teuk_modes = len(self.l_arr)
+        lm = self.l_arr.astype(np.int64) * 100 + self.m_arr
+        _, first, inverse = np.unique(lm, return_index=True, return_inverse=True)
+        self.unique_l = self.l_arr[first]
+        self.unique_m = self.m_arr[first]
+        self.inverse_lm = inverse
+
+    def __call__(self, p, e, *args, specific_modes=None, **kwargs):
+        p = np.atleast_1d(np.asarray(p, dtype=np.float64))[:, None]
+        e = np.atleast_1d(np.asarray(e, dtype=np.float64))[:, None]
+        l = self.l_arr[None, :].astype(np.float64)
+        m = self.m_arr[None, :].astype(np.float64)
+        n = self.n_arr[None, :].astype(np.float64)
+        base = (1.0 / p) * p ** (-(l - 2.0) / 2.0) * (0.6 ** (l - 2.0)) / (1.0 + (l - m))
+        n0 = 2.5 * e / np.sqrt(1.0 - e) * (1.0 + 0.2 * m)
+        sig = 0.35 + 3.5 * e
+        env = np.exp(-((n - n0) ** 2) / (2.0 * sig * sig))
+        ph = 0.4 * l - 0.25 * m + 0.15 * n + 8.0 / p + 0.5 * e * n / 3.0
+        out = base * env * np.exp(1j * ph)
+        if specific_modes is not None:
+            res = {}
+            for (ll, mm, nn) in specific_modes:
+                idx = np.where((self.l_arr == ll) & (self.m_arr == abs(mm)) & (self.n_arr == nn))[0][0]
+                res[(ll, mm, nn)] = out[:, idx].copy()
+            return res
+        return out

@@ -1,0 +1,40 @@
+"""Mode selection by power (mirror of ``few.utils.modeselector.ModeSelector``).
+
+Host-side; sits immediately before the hot path (SURVEY.md section 8f rank 1 lists a device version
+as "next").  Semantics: power = |[A, conj(A[:, m>0])] * ylms|^2 per time sample, sort descending,
+cumulative sum, keep while cumsum < (1 - eps) * total (first always kept), union over time samples,
+fold -m picks back onto their +m mode so +-m stay together.
+"""
+import numpy as np
+
+
+class ModeSelector:
+    def __init__(self, m0mask, use_gpu=False, **kwargs):
+        self.m0mask = np.asarray(m0mask, dtype=bool)       # True where m != 0
+        self.num_m_zero_up = len(self.m0mask)
+        self.num_m_1_up = int(self.m0mask.sum())
+        self.num_m0 = self.num_m_zero_up - self.num_m_1_up
+
+    def __call__(self, teuk_modes, ylms, modeinds, eps=1e-5):
+        """teuk_modes [L, M]; ylms [M + M_{m>0}] ( +m block, then -m block for m>0 modes );
+        modeinds = [l_arr, m_arr, n_arr].  Returns (teuk_modes_kept, ylms_kept [2K], ls, ms, ns)."""
+        zero_up = self.num_m_zero_up
+        full = np.concatenate([teuk_modes, np.conj(teuk_modes[:, self.m0mask])], axis=1)
+        power = np.abs(full * ylms[None, :]) ** 2
+        inds_sort = np.argsort(power, axis=1)[:, ::-1]
+        power_sorted = np.take_along_axis(power, inds_sort, axis=1)
+        cumsum = np.cumsum(power_sorted, axis=1)
+        thresh = cumsum[:, -1][:, None] * (1.0 - eps)
+        keep_sorted = np.ones_like(cumsum, dtype=bool)
+        keep_sorted[:, 1:] = cumsum[:, :-1] < thresh
+        picked = np.unique(inds_sort[keep_sorted])
+        # fold -m picks onto their +m partner
+        m_nonzero_idx = np.where(self.m0mask)[0]
+        neg = picked >= zero_up
+        keep_modes = np.unique(np.concatenate([picked[~neg], m_nonzero_idx[picked[neg] - zero_up]]))
+        # position of each kept mode inside the -m block (m = 0 modes reuse their +m ylm)
+        pos_in_neg = np.cumsum(self.m0mask) - 1
+        neg_idx = np.where(self.m0mask[keep_modes], zero_up + pos_in_neg[keep_modes], keep_modes)
+        ylms_kept = np.concatenate([ylms[keep_modes], ylms[neg_idx]])
+        l_arr, m_arr, n_arr = modeinds
+        return (teuk_modes[:, keep_modes], ylms_kept, l_arr[keep_modes], m_arr[keep_modes], n_arr[keep_modes])

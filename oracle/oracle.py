@@ -1,0 +1,151 @@
+"""ctypes front-end of the CPU oracle (oracle/emrifd_oracle.c).
+
+TEST INFRASTRUCTURE ONLY: may be imported by tests/, __graft_entry__.smoke() and bench.py's
+cpu_baseline / --impl reference legs -- never by the product package.  "parity unpinned" against
+FastEMRIWaveforms itself (not installable here); pinned against SciPy/mpmath/lisatools-derived goldens.
+"""
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_BUILD = os.path.join(_HERE, "_build")
+MAXBR = 4
+
+BRANCH_DTYPE = np.dtype([
+    ("mode", np.int32), ("dir", np.int32), ("ja", np.int32), ("jb", np.int32),
+    ("closed_end", np.int32), ("pad", np.int32), ("start", np.int64), ("end", np.int64),
+    ("xa", np.float64), ("xb", np.float64), ("Fa", np.float64), ("Fb", np.float64)])
+
+
+def build(force=False):
+    """Compile the oracle with its Makefile (gcc, -ffp-contract=off)."""
+    need = force or not all(os.path.exists(os.path.join(_BUILD, f))
+                            for f in ("liboracle_f64.so", "liboracle_quad.so"))
+    if need:
+        subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
+
+
+_dp = np.ctypeslib.ndpointer(dtype=np.float64, flags="C_CONTIGUOUS")
+_ip = np.ctypeslib.ndpointer(dtype=np.int32, flags="C_CONTIGUOUS")
+
+
+class Oracle:
+    """One precision flavour of the oracle: 'quad' (binary128 evaluation, the truth) or 'f64'."""
+
+    def __init__(self, flavour="quad"):
+        build()
+        self.flavour = flavour
+        self.lib = C.CDLL(os.path.join(_BUILD, f"liboracle_{flavour}.so"))
+        L = self.lib
+        assert L.orc_sizeof_branch() == BRANCH_DTYPE.itemsize
+        L.orc_spline_build.argtypes = [_dp, _dp, C.c_int, C.c_int, _dp]
+        L.orc_spline_eval.argtypes = [_dp, _dp, C.c_int, C.c_int, _dp, C.c_int64, _dp]
+        L.orc_segment_build.argtypes = [_dp, _dp, C.c_int, C.c_int, _ip, _ip, C.c_int64, C.c_double,
+                                        C.c_void_p, C.c_void_p, _ip]
+        L.orc_mode_sum.argtypes = [_dp, _dp, C.c_int, C.c_int, _ip, _ip, _dp, C.c_int64, C.c_double,
+                                   C.c_void_p, C.c_void_p, _ip, C.c_int, C.c_double, C.c_double,
+                                   C.c_double, C.c_int64, C.c_int64, _dp, _dp, C.c_void_p]
+        L.orc_inner_product.argtypes = [_dp, _dp, C.c_int, C.c_int64, _dp, C.c_void_p]
+        L.orc_inner_product.restype = C.c_double
+        L.orc_loglike.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int64, _dp]
+        L.orc_spa_R.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_spa_S.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+
+    # -- A3 ---------------------------------------------------------------------------------
+    def spline_build(self, t, y):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        y = np.ascontiguousarray(np.atleast_2d(y), dtype=np.float64)
+        R, L = y.shape
+        coeff = np.zeros((L, R, 4))
+        rc = self.lib.orc_spline_build(t, y, L, R, coeff)
+        if rc:
+            raise ValueError(f"oracle spline_build failed rc={rc}")
+        return coeff
+
+    def spline_eval(self, t, coeff, tnew):
+        t = np.ascontiguousarray(t, dtype=np.float64)
+        tnew = np.ascontiguousarray(tnew, dtype=np.float64)
+        L, R, _ = coeff.shape
+        out = np.zeros((R, len(tnew)))
+        self.lib.orc_spline_eval(t, np.ascontiguousarray(coeff), L, R, tnew, len(tnew), out)
+        return out
+
+    # -- A4 ---------------------------------------------------------------------------------
+    def segment_build(self, t, coeff, m_arr, n_arr, N, val=0.0, fpos=None):
+        L, R, _ = coeff.shape
+        K = (R - 4) // 2
+        br = np.zeros((K, MAXBR), dtype=BRANCH_DTYPE)
+        nbr = np.zeros(K, dtype=np.int32)
+        fp = None if fpos is None else np.ascontiguousarray(fpos, dtype=np.float64)
+        rc = self.lib.orc_segment_build(
+            np.ascontiguousarray(t, dtype=np.float64), np.ascontiguousarray(coeff), L, K,
+            np.ascontiguousarray(m_arr, dtype=np.int32), np.ascontiguousarray(n_arr, dtype=np.int32),
+            int(N), float(val), None if fp is None else fp.ctypes.data, br.ctypes.data, nbr)
+        if rc:
+            raise ValueError(f"oracle segment_build failed rc={rc}")
+        return br, nbr
+
+    # -- A5-A7 ------------------------------------------------------------------------------
+    def mode_sum(self, t, coeff, m_arr, n_arr, ylms, N, branches, nbr, val=0.0, fpos=None,
+                 include_minus_m=True, scale=1.0, cos2psi=1.0, sin2psi=0.0, out_lo=0, out_n=None):
+        L, R, _ = coeff.shape
+        K = (R - 4) // 2
+        out_n = int(N - out_lo if out_n is None else out_n)
+        hp = np.zeros(2 * out_n)
+        hc = np.zeros(2 * out_n)
+        fp = None if fpos is None else np.ascontiguousarray(fpos, dtype=np.float64)
+        nev = C.c_int64(0)
+        yl = np.ascontiguousarray(ylms, dtype=np.complex128).view(np.float64)
+        rc = self.lib.orc_mode_sum(
+            np.ascontiguousarray(t, dtype=np.float64), np.ascontiguousarray(coeff), L, K,
+            np.ascontiguousarray(m_arr, dtype=np.int32), np.ascontiguousarray(n_arr, dtype=np.int32),
+            yl, int(N), float(val), None if fp is None else fp.ctypes.data,
+            branches.ctypes.data, np.ascontiguousarray(nbr, dtype=np.int32), int(include_minus_m),
+            float(scale), float(cos2psi), float(sin2psi), int(out_lo), out_n, hp, hc, C.addressof(nev))
+        if rc:
+            raise ValueError(f"oracle mode_sum failed rc={rc}")
+        self.last_n_eval = nev.value
+        return hp.view(np.complex128), hc.view(np.complex128)
+
+    # -- A10/A11 ----------------------------------------------------------------------------
+    def inner_product(self, a, b, freqs, psd=None):
+        a = np.ascontiguousarray(np.atleast_2d(a), dtype=np.complex128)
+        b = np.ascontiguousarray(np.atleast_2d(b), dtype=np.complex128)
+        nch, n = a.shape
+        ps = None if psd is None else np.ascontiguousarray(psd, dtype=np.float64)
+        return self.lib.orc_inner_product(a.view(np.float64), b.view(np.float64), nch, n,
+                                          np.ascontiguousarray(freqs, dtype=np.float64),
+                                          None if ps is None else ps.ctypes.data)
+
+    def loglike(self, d_whitened, h, noise_factor):
+        d = np.ascontiguousarray(np.atleast_2d(d_whitened), dtype=np.complex128)
+        hh = np.ascontiguousarray(np.atleast_2d(h), dtype=np.complex128)
+        w = np.ascontiguousarray(np.atleast_2d(noise_factor), dtype=np.float64)
+        nch, n = d.shape
+        out = np.zeros(3)
+        self.lib.orc_loglike(d.view(np.float64), hh.view(np.float64), w, nch, n, out)
+        return out  # ll, 4*sum Re(d* h w), 4*sum |h w|^2
+
+    def spa_R(self, X):
+        a, b = C.c_double(), C.c_double()
+        self.lib.orc_spa_R(float(X), C.byref(a), C.byref(b))
+        return complex(a.value, b.value)
+
+    def spa_S(self, X):
+        a, b = C.c_double(), C.c_double()
+        self.lib.orc_spa_S(float(X), C.byref(a), C.byref(b))
+        return complex(a.value, b.value)
+
+    # -- whole FDInterpolatedModeSum.sum restated -------------------------------------------
+    def fd_sum(self, t, teuk_modes, ylms, Phi_phi, Phi_r, m_arr, n_arr, f_phi, f_r, N, val=0.0,
+               fpos=None, **kw):
+        """y_all rows = [Re A | Im A | f_phi, f_r, Phi_phi, Phi_r]; returns (hp, hc, coeff, branches, nbr)."""
+        y = np.concatenate([teuk_modes.T.real, teuk_modes.T.imag,
+                            np.stack([f_phi, f_r, Phi_phi, Phi_r])])
+        coeff = self.spline_build(t, y)
+        br, nbr = self.segment_build(t, coeff, m_arr, n_arr, N, val, fpos)
+        hp, hc = self.mode_sum(t, coeff, m_arr, n_arr, ylms, N, br, nbr, val, fpos, **kw)
+        return hp, hc, coeff, br, nbr
