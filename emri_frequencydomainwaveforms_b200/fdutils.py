@@ -1,0 +1,65 @@
+"""FD adapters of the reference's FDutils.py that sit on the hot path.
+
+* ``get_sensitivity(f)``  -- FDutils.py:4-5,21-33: not-a-knot cubic spline through the
+  LISA_Alloc_Sh table, evaluated WITH extrapolation (f = 0 included).  Built and evaluated on the GPU
+  with the same spline kernels as the waveform (data/lisa_alloc_sh.npy is the table, converted by
+  scripts/convert_reference_data.py).
+* ``get_fd_waveform_fromFD`` -- FDutils.py:105-139: call the generator, keep f >= 0, zero outside
+  ``non_zero_mask``.  When the mask is exactly ``frequency >= 0`` the generator is asked for
+  ``mask_positive=True`` so no boolean gather pass is needed.
+"""
+import os
+
+import numpy as np
+
+_DATA = os.path.join(os.path.dirname(os.path.abspath(__file__)), "data")
+_psd_spline = None
+
+
+def _spline():
+    global _psd_spline
+    if _psd_spline is None:
+        from .summation.interpolatedmodesum import CubicSplineInterpolant
+        S = np.load(os.path.join(_DATA, "lisa_alloc_sh.npy"))
+        _psd_spline = CubicSplineInterpolant(S[:, 0], S[:, 1])
+    return _psd_spline
+
+
+def get_sensitivity(f):
+    """LISA sensitivity S_n(f) [s]; returns the input's array type (numpy in -> numpy out)."""
+    import torch
+    out = _spline()(f)[0]
+    if torch.is_tensor(f):
+        return out
+    return out.cpu().numpy() if np.ndim(f) else float(out.cpu().numpy())
+
+
+class get_fd_waveform_fromFD:
+    def __init__(self, waveform_generator, positive_frequency_mask, dt, non_zero_mask=None, window=None,
+                 window_in_fd=False):
+        if window is not None:
+            raise ValueError("Windowed FD convolution is not on this path yet (SURVEY.md section 8f rank 2).")
+        self.waveform_generator = waveform_generator
+        self.positive_frequency_mask = positive_frequency_mask
+        self.non_zero_mask = non_zero_mask
+        self.window = window
+        self.window_in_fd = window_in_fd
+        m = np.asarray(positive_frequency_mask.cpu() if hasattr(positive_frequency_mask, "cpu")
+                       else positive_frequency_mask)
+        n = len(m)
+        self._is_upper_half = bool(n % 2 == 1 and m[(n - 1) // 2:].all() and not m[: (n - 1) // 2].any())
+
+    def __call__(self, *args, **kwargs):
+        import torch
+        if self._is_upper_half and not kwargs.get("mask_positive", False):
+            ch1, ch2 = self.waveform_generator(*args, mask_positive=True, **kwargs)
+        else:
+            chans = self.waveform_generator(*args, **kwargs)
+            mask = torch.as_tensor(np.asarray(self.positive_frequency_mask), device=chans[0].device)
+            ch1, ch2 = chans[0][mask], chans[1][mask]
+        if self.non_zero_mask is not None:
+            nz = torch.as_tensor(np.asarray(self.non_zero_mask.cpu() if hasattr(self.non_zero_mask, "cpu")
+                                            else self.non_zero_mask), device=ch1.device)
+            ch1 = torch.where(nz, ch1, torch.zeros_like(ch1))
+            ch2 = torch.where(nz, ch2, torch.zeros_like(ch2))
+        return [ch1, ch2]

@@ -97,3 +97,176 @@ def test_cubic_spline_interpolant(oracle_quad, torch_cuda):
         CubicSplineInterpolant(t[:3], y[:, :3])         # not-a-knot needs >= 4 knots
     with pytest.raises(ValueError):
         CubicSplineInterpolant(t[::-1].copy(), y)       # knots must increase
+
+
+# ------------------------------------------------------------------------------------------------
+# A9-A11: PSD, inner product, likelihood
+# ------------------------------------------------------------------------------------------------
+import os
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+
+
+def test_get_sensitivity_matches_scipy_golden(torch_cuda):
+    from emri_frequencydomainwaveforms_b200.fdutils import get_sensitivity
+    g = np.load(os.path.join(GOLD, "spline_golden.npz"))
+    ev = get_sensitivity(g["psd_f"])
+    assert isinstance(ev, np.ndarray) and np.all(ev[:3] > 0)            # extrapolated S(0) > 0
+    assert np.max(np.abs(ev - g["psd_val"]) / np.abs(g["psd_val"])) < 1e-9
+
+
+def test_inner_product_matches_lisatools_golden(torch_cuda):
+    from emri_frequencydomainwaveforms_b200.lisatools.diagnostic import inner_product, snr
+    g = np.load(os.path.join(GOLD, "lisatools_golden.npz"))
+    a, b, f, psd = [g["a"][0], g["a"][1]], [g["b"][0], g["b"][1]], g["f"], g["psd"]
+    assert np.isclose(inner_product(a, b, f_arr=f, PSD=psd), g["ip_ab"], rtol=1e-12)
+    assert np.isclose(inner_product(a, b, f_arr=f, PSD=psd, normalize=True), g["ip_ab_norm"], rtol=1e-12)
+    assert np.isclose(inner_product(a, b, f_arr=f, PSD=psd, complex=True), g["ip_ab_complex"], rtol=1e-12)
+    assert np.isclose(inner_product(a, b, f_arr=f, PSD=psd, normalize="sig1"), g["ip_ab_sig1"], rtol=1e-12)
+    assert np.isclose(inner_product(a[0], b[0], f_arr=f, PSD=psd), g["ip_a0b0"], rtol=1e-12)
+    assert np.isclose(inner_product(a, b, df=f[1] - f[0], PSD=psd), g["ip_df"], rtol=1e-12)
+    assert np.isclose(snr(a, f_arr=f, PSD=psd), g["snr_a"], rtol=1e-12)
+    assert np.isclose(inner_product(a, a, f_arr=f, PSD=psd, normalize=True), 1.0, rtol=1e-14)
+    ta = [torch_cuda.as_tensor(x).cuda() for x in a]                      # device tensors in -> same number
+    assert np.isclose(inner_product(ta, ta, f_arr=torch_cuda.as_tensor(f).cuda(), PSD=torch_cuda.as_tensor(psd).cuda()),
+                      inner_product(a, a, f_arr=f, PSD=psd), rtol=1e-15)
+    with pytest.raises(ValueError):
+        inner_product(a, b)
+    with pytest.raises(ValueError):
+        inner_product(a, b[:1], f_arr=f, PSD=psd)
+
+
+def test_likelihood_mirror_matches_lisatools_golden(torch_cuda):
+    from emri_frequencydomainwaveforms_b200.lisatools.likelihood import Likelihood
+    from emri_frequencydomainwaveforms_b200.fdutils import get_sensitivity
+    g = np.load(os.path.join(GOLD, "lisatools_golden.npz"))
+    templates, f = g["templates"], g["f"]
+
+    def model(idx, amp, **kw):
+        return [amp * templates[int(idx)][0], amp * templates[int(idx)][1]]
+
+    like = Likelihood(model, 2, f_arr=f, vectorized=False, transpose_params=False, subset=2)
+    like.inject_signal(data_stream=[g["a"][0], g["a"][1]], noise_fn=[get_sensitivity, get_sensitivity], noise_kwargs=[{}, {}])
+    assert np.allclose(like.noise_factor, g["like_noise_factor"], rtol=1e-9)
+    ll = like(g["like_params"])
+    assert ll.shape == (5,) and abs(ll[0]) < 1e-20                        # likelihood at the injection is 0
+    assert np.allclose(ll[1:], g["like_ll"][1:], rtol=1e-8)
+    with pytest.raises(ValueError):
+        like(list(g["like_params"]))
+
+
+def _emri_params(n, rng=None):
+    base = np.array([1e6, 50.0, 0.0, 9.0, 0.3, 1.0, 1.0, 0.8, 0.4, 1.1, 2.0, 0.3, 0.0, 1.1])
+    out = np.tile(base, (n, 1))
+    if rng is not None and n > 1:
+        out[1:, 0] *= 1 + 1e-5 * rng.normal(size=n - 1)
+        out[1:, 3] += 1e-4 * rng.normal(size=n - 1)
+        out[1:, 4] += 1e-4 * rng.normal(size=n - 1)
+        out[1:, 11] += 1e-2 * rng.normal(size=n - 1)
+    return out
+
+
+def test_generate_emri_waveform_surface(oracle_quad, torch_cuda):
+    from emri_frequencydomainwaveforms_b200.waveform import GenerateEMRIWaveform
+    kw = dict(T=0.1, dt=20.0, eps=1e-2)
+    sum_kwargs = dict(pad_output=True, output_type="fd", odd_len=True)
+    gen = GenerateEMRIWaveform("FastSchwarzschildEccentricFlux", sum_kwargs=sum_kwargs, use_gpu=True, return_list=False)
+    gen_list = GenerateEMRIWaveform("FastSchwarzschildEccentricFlux", sum_kwargs=sum_kwargs, use_gpu=True, return_list=True)
+    p = _emri_params(1)[0]
+    h = gen(*p, **kw)
+    hl = gen_list(*p, **kw)
+    freq = gen.waveform_generator.create_waveform.frequency                 # emri_pe.py:238
+    N = h.shape[0]
+    assert N % 2 == 1 and freq.shape[0] == N and int((freq == 0).sum()) == 1
+    assert torch_cuda.equal(h, hl[0] - 1j * hl[1])                          # check_mode_by_mode.py:247 "check 1 =="
+    pos = gen_list(*p, mask_positive=True, **kw)                            # emri_pe.py:241-243
+    mask = (freq >= 0.0)
+    assert torch_cuda.equal(pos[0], hl[0][mask]) and torch_cuda.equal(pos[1], hl[1][mask])
+    # against the oracle, including distance scaling and the SSB polarisation rotation
+    base = gen.waveform_generator
+    theta, phi, c2, s2 = gen._transform(*p[7:11])
+    it = base.prepare(p[0], p[1], p[3], p[4], theta, phi, dist=p[6], Phi_phi0=p[11], Phi_r0=p[13], **kw)
+    hp_o, hc_o, *_ = oracle_quad.fd_sum(it["t"], it["teuk_modes"], it["ylms"], it["Phi_phi"], it["Phi_r"], it["m_arr"],
+                                        it["n_arr"], it["f_phi"], it["f_r"], N, 1.0 / (N * kw["dt"]), scale=it["scale"],
+                                        cos2psi=c2, sin2psi=s2)
+    assert rel_err(hl[0].cpu().numpy(), hp_o) <= TOL_BIN and rel_err(hl[1].cpu().numpy(), hc_o) <= TOL_BIN
+    with pytest.raises(ValueError):
+        gen(*np.r_[p[:4], 0.9, p[5:]], **kw)                                # e0 out of range -> ValueError like FEW
+
+
+def test_fused_batched_likelihood_against_oracle(oracle_quad, torch_cuda):
+    """emri_pe.py-style: inject the FD signal, evaluate a ragged walker batch through the plugin
+    (fill_data_noise=True path of likelihood.py:330-331) -- one fused launch sequence, no h(f) in HBM."""
+    from emri_frequencydomainwaveforms_b200.waveform import GenerateEMRIWaveform
+    from emri_frequencydomainwaveforms_b200.lisatools.likelihood import FDTemplateModel, Likelihood
+    from emri_frequencydomainwaveforms_b200.fdutils import get_sensitivity
+    kw = dict(T=0.1, dt=20.0, eps=1e-2)
+    gen_list = GenerateEMRIWaveform("FastSchwarzschildEccentricFlux", sum_kwargs=dict(pad_output=True, output_type="fd", odd_len=True),
+                                    use_gpu=True, return_list=True)
+    rng = np.random.default_rng(3)
+    params = _emri_params(5, rng)
+    model = FDTemplateModel(gen_list)
+    sig = model(*params[0], **kw)
+    n = sig[0].shape[0]
+    N = 2 * n - 1
+    f_arr = np.arange(n) / (N * kw["dt"])
+    like = Likelihood(model, 2, f_arr=f_arr, fill_data_noise=True, subset=3)
+    like.inject_signal(data_stream=[sig[0], sig[1]], noise_fn=[get_sensitivity, get_sensitivity], noise_kwargs=[{}, {}])
+    ll = like(params, **kw)
+    assert ll.shape == (5,)
+    # oracle: per-walker waveform on f >= 0 and the lisatools likelihood algebra
+    items, ok = model.prepare_batch(params, **kw)
+    assert ok.all() and len({it["teuk_modes"].shape for it in items}) >= 1
+    dd = oracle_quad.loglike(like.injection_channels, np.zeros_like(like.injection_channels), like.noise_factor)[0]
+    for i, it in enumerate(items):
+        hp_o, hc_o, *_ = oracle_quad.fd_sum(it["t"], it["teuk_modes"], it["ylms"], it["Phi_phi"], it["Phi_r"], it["m_arr"],
+                                            it["n_arr"], it["f_phi"], it["f_r"], N, 1.0 / (N * kw["dt"]), scale=it["scale"],
+                                            cos2psi=it["cos2psi"], sin2psi=it["sin2psi"], out_lo=n - 1, out_n=n)
+        ref = oracle_quad.loglike(like.injection_channels, np.stack([hp_o, hc_o]), like.noise_factor)[0]
+        assert abs(ll[i] - ref) <= 1e-10 * abs(dd), (i, ll[i], ref)
+    assert abs(ll[0]) <= 1e-10 * abs(dd) and np.all(ll[1:] < 0)             # emri_pe.py:451: ll(injection) = 0
+    # materialised route (per-walker templates + emrifd_loglike) agrees with the fused route
+    like2 = Likelihood(lambda *p, **k: model(*p, **k), 2, f_arr=f_arr)
+    like2.inject_signal(data_stream=[sig[0], sig[1]], noise_fn=[get_sensitivity, get_sensitivity], noise_kwargs=[{}, {}])
+    ll2 = like2(params[:3], **kw)
+    assert np.allclose(ll2, ll[:3], rtol=1e-9, atol=1e-12 * abs(dd))
+    # an out-of-domain walker yields NaN (Eryn maps it to -1e300), the others are unaffected
+    bad = params.copy()
+    bad[2, 4] = 0.95
+    ll3 = like(bad, **kw)
+    assert np.isnan(ll3[2]) and np.array_equal(ll3[[0, 1, 3, 4]], ll[[0, 1, 3, 4]])
+
+
+def test_ragged_batch_equals_single_calls(generator, torch_cuda):
+    from emri_frequencydomainwaveforms_b200 import engine, _lib
+    items = [make_item(generator, n, dt=40.0) for n in ("plunge", "cfg1_like", "ecc_many")]
+    N = max(it["N"] for it in items)
+    val = 1.0 / (N * 40.0)
+    h = _lib.get_handle()
+    db = engine.DeviceBatch(engine.PackedBatch(items), h)
+    hp, hc, _ = engine.run_waveform(db, N, val, mask_positive=True)
+    h.status()
+    for i, it in enumerate(items):
+        d1 = engine.DeviceBatch(engine.PackedBatch([it]), h)
+        a, b, _ = engine.run_waveform(d1, N, val, mask_positive=True)
+        assert torch_cuda.equal(a[0], hp[i]) and torch_cuda.equal(b[0], hc[i])   # bit-identical: no atomics, fixed order
+
+
+def test_error_codes(generator, torch_cuda):
+    from emri_frequencydomainwaveforms_b200 import engine, _lib
+    from emri_frequencydomainwaveforms_b200.summation.fdinterp import FDInterpolatedModeSum
+    it = make_item(generator, "cfg1_like")
+    s = FDInterpolatedModeSum(pad_output=True, output_type="fd", odd_len=False)
+    args = (it["t"], it["teuk_modes"], it["ylms"], it["Phi_phi"], it["Phi_r"], it["m_arr"], it["n_arr"], it["M"], it["p"], it["e"])
+    with pytest.raises(ValueError):
+        s.sum(*args, f_arr=np.array([]))                                   # "Input f_arr has zero length."
+    with pytest.raises(ValueError):
+        s.sum(*args, f_arr=np.linspace(-1, 1, 10))                         # even length / no single zero
+    with pytest.raises(ValueError):
+        FDInterpolatedModeSum(output_type="td")
+    h = _lib.get_handle()
+    short = dict(it, t=it["t"][:3], teuk_modes=it["teuk_modes"][:3], Phi_phi=it["Phi_phi"][:3], Phi_r=it["Phi_r"][:3],
+                 f_phi=it["f_phi"][:3], f_r=it["f_r"][:3])
+    with pytest.raises(ValueError):
+        engine.run_waveform(engine.DeviceBatch(engine.PackedBatch([short]), h), 1001, 1e-5)    # < 4 knots
+    with pytest.raises(ValueError):
+        engine.run_loglike(engine.DeviceBatch(engine.PackedBatch([it]), _lib.Handle()), it["N"], 1.0 / (it["N"] * 10.0))  # no data set

@@ -1,0 +1,156 @@
+"""CPU tests of the host logic and of the C-ABI library's export table (no compute without a GPU)."""
+import ctypes
+import os
+import re
+
+import numpy as np
+import pytest
+
+from helpers import CASES, grid_size, make_item
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+GOLD = os.path.join(ROOT, "tests", "golden")
+
+
+def test_library_exports_every_declared_symbol():
+    from emri_frequencydomainwaveforms_b200 import _lib
+    from emri_frequencydomainwaveforms_b200.csrc import build
+    build.build()
+    header = open(os.path.join(ROOT, "include", "emrifd.h")).read()
+    declared = set(re.findall(r"\b(emrifd_[a-z0-9_]+)\s*\(", header))
+    assert declared == set(_lib.SYMBOLS)
+    lib = ctypes.CDLL(_lib.LIB_PATH)
+    for name in declared:
+        assert hasattr(lib, name), name
+    assert lib.emrifd_version() == 100
+    assert lib.emrifd_sizeof_branch() == _lib.BRANCH_DTYPE.itemsize == 72
+    assert lib.emrifd_sizeof_walker() == _lib.WALKER_DTYPE.itemsize
+
+
+def test_no_cpu_fallback():
+    import torch
+    if torch.cuda.is_available():
+        pytest.skip("GPU present")
+    from emri_frequencydomainwaveforms_b200 import _lib
+    from emri_frequencydomainwaveforms_b200.summation.interpolatedmodesum import CubicSplineInterpolant
+    with pytest.raises(_lib.EmrifdError):
+        CubicSplineInterpolant(np.arange(5.0), np.arange(5.0))
+    # the C-ABI itself refuses to create a handle without a device (no abort, an error code)
+    lib = _lib.load()
+    hp = ctypes.c_void_p()
+    assert lib.emrifd_create(0, None, ctypes.byref(hp)) == -6 and not hp.value
+
+
+def test_product_never_imports_oracle():
+    pkg = os.path.join(ROOT, "emri_frequencydomainwaveforms_b200")
+    for dp, _, files in os.walk(pkg):
+        for f in files:
+            if f.endswith((".py", ".cu", ".h")):
+                src = open(os.path.join(dp, f)).read()
+                assert not re.search(r"(import\s+oracle|from\s+oracle|liboracle|oracle[/.]_build|#include.*oracle|orc_[a-z_]+\()", src), f
+
+
+def test_fundamental_frequencies_against_quadrature():
+    from emri_frequencydomainwaveforms_b200.utils.utility import get_fundamental_frequencies, get_separatrix
+    p = np.array([12.0, 8.0, 7.5, 10.0, 6.3, 20.0, 9.1])
+    e = np.array([0.35, 0.5, 0.7, 1e-6, 0.1, 0.0, 0.62])
+    om_phi, om_th, om_r = get_fundamental_frequencies(0.0, p, e, np.ones_like(p))
+    chi = 2 * np.pi * np.arange(8192) / 8192
+    for i in range(len(p)):
+        c = np.cos(chi)
+        dt = p[i] ** 2 / ((p[i] - 2 - 2 * e[i] * c) * (1 + e[i] * c) ** 2) * np.sqrt(((p[i] - 2) ** 2 - 4 * e[i] ** 2) / (p[i] - 6 - 2 * e[i] * c))
+        dphi = np.sqrt(p[i] / (p[i] - 6 - 2 * e[i] * c))
+        Tr = dt.mean() * 2 * np.pi
+        assert abs(om_r[i] * Tr / (2 * np.pi) - 1) < 5e-14
+        assert abs(om_phi[i] * Tr / (dphi.mean() * 2 * np.pi) - 1) < 5e-14
+    assert np.allclose(om_phi[5], 20.0 ** -1.5) and np.allclose(om_r[5], 20.0 ** -1.5 * np.sqrt(1 - 6 / 20.0))
+    assert np.array_equal(get_separatrix(0.0, e, 1.0), 6 + 2 * e)
+    with pytest.raises(ValueError):
+        get_fundamental_frequencies(0.5, p, e, np.ones_like(p))
+
+
+def test_ylm_closed_forms_and_poles():
+    from emri_frequencydomainwaveforms_b200.utils.ylm import GetYlms, spin_weighted_ylm
+    th, ph = 0.7, 0.3
+    assert np.isclose(spin_weighted_ylm(-2, 2, 2, th, ph), np.sqrt(5 / (64 * np.pi)) * (1 + np.cos(th)) ** 2 * np.exp(2j * ph))
+    assert np.isclose(spin_weighted_ylm(-2, 2, -2, th, ph), np.sqrt(5 / (64 * np.pi)) * (1 - np.cos(th)) ** 2 * np.exp(-2j * ph))
+    assert np.isclose(spin_weighted_ylm(-2, 2, 0, th, ph), np.sqrt(15 / (32 * np.pi)) * np.sin(th) ** 2)
+    assert np.isclose(spin_weighted_ylm(-2, 3, 3, th, ph), -np.sqrt(21 / (2 * np.pi)) * np.cos(th / 2) ** 5 * np.sin(th / 2) * np.exp(3j * ph))
+    g = GetYlms(assume_positive_m=True)
+    y = g(np.array([2, 2, 3]), np.array([2, 0, 2]), np.pi, -np.pi / 2)      # the scripts' geometry: theta = pi
+    assert len(y) == 6 and abs(y[0]) < 1e-30 and abs(y[3]) > 0.1            # only Y_{l,-2} survives at the south pole
+    # orthonormality of l = 2..4, m = 1 on a quadrature grid
+    x, w = np.polynomial.legendre.leggauss(40)
+    for l1 in (2, 3, 4):
+        for l2 in (2, 3, 4):
+            v = sum(wi * spin_weighted_ylm(-2, l1, 1, np.arccos(xi), 0.0) * np.conj(spin_weighted_ylm(-2, l2, 1, np.arccos(xi), 0.0))
+                    for xi, wi in zip(x, w)) * 2 * np.pi
+            assert np.isclose(v, 1.0 if l1 == l2 else 0.0, atol=1e-12)
+    with pytest.raises(ValueError):
+        g(np.array([2]), np.array([-2]), 1.0, 0.0)
+
+
+def test_mode_selector_semantics(generator):
+    it2 = make_item(generator, "plunge")
+    it5 = make_item(generator, "plunge", eps=1e-5)
+    s2 = set(zip(it2["l_arr"].tolist(), it2["m_arr"].tolist(), it2["n_arr"].tolist()))
+    s5 = set(zip(it5["l_arr"].tolist(), it5["m_arr"].tolist(), it5["n_arr"].tolist()))
+    assert s2 < s5 and len(s5) > 3 * len(s2)                    # smaller eps keeps a superset
+    assert np.all(it2["m_arr"] >= 0) and len(it2["ylms"]) == 2 * len(it2["m_arr"])
+    K = len(it2["m_arr"])
+    m0 = it2["m_arr"] == 0
+    assert np.array_equal(it2["ylms"][:K][m0], it2["ylms"][K:][m0])   # m = 0: the -m slot repeats the +m ylm
+    it3 = generator.prepare(1e6, 10.0, 12.0, 0.35, 1.0, -np.pi / 2, T=0.05, mode_selection=[(2, 2, 0), (2, -2, 1), (3, 0, 1)])
+    assert sorted(zip(it3["l_arr"], it3["m_arr"], it3["n_arr"])) == [(2, 2, -1), (2, 2, 0), (3, 0, 1)]
+    with pytest.raises(ValueError):
+        generator.prepare(1e6, 10.0, 12.0, 0.35, 1.0, 0.0, T=0.05, mode_selection=[])
+    with pytest.raises(ValueError):
+        generator.prepare(1e6, 10.0, 12.0, 0.9, 1.0, 0.0, T=0.05)         # sanity_check_init: e0 > 0.75
+
+
+def test_trajectory_and_sizing(generator):
+    from emri_frequencydomainwaveforms_b200.trajectory.inspiral import EMRIInspiral
+    from emri_frequencydomainwaveforms_b200.utils.utility import get_p_at_t
+    from emri_frequencydomainwaveforms_b200.utils.constants import YRSID_SI
+    traj = EMRIInspiral(func="SchwarzEccFlux")
+    t, p, e, x, Pp, Pt, Pr = traj(1e6, 10.0, 0.0, 12.0, 0.35, 1.0, T=1.0)
+    assert 20 <= len(t) <= 200 and t[0] == 0.0 and np.all(np.diff(t) > 0)
+    assert np.isclose(t[-1], YRSID_SI) and np.all(np.diff(p) < 0) and np.all(np.diff(Pp) > 0)
+    assert grid_size(t, 1.0, 10.0) == 3155815                     # N at T = 1 yr, dt = 10 s
+    assert grid_size(t, 2.0, 10.0) % 2 == 1
+    p0 = get_p_at_t(traj, 0.2, [1e6, 50.0, 0.0, 0.3, 1.0])
+    t2, p2, e2, *_ = traj(1e6, 50.0, 0.0, p0, 0.3, 1.0, T=1.0)
+    assert abs(t2[-1] / YRSID_SI - 0.2) < 1e-6 and abs(p2[-1] - (6 + 2 * e2[-1] + 0.1)) < 1e-8
+    with pytest.raises(ValueError):
+        traj(1e6, 10.0, 0.0, 6.5, 0.3, 1.0)
+
+
+def test_grid_validation_and_packing(generator):
+    from emri_frequencydomainwaveforms_b200 import engine
+    N, fpos = engine.grid_from_frequency(np.fft.fftshift(np.fft.fftfreq(101, 10.0)))
+    assert N == 101 and len(fpos) == 51 and fpos[0] == 0.0
+    p = np.linspace(0.0, 0.01, 50)
+    N, fpos = engine.grid_from_frequency(np.hstack((-p[::-1][:-1], p)))       # emri_pe.py:339-342
+    assert N == 99 and np.array_equal(fpos, p)
+    for bad in (np.array([]), np.arange(-2.0, 2.0), np.array([-1.0, 0.0, 2.0]), np.array([-1.0, 0.5, 1.0])):
+        with pytest.raises(ValueError):
+            engine.grid_from_frequency(bad)
+    items = [make_item(generator, "cfg1_like"), make_item(generator, "ecc_many")]
+    pb = engine.PackedBatch(items)
+    w = pb.walkers
+    assert pb.B == 2 and w["knot_off"][1] == w["L"][0] and w["mode_off"][1] == w["K"][0]
+    assert w["coeff_off"][1] == w["L"][0] * (2 * w["K"][0] + 4) * 4 and len(pb.ylm) == 2 * pb.n_modes
+    assert pb.h2d_bytes() > 0
+    bad = dict(items[0], m_arr=items[0]["m_arr"][:-1])
+    with pytest.raises(ValueError):
+        engine.PackedBatch([bad])
+
+
+def test_transform_container_contract():
+    """The 6 -> 14 parameter fill + (logM, log eta) -> (M, mu) of emri_pe.py:161-206 (eryn transform.py:181-226)."""
+    g = np.load(os.path.join(GOLD, "lisatools_golden.npz"))
+    p6, p14 = g["tc_in"], g["tc_out"]
+    from emri_frequencydomainwaveforms_b200.utils.transform import fill_and_transform
+    out = fill_and_transform(p6, fill_inds=np.array([2, 5, 6, 7, 8, 9, 10, 12]),
+                             fill_values=np.array([0.0, 1.0, 2.45, np.pi / 3, np.pi / 3, np.pi / 3, np.pi / 3, 0.0]))
+    assert np.allclose(out, p14, rtol=1e-15)
