@@ -70,7 +70,7 @@ def load():
     lib.emrifd_set_data.argtypes = [vp, vp, vp, i64]
     lib.emrifd_inner_product.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
     lib.emrifd_loglike.argtypes = [vp, vp, i64, vp]
-    lib.emrifd_loglike_batch_host.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, vp, i32, vp]
+    lib.emrifd_loglike_batch_host.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, vp, i32, vp, vp, vp]
     lib.emrifd_bench_fp64_fma.argtypes = [vp, i32, C.POINTER(dbl)]
     lib.emrifd_launch_count.argtypes = [vp]
     lib.emrifd_launch_count.restype = i64

@@ -1112,7 +1112,8 @@ int emrifd_loglike_batch_host(emrifd_handle_t *h, const emrifd_walker_t *walkers
                               const double *t, const double *teuk, const double *f_phi, const double *f_r,
                               const double *Phi_phi, const double *Phi_r,
                               const int32_t *m_arr, const int32_t *n_arr, const double *ylm,
-                              int64_t N, double val, const double *fpos_dev, int flags, double *like_out_host) {
+                              int64_t N, double val, const double *fpos_dev, int flags,
+                              double *hp_dev, double *hc_dev, double *like_out_host) {
     if (!h || !t || !teuk || !f_phi || !f_r || !Phi_phi || !Phi_r || !m_arr || !n_arr || !ylm || !like_out_host)
         return set_err(h, EMRIFD_ERR_INVALID, "loglike_batch_host: NULL argument");
     int Lmax, Kmax, rc;
@@ -1153,7 +1154,7 @@ int emrifd_loglike_batch_host(emrifd_handle_t *h, const emrifd_walker_t *walkers
                                (double *)(d + o_pp), (double *)(d + o_pr), coeff))) return rc;
     if ((rc = batch_segment_dev(h, B, Kmax, (double *)(d + o_t), coeff, (int32_t *)(d + o_m), (int32_t *)(d + o_n), N, val, fpos_dev, br, nullptr))) return rc;
     if ((rc = batch_sum_dev(h, B, Lmax, (double *)(d + o_t), coeff, (int32_t *)(d + o_m), (int32_t *)(d + o_n), (double *)(d + o_y), br,
-                            N, val, fpos_dev, flags | EMRIFD_MASK_POSITIVE, 0, (N + 1) / 2, nullptr, nullptr, dout))) return rc;
+                            N, val, fpos_dev, flags | EMRIFD_MASK_POSITIVE, 0, (N + 1) / 2, hp_dev, hc_dev, dout))) return rc;
     double *hres = (double *)(hs + in_bytes);
     CUDA_TRY(h, cudaMemcpyAsync(hres, dout, sizeof(double) * 3 * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
     int st = 0;

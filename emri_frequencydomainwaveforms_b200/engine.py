@@ -132,13 +132,17 @@ def run_loglike(db, N, val=0.0, fpos_dev=None, include_minus_m=True):
     return like_out
 
 
-def run_loglike_host(pb, handle, N, val=0.0, fpos_dev=None, include_minus_m=True):
-    """The e2e call: HOST packed inputs in, HOST ll[B,3] out (H2D + kernels + D2H inside)."""
+def run_loglike_host(pb, handle, N, val=0.0, fpos_dev=None, include_minus_m=True, hp_dev=None, hc_dev=None):
+    """The e2e call: HOST packed inputs in, HOST ll[B,3] out (H2D + kernels + D2H inside).
+    hp_dev / hc_dev: optional device tensors [B, (N+1)/2] complex128 that receive the waveforms."""
     out = np.zeros((pb.B, 3))
+    if hp_dev is not None:
+        pb.walkers["out_off"] = np.arange(pb.B, dtype=np.int64) * ((N + 1) // 2)
     flags = (INCLUDE_MINUS_M if include_minus_m else 0) | MASK_POSITIVE
     rc = handle.lib.emrifd_loglike_batch_host(
         handle.h, pb.walkers.ctypes.data, pb.B, pb.t.ctypes.data, pb.teuk.ctypes.data, pb.f_phi.ctypes.data,
         pb.f_r.ctypes.data, pb.Phi_phi.ctypes.data, pb.Phi_r.ctypes.data, pb.m.ctypes.data, pb.n.ctypes.data,
-        pb.ylm.ctypes.data, int(N), float(val), _lib.ptr(fpos_dev), flags, out.ctypes.data)
+        pb.ylm.ctypes.data, int(N), float(val), _lib.ptr(fpos_dev), flags, _lib.ptr(hp_dev), _lib.ptr(hc_dev),
+        out.ctypes.data)
     handle.check(rc)
     return out

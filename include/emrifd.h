@@ -145,12 +145,15 @@ int emrifd_loglike(emrifd_handle_t *h, const double *templates, int64_t B, doubl
  * One call = what Likelihood.get_ll does per batch of walkers on the reference
  * (likelihood.py:245-274): FD template for every walker + ll against the injected data.
  * All array arguments are HOST pointers (pinned or pageable); H2D of the packed sparse inputs,
- * all kernels and the D2H of ll[B][3] happen inside; returns after the results are on the host. */
+ * all kernels and the D2H of ll[B][3] happen inside; returns after the results are on the host.
+ * If hp_dev/hc_dev are given the f >= 0 waveforms are also materialised on the device (like the
+ * reference's GPU path, where h stays a device array and only the likelihood crosses to the host). */
 int emrifd_loglike_batch_host(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,
                               const double *t, const double *teuk, const double *f_phi, const double *f_r,
                               const double *Phi_phi, const double *Phi_r,
                               const int32_t *m_arr, const int32_t *n_arr, const double *ylm,
                               int64_t N, double val, const double *fpos_dev, int flags,
+                              double *hp_dev, double *hc_dev, /* optional DEVICE outputs [B][(N+1)/2] complex (walker out_off), or NULL */
                               double *like_out_host /* [B][3] */);
 
 /* ---- measurement helpers (bench.py roofline denominators) ----------------------------------- */
