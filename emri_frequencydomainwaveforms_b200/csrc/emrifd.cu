@@ -24,8 +24,8 @@
 
 #define MAXBR EMRIFD_MAX_BRANCHES
 #define SUM_THREADS 256
-#define SUM_TILE 256
-#define LIST_CAP 768
+#define SUM_BPT 4 /* consecutive bins per thread */
+#define SUM_TILE (SUM_THREADS * SUM_BPT)
 #define SPL_THREADS 128
 #define SEG_THREADS 128
 #define SMEM_PER_KNOT 21 /* doubles: t, 16 track coefficients, 4 reduced knot phases */
@@ -431,43 +431,19 @@ struct SumParams {
     double *partial;   // [B][ntiles][3]
 };
 
-struct SmemView {
-    const double *T;  // [L]
-    const double *Q;  // [L][16]: f_phi(y,c1,c2,c3) f_r(..) Phi_phi(..) Phi_r(..)
-    const double *U;  // [L][4] : reduced knot phases in cycles (hi, lo) x (phi, r)
-};
 
-// one stationary point: returns C = A(t*) G e^{i(2 pi f t* - Phi_mn(t*))}
-__device__ __forceinline__ void eval_root(const SmemView &s, const double *__restrict__ coeff, int R, int K,
-                                          int k, double dm, double dn, int dir, int ja, int jb, double xa, double xb,
-                                          double f, double &Cr, double &Ci) {
-    // segment inside the branch
-    int lo = ja, hi = jb;
-    while (lo < hi) {
-        int mid = (lo + hi + 1) >> 1;
-        double Fk = radd(rmul(dm, s.Q[mid * 16 + 0]), rmul(dn, s.Q[mid * 16 + 4]));
-        bool ok = dir > 0 ? (Fk <= f) : (Fk >= f);
-        if (ok) lo = mid; else hi = mid - 1;
-    }
-    const int j = lo;
-    const double *q = s.Q + j * 16;
-    const double tj = s.T[j];
-    const double hj = s.T[j + 1] - tj;
-    const double c0 = radd(rmul(dm, q[0]), rmul(dn, q[4]));
-    const double c1 = fma(dm, q[1], dn * q[5]);
-    const double c2 = fma(dm, q[2], dn * q[6]);
-    const double c3 = fma(dm, q[3], dn * q[7]);
-    const double delta = f - c0;
-    double xl = (j == ja) ? xa : 0.0, xh = (j == jb) ? xb : hj;
-    // bracketed Newton on g(x) = x(c1 + x(c2 + x c3)) - delta
+// ---- fast reciprocal for Newton steps: 24-bit seed is enough (the iteration is self-correcting) ----
+__device__ __forceinline__ double fast_rcp(double d) { return (double)__frcp_rn((float)d); }
+
+// robust bracketed Newton (rare path: cold-start failures, turnover neighbourhood)
+__device__ __noinline__ double solve_bracketed(double c1, double c2, double c3, double delta, double xl, double xh,
+                                               double sdir, double hj) {
     double gl = xl * fma(xl, fma(xl, c3, c2), c1) - delta;
     double gh = xh * fma(xh, fma(xh, c3, c2), c1) - delta;
     double x = (gh == gl) ? 0.5 * (xl + xh) : xl - gl * (xh - xl) / (gh - gl);
     x = fmin(fmax(x, xl), xh);
-    const double sdir = (double)dir;
     const double tol = 1e-9 * hj;
-#pragma unroll 1
-    for (int it = 0; it < 60; it++) {
+    for (int it = 0; it < 80; it++) {
         const double gx = x * fma(x, fma(x, c3, c2), c1) - delta;
         const double dg = fma(x, fma(3.0 * c3, x, 2.0 * c2), c1);
         if (gx * sdir > 0.0) xh = x; else xl = x;
@@ -477,52 +453,70 @@ __device__ __forceinline__ void eval_root(const SmemView &s, const double *__res
         x = xn;
         if (dx <= tol) break;
     }
-    // amplitude splines (global, L2-resident quads)
-    const double4 a = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + k) * 4);
-    const double4 b = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + K + k) * 4);
-    const double ReA = fma(x, fma(x, fma(x, a.w, a.z), a.y), a.x);
-    const double ImA = fma(x, fma(x, fma(x, b.w, b.z), b.y), b.x);
-    const double fdot = fma(x, fma(3.0 * c3, x, 2.0 * c2), c1);
-    const double fddot = fma(6.0 * c3, x, 2.0 * c2);
-    double Gre, Gim;
-    spa_G(fdot, fddot, Gre, Gim);
-    // phase in cycles, reduced:  f t_j (exact product, mod 1) + f x - (m u_phi + n u_r) - (m p_phi(x) + n p_r(x))/2pi
-    const double pp = x * fma(x, fma(x, q[11], q[10]), q[9]);
-    const double pr = x * fma(x, fma(x, q[15], q[14]), q[13]);
-    double p0 = f * tj;
-    const double e0 = fma(f, tj, -p0);
-    p0 -= rint(p0);
-    const double *u = s.U + j * 4;
-    double cyc = p0 - fma(dm, u[0], dn * u[2]);
-    cyc -= rint(cyc);
-    const double small = e0 - fma(dm, u[1], dn * u[3]);
-    const double poly = fma(f, x, -EMRIFD_INV2PI_HI * fma(dm, pp, dn * pr));
-    cyc += (poly - rint(poly)) + small;
-    double sn, cs;
-    sincospi(2.0 * cyc, &sn, &cs);
-    const double agr = ReA * Gre - ImA * Gim, agi = ReA * Gim + ImA * Gre;
-    Cr = agr * cs - agi * sn;
-    Ci = agr * sn + agi * cs;
+    return x;
 }
 
+// SPA factor from fdot, fddot without divisions on the common path:
+//   s = 1/sqrt|fdot|,  u = 1/X = 3 fddot^2 s^6 / (2 pi)
+__device__ __forceinline__ void spa_G2(double fdot, double fddot, double &gre, double &gim) {
+    const double af = fabs(fdot);
+    const double s = rsqrt(af);
+    const double s2 = s * s;
+    const double u = 0.477464829275686 * (fddot * fddot) * (s2 * s2 * s2); // 3/(2 pi)
+    double re, im;
+    if (u <= 0.03125) { // X >= 32 (covers fddot == 0)
+        const double w = u * u;
+        if (u <= 0.0009765625) {
+            re = fma(w, fma(w, k13_asym_re[2], k13_asym_re[1]), 1.0);
+            im = u * fma(w, fma(w, k13_asym_im[2], k13_asym_im[1]), k13_asym_im[0]);
+        } else {
+            double pr = k13_asym_re[6], pi = k13_asym_im[6];
+#pragma unroll
+            for (int k = 5; k >= 0; k--) { pr = fma(pr, w, k13_asym_re[k]); pi = fma(pi, w, k13_asym_im[k]); }
+            re = pr; im = u * pi;
+        }
+        re *= s; im *= s;
+    } else if (u <= 1.0) { // 1 <= X < 32
+        k13_mid(1.0 / u, re, im);
+        re *= s; im *= s;
+    } else {               // X < 1: turnover regime, finite as fdot -> 0
+        const double X = 2.0943951023931953 * af * af * af / (fddot * fddot);
+        k13_small_S(X, re, im);
+        const double sc = cbrt(1.4472025091165353 / fabs(fddot));
+        re *= sc; im *= sc;
+    }
+    const double r2 = 0.7071067811865476;
+    gre = (-re - im) * r2;
+    gim = (re - im) * r2;
+    if (fdot < 0.0) gim = -gim;
+}
+
+// compacted work-list entry cached in shared memory (one per overlapping branch of the current chunk)
+struct __align__(16) Entry {
+    double xa, xb;
+    double ypr, ypi, ymr, ymi;
+    long long start, end;
+    int mode, dir, ja, jb;
+    int m, n, mirror, pad;
+};
+
 template <bool WRITE_H, bool LIKE>
-__global__ void __launch_bounds__(SUM_THREADS) mode_sum_kernel(SumParams p) {
-    extern __shared__ double sm[];
-    __shared__ int s_list[LIST_CAP];
+__global__ void __launch_bounds__(SUM_THREADS, 2) mode_sum_kernel(SumParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ int s_list[SUM_THREADS];
     __shared__ int s_wcount[SUM_THREADS / 32];
-    __shared__ int s_count;
     __shared__ double s_red[3][SUM_THREADS / 32];
 
     const emrifd_walker_t wd = p.w[blockIdx.y];
     const int L = wd.L, K = wd.K, R = 2 * K + 4;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long jt0 = p.j_lo + (long long)blockIdx.x * SUM_TILE;
-    const long long jend = p.j_lo + p.j_cnt; // exclusive
+    const long long jend = p.j_lo + p.j_cnt;                                   // exclusive
     const long long jt1 = (jt0 + SUM_TILE < jend ? jt0 + SUM_TILE : jend) - 1; // inclusive
-    const long long j = jt0 + tid;
-    const bool active = j <= jt1;
+    const long long j0 = jt0 + (long long)tid * SUM_BPT;                       // this thread's first bin
+    int nb = (int)(jt1 - j0 + 1);                                              // its number of valid bins
+    nb = nb < 0 ? 0 : (nb > SUM_BPT ? SUM_BPT : nb);
     const long long zero = p.g.zero;
-    // full-grid index ranges touched by this tile
     const long long pos_lo = zero + jt0, pos_hi = zero + jt1;
     const long long neg_lo = zero - jt1, neg_hi = zero - jt0;
 
@@ -531,107 +525,214 @@ __global__ void __launch_bounds__(SUM_THREADS) mode_sum_kernel(SumParams p) {
     const int *marr = p.m + wd.mode_off, *narr = p.n + wd.mode_off;
     const double2 *ylm = p.ylm + 2 * wd.mode_off;
 
-    double *sT = sm, *sQ = sm + L, *sU = sm + 17 * L;
-    SmemView sv; sv.T = sT; sv.Q = sQ; sv.U = sU;
-
-    double wpr = 0, wpi = 0, wmr = 0, wmi = 0; // W(+f_j), W(-f_j)
-    const double fj = active ? (p.g.fpos ? p.g.fpos[j] : rmul((double)j, p.g.val)) : 0.0;
+    // dynamic smem: accumulators [4][SUM_BPT][SUM_THREADS] | entry cache | T[L] | Q[L][16] | U[L][4]
+    double *acc = reinterpret_cast<double *>(smraw);
+    Entry *ent = reinterpret_cast<Entry *>(acc + 4 * SUM_BPT * SUM_THREADS);
+    double *sT = reinterpret_cast<double *>(ent + SUM_THREADS);
+    double *sQ = sT + L, *sU = sT + 17 * L;
+#define ACC(c, b) acc[((c) * SUM_BPT + (b)) * SUM_THREADS + tid]
+#pragma unroll
+    for (int i = 0; i < 4 * SUM_BPT; i++) acc[i * SUM_THREADS + tid] = 0.0;
 
     const int nrec = K * MAXBR;
     bool staged = false;
-    if (tid == 0) s_count = 0;
-    __syncthreads();
+    const double val = p.g.val;
+    const double *fpos = p.g.fpos;
 
-    for (int base = 0;; base += SUM_THREADS) {
-        const bool scanning = base < nrec;
-        if (scanning) {
-            // ordered compaction of the records overlapping this tile
-            const int r = base + tid;
-            bool pred = false;
-            if (r < nrec) {
-                const long long s0 = br[r].start, e0 = br[r].end;
-                pred = (e0 >= s0) && ((s0 <= pos_hi && e0 >= pos_lo) || (s0 <= neg_hi && e0 >= neg_lo));
-            }
-            const unsigned bal = __ballot_sync(0xffffffffu, pred);
-            if (lane == 0) s_wcount[wid] = __popc(bal);
-            __syncthreads();
-            int off = s_count;
-            for (int q = 0; q < wid; q++) off += s_wcount[q];
-            if (pred) s_list[off + __popc(bal & ((1u << lane) - 1))] = r;
-            __syncthreads();
-            if (tid == 0) { int tot = 0; for (int q = 0; q < SUM_THREADS / 32; q++) tot += s_wcount[q]; s_count += tot; }
-            __syncthreads();
+    for (int base = 0; base < nrec; base += SUM_THREADS) {
+        // ---- ordered compaction of this chunk's records that overlap the tile ------------------
+        const int r = base + tid;
+        bool pred = false;
+        if (r < nrec) {
+            const long long s0 = br[r].start, e0 = br[r].end;
+            pred = (e0 >= s0) && ((s0 <= pos_hi && e0 >= pos_lo) || (s0 <= neg_hi && e0 >= neg_lo));
         }
-        const int count = s_count;
-        const bool flush = (!scanning && count > 0) || (count + SUM_THREADS > LIST_CAP);
-        if (flush) {
-            if (!staged) {
-                // stage the shared tracks: knots, the four track quads, reduced knot phases
-                const double *t = p.t + wd.knot_off;
-                for (int i = tid; i < L; i += SUM_THREADS) sT[i] = t[i];
-                for (int i = tid; i < L * 4; i += SUM_THREADS) {
-                    const int jj = i >> 2, q = i & 3;
-                    const double4 c = *reinterpret_cast<const double4 *>(coeff + ((long long)jj * R + 2 * K + q) * 4);
-                    double *d = sQ + jj * 16 + q * 4;
-                    d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
-                    if (q >= 2) {
-                        // Phi/(2 pi) mod 1 as a double-double (hi, lo)
-                        const double ph = c.x;
-                        double a = ph * EMRIFD_INV2PI_HI;
-                        double e = fma(ph, EMRIFD_INV2PI_HI, -a);
-                        a -= rint(a);
-                        e = fma(ph, EMRIFD_INV2PI_LO, e);
-                        const double hi = a + e;
-                        const double lo = e - (hi - a);
-                        sU[jj * 4 + (q - 2) * 2 + 0] = hi;
-                        sU[jj * 4 + (q - 2) * 2 + 1] = lo;
+        const unsigned bal = __ballot_sync(0xffffffffu, pred);
+        if (lane == 0) s_wcount[wid] = __popc(bal);
+        __syncthreads();
+        int off = 0, count = 0;
+#pragma unroll
+        for (int q = 0; q < SUM_THREADS / 32; q++) { const int c = s_wcount[q]; if (q < wid) off += c; count += c; }
+        if (pred) s_list[off + __popc(bal & ((1u << lane) - 1))] = r;
+        if (count == 0) { __syncthreads(); continue; } // block-uniform
+        if (!staged) {
+            // stage the shared tracks once: knots, the four track quads, reduced knot phases
+            const double *t = p.t + wd.knot_off;
+            for (int i = tid; i < L; i += SUM_THREADS) sT[i] = t[i];
+            for (int i = tid; i < L * 4; i += SUM_THREADS) {
+                const int jj = i >> 2, q = i & 3;
+                const double4 c = *reinterpret_cast<const double4 *>(coeff + ((long long)jj * R + 2 * K + q) * 4);
+                double *d = sQ + jj * 16 + q * 4;
+                d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
+                if (q >= 2) { // Phi/(2 pi) mod 1 as a double-double (hi, lo)
+                    const double ph = c.x;
+                    double a = ph * EMRIFD_INV2PI_HI;
+                    double e = fma(ph, EMRIFD_INV2PI_HI, -a);
+                    a -= rint(a);
+                    e = fma(ph, EMRIFD_INV2PI_LO, e);
+                    const double hi = a + e;
+                    sU[jj * 4 + (q - 2) * 2 + 0] = hi;
+                    sU[jj * 4 + (q - 2) * 2 + 1] = e - (hi - a);
+                }
+            }
+            staged = true;
+        }
+        __syncthreads();
+        if (tid < count) { // fill the entry cache
+            const int rr = s_list[tid];
+            const emrifd_branch_t b = br[rr];
+            const int k = b.mode;
+            Entry e;
+            e.xa = b.xa; e.xb = b.xb; e.start = b.start; e.end = b.end;
+            e.mode = k; e.dir = b.dir; e.ja = b.ja; e.jb = b.jb;
+            e.m = marr[k]; e.n = narr[k];
+            e.mirror = (e.m > 0) && p.include_minus_m; e.pad = 0;
+            const double2 yp = ylm[k], ym = ylm[K + k];
+            e.ypr = yp.x; e.ypi = yp.y; e.ymr = ym.x; e.ymi = ym.y;
+            ent[tid] = e;
+        }
+        __syncthreads();
+
+        // ---- evaluate: every thread walks its SUM_BPT consecutive bins along each listed branch ----
+        if (nb > 0) {
+            for (int li = 0; li < count; li++) {
+                const Entry &E = ent[li];
+                const long long st = E.start, en = E.end;
+#pragma unroll 1
+                for (int side = 0; side < 2; side++) {
+                    int bl, bh;
+                    if (side == 0) { // +f bins: full-grid index zero + j
+                        const long long lo = st - (zero + j0), hi = en - (zero + j0);
+                        bl = lo > 0 ? (int)(lo < SUM_BPT ? lo : SUM_BPT) : 0;
+                        bh = hi < nb - 1 ? (int)(hi < -1 ? -1 : hi) : nb - 1;
+                    } else {         // -f bins: full-grid index zero - j  (j = 0 is handled on the + side)
+                        const long long lo = (zero - j0) - en, hi = (zero - j0) - st;
+                        bl = lo > 0 ? (int)(lo < SUM_BPT ? lo : SUM_BPT) : 0;
+                        if (j0 == 0 && bl == 0) bl = 1;
+                        bh = hi < nb - 1 ? (int)(hi < -1 ? -1 : hi) : nb - 1;
+                    }
+                    if (bl > bh) continue;
+                    const double sgn = side == 0 ? 1.0 : -1.0;
+                    const int k = E.mode, dir = E.dir, ja = E.ja, jb = E.jb;
+                    const double dm = (double)E.m, dn = (double)E.n, sdir = (double)dir;
+                    // per-segment state
+                    int j = -1;
+                    double segA = 0, segB = 0; // frequency at the time-start / time-end of the current sub-interval
+                    double tj = 0, hj = 0, xl0 = 0, xh0 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
+                    double4 qa = make_double4(0, 0, 0, 0), qb = qa;
+                    double xprev = 0, fprev = 0, rprev = 0;
+                    bool warm = false;
+                    for (int b = bl; b <= bh; b++) {
+                        const long long jj = j0 + b;
+                        const double f = sgn * (fpos ? fpos[jj] : rmul((double)jj, val));
+                        // ---- segment lookup: binary search on the first bin, short walk afterwards ----
+                        bool inside = (j >= 0) && (dir > 0 ? (f >= segA && f < segB) : (f <= segA && f > segB));
+                        if (!inside) {
+                            int lo = ja, hi = jb;
+                            if (j >= 0) { // walk from the previous segment
+                                lo = j;
+                                if (dir * sgn > 0) { while (lo < jb) { const double Fk = radd(rmul(dm, sQ[(lo + 1) * 16]), rmul(dn, sQ[(lo + 1) * 16 + 4])); if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo++; else break; } }
+                                else { while (lo > ja) { const double Fk = radd(rmul(dm, sQ[lo * 16]), rmul(dn, sQ[lo * 16 + 4])); if (dir > 0 ? (Fk > f) : (Fk < f)) lo--; else break; } }
+                            } else {
+                                while (lo < hi) {
+                                    const int mid = (lo + hi + 1) >> 1;
+                                    const double Fk = radd(rmul(dm, sQ[mid * 16]), rmul(dn, sQ[mid * 16 + 4]));
+                                    if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo = mid; else hi = mid - 1;
+                                }
+                            }
+                            j = lo;
+                            const double *q = sQ + j * 16;
+                            qa = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + k) * 4);
+                            qb = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + K + k) * 4);
+                            tj = sT[j]; hj = sT[j + 1] - tj;
+                            c0 = radd(rmul(dm, q[0]), rmul(dn, q[4]));
+                            c1 = fma(dm, q[1], dn * q[5]);
+                            c2 = fma(dm, q[2], dn * q[6]);
+                            c3 = fma(dm, q[3], dn * q[7]);
+                            xl0 = (j == ja) ? E.xa : 0.0;
+                            xh0 = (j == jb) ? E.xb : hj;
+                            // sub-interval frequency bounds for the cheap "still inside" test
+                            segA = (j == ja) ? fma(xl0, fma(xl0, fma(xl0, c3, c2), c1), c0) : c0;
+                            segB = (j == jb) ? fma(xh0, fma(xh0, fma(xh0, c3, c2), c1), c0)
+                                             : radd(rmul(dm, q[16]), rmul(dn, q[20]));
+                            warm = false;
+                        }
+                        const double delta = f - c0;
+                        // ---- root of x(c1 + x(c2 + x c3)) = delta: warm-started Newton, robust fallback ----
+                        double x;
+                        if (warm) x = fma(f - fprev, rprev, xprev);
+                        else {
+                            const double gl = xl0 * fma(xl0, fma(xl0, c3, c2), c1) - delta;
+                            const double gh = xh0 * fma(xh0, fma(xh0, c3, c2), c1) - delta;
+                            x = xl0 - gl * (xh0 - xl0) * fast_rcp(gh - gl);
+                        }
+                        const double tol = 1e-9 * hj;
+                        bool ok = false;
+                        double rr = 0.0;
+#pragma unroll 1
+                        for (int it = 0; it < 6; it++) {
+                            const double gx = x * fma(x, fma(x, c3, c2), c1) - delta;
+                            const double dg = fma(x, fma(3.0 * c3, x, 2.0 * c2), c1);
+                            rr = fast_rcp(dg);
+                            const double dx = gx * rr;
+                            x -= dx;
+                            if (fabs(dx) <= tol) { ok = true; break; }
+                        }
+                        const double slack = 1e-6 * hj;
+                        if (!(ok && x >= xl0 - slack && x <= xh0 + slack)) {
+                            x = solve_bracketed(c1, c2, c3, delta, xl0, xh0, sdir, hj);
+                            rr = fast_rcp(fma(x, fma(3.0 * c3, x, 2.0 * c2), c1));
+                        }
+                        xprev = x; fprev = f; rprev = rr; warm = true;
+                        // ---- amplitude, SPA factor, phase ----
+                        const double ReA = fma(x, fma(x, fma(x, qa.w, qa.z), qa.y), qa.x);
+                        const double ImA = fma(x, fma(x, fma(x, qb.w, qb.z), qb.y), qb.x);
+                        const double fdot = fma(x, fma(3.0 * c3, x, 2.0 * c2), c1);
+                        const double fddot = fma(6.0 * c3, x, 2.0 * c2);
+                        double Gre, Gim;
+                        spa_G2(fdot, fddot, Gre, Gim);
+                        const double *q = sQ + j * 16;
+                        const double pp = x * fma(x, fma(x, q[11], q[10]), q[9]);
+                        const double pr = x * fma(x, fma(x, q[15], q[14]), q[13]);
+                        double p0 = f * tj;
+                        const double e0 = fma(f, tj, -p0);
+                        p0 -= rint(p0);
+                        const double *u = sU + j * 4;
+                        double cyc = p0 - fma(dm, u[0], dn * u[2]);
+                        cyc -= rint(cyc);
+                        const double small = e0 - fma(dm, u[1], dn * u[3]);
+                        const double poly = fma(f, x, -EMRIFD_INV2PI_HI * fma(dm, pp, dn * pr));
+                        cyc += (poly - rint(poly)) + small;
+                        double sn, cs;
+                        sincospi(2.0 * cyc, &sn, &cs);
+                        const double agr = ReA * Gre - ImA * Gim, agi = ReA * Gim + ImA * Gre;
+                        const double Cr = agr * cs - agi * sn, Ci = agr * sn + agi * cs;
+                        // direct term lands on the bin of this side, the mirrored -m term on the other side
+                        const int cd = side * 2, cm = 2 - cd;
+                        ACC(cd, b) += E.ypr * Cr - E.ypi * Ci;
+                        ACC(cd + 1, b) += E.ypr * Ci + E.ypi * Cr;
+                        if (E.mirror) {
+                            ACC(cm, b) += E.ymr * Cr + E.ymi * Ci;
+                            ACC(cm + 1, b) += E.ymi * Cr - E.ymr * Ci;
+                        }
                     }
                 }
-                staged = true;
-                __syncthreads();
             }
-            for (int li = 0; li < count; li++) {
-                const int r = s_list[li];
-                const emrifd_branch_t b = br[r];
-                const int k = b.mode;
-                if (!active) continue;
-                const long long ip = zero + j, in_ = zero - j;
-                const bool hit_p = ip >= b.start && ip <= b.end;
-                const bool hit_n = (j > 0) && in_ >= b.start && in_ <= b.end;
-                if (!(hit_p || hit_n)) continue;
-                const int mi = marr[k], ni = narr[k];
-                const double dm = (double)mi, dn = (double)ni;
-                const bool mirror = (mi > 0) && p.include_minus_m;
-                const double2 yp = ylm[k], ym = ylm[K + k];
-                if (hit_p) {
-                    double Cr, Ci;
-                    eval_root(sv, coeff, R, K, k, dm, dn, b.dir, b.ja, b.jb, b.xa, b.xb, fj, Cr, Ci);
-                    wpr += yp.x * Cr - yp.y * Ci; wpi += yp.x * Ci + yp.y * Cr;
-                    if (mirror) { wmr += ym.x * Cr + ym.y * Ci; wmi += ym.y * Cr - ym.x * Ci; }
-                }
-                if (hit_n) {
-                    double Cr, Ci;
-                    eval_root(sv, coeff, R, K, k, dm, dn, b.dir, b.ja, b.jb, b.xa, b.xb, -fj, Cr, Ci);
-                    wmr += yp.x * Cr - yp.y * Ci; wmi += yp.x * Ci + yp.y * Cr;
-                    if (mirror) { wpr += ym.x * Cr + ym.y * Ci; wpi += ym.y * Cr - ym.x * Ci; }
-                }
-            }
-            __syncthreads();
-            if (tid == 0) s_count = 0;
-            __syncthreads();
         }
-        if (!scanning) break;
+        __syncthreads();
     }
 
-    // A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate
-    double hpr = 0, hpi = 0, hxr = 0, hxi = 0;
-    if (active) {
+    // ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
+    double a0 = 0, a1 = 0, a2 = 0;
+    for (int b = 0; b < nb; b++) {
+        const long long j = j0 + b;
+        double wpr = ACC(0, b), wpi = ACC(1, b), wmr = ACC(2, b), wmi = ACC(3, b);
         if (j == 0) { wpr += wmr; wpi += wmi; wmr = wpr; wmi = wpi; }
         const double pr_ = 0.5 * (-wmr - wpr), pi_ = 0.5 * (-wmi + wpi);
         const double xr_ = 0.5 * (wmi + wpi), xi_ = 0.5 * (-wmr + wpr);
         const double sc = wd.scale, c2 = wd.cos2psi, s2 = wd.sin2psi;
-        hpr = sc * (c2 * pr_ - s2 * xr_); hpi = sc * (c2 * pi_ - s2 * xi_);
-        hxr = sc * (s2 * pr_ + c2 * xr_); hxi = sc * (s2 * pi_ + c2 * xi_);
+        const double hpr = sc * (c2 * pr_ - s2 * xr_), hpi = sc * (c2 * pi_ - s2 * xi_);
+        const double hxr = sc * (s2 * pr_ + c2 * xr_), hxi = sc * (s2 * pi_ + c2 * xi_);
         if (WRITE_H) {
             if (p.mask_positive) {
                 const long long o = wd.out_off + (j - p.j_lo);
@@ -647,18 +748,18 @@ __global__ void __launch_bounds__(SUM_THREADS) mode_sum_kernel(SumParams p) {
                 }
             }
         }
-    }
-    if (LIKE) {
-        double a0 = 0, a1 = 0, a2 = 0;
-        if (active) {
+        if (LIKE) {
             const double2 d0 = p.dw[j], d1 = p.dw[p.n_data + j];
             const double w0 = p.wf[j], w1 = p.wf[p.n_data + j];
             const double h0r = hpr * w0, h0i = hpi * w0, h1r = hxr * w1, h1i = hxi * w1;
             const double r0 = d0.x - h0r, i0 = d0.y - h0i, r1 = d1.x - h1r, i1 = d1.y - h1i;
-            a0 = r0 * r0 + i0 * i0 + r1 * r1 + i1 * i1;
-            a1 = d0.x * h0r + d0.y * h0i + d1.x * h1r + d1.y * h1i;
-            a2 = h0r * h0r + h0i * h0i + h1r * h1r + h1i * h1i;
+            a0 += r0 * r0 + i0 * i0 + r1 * r1 + i1 * i1;
+            a1 += d0.x * h0r + d0.y * h0i + d1.x * h1r + d1.y * h1i;
+            a2 += h0r * h0r + h0i * h0i + h1r * h1r + h1i * h1i;
         }
+    }
+#undef ACC
+    if (LIKE) {
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             a0 += __shfl_down_sync(0xffffffffu, a0, o);
@@ -784,6 +885,10 @@ __global__ void __launch_bounds__(256) fma_bench_kernel(double *out, int iters, 
 // ==========================================================================================
 // host side
 // ==========================================================================================
+static size_t sum_smem_bytes(int L) {
+    return sizeof(double) * 4 * SUM_BPT * SUM_THREADS + sizeof(Entry) * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
+}
+
 static int ensure_bytes(emrifd_handle *h, void **ptr, int64_t *cap, int64_t need, bool pinned_host = false) {
     if (need <= *cap) return 0;
     int64_t ncap = need + need / 4 + 256;
@@ -863,7 +968,7 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaMemset(h->d_status, 0, sizeof(int));
     for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
     for (int i = 0; i < 64; i++) { cudaEventCreate(&h->ev_a[i]); cudaEventCreate(&h->ev_b[i]); }
-    const int big = SMEM_PER_KNOT * 8 * EMRIFD_MAX_KNOTS + 1024;
+    const int big = (int)sum_smem_bytes(EMRIFD_MAX_KNOTS);
     cudaFuncSetAttribute(mode_sum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -1003,7 +1108,7 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, const double *t,
         if (rc) return rc;
         p.partial = h->d_partial;
     }
-    const size_t smem = sizeof(double) * SMEM_PER_KNOT * (size_t)Lmax;
+    const size_t smem = sum_smem_bytes(Lmax);
     dim3 grid((unsigned)ntiles, (unsigned)B);
     int ev = -1;
     if (h->timing && h->ev_n < 64) { ev = h->ev_n++; cudaEventRecord(h->ev_a[ev], h->stream); }
