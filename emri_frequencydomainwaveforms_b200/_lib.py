@@ -6,7 +6,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "csrc", "libemrifd.so")
+LIB_PATH = os.environ.get("EMRIFD_LIB", os.path.join(_HERE, "csrc", "libemrifd.so"))
 
 MAX_BRANCHES = 4
 INCLUDE_MINUS_M = 1

@@ -23,8 +23,15 @@
 #include "k13_tables.h"
 
 #define MAXBR EMRIFD_MAX_BRANCHES
+#ifndef SUM_THREADS
 #define SUM_THREADS 256
+#endif
+#ifndef SUM_BPT
 #define SUM_BPT 4 /* consecutive bins per thread */
+#endif
+#ifndef SUM_MINB
+#define SUM_MINB 2 /* resident CTAs per SM the register allocation is tuned for */
+#endif
 #define SUM_TILE (SUM_THREADS * SUM_BPT)
 #define SPL_THREADS 128
 #define SEG_THREADS 128
@@ -50,6 +57,7 @@ struct emrifd_handle {
     char *d_ws; int64_t ws_cap;
     char *h_ws; int64_t h_ws_cap;
     int64_t launches;
+    int max_dyn_smem;
     // kernel timing
     int timing;
     cudaEvent_t ev_a[64], ev_b[64];
@@ -433,7 +441,42 @@ struct SumParams {
 
 
 // ---- fast reciprocal for Newton steps: 24-bit seed is enough (the iteration is self-correcting) ----
-__device__ __forceinline__ double fast_rcp(double d) { return (double)__frcp_rn((float)d); }
+// (MUFU.RCP64H, ~20 bits; the Newton iteration it feeds is self-correcting)
+__device__ __forceinline__ double fast_rcp(double d) {
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    return r;
+}
+// 1/sqrt(a): MUFU.RSQ64H seed + two Newton steps (full double accuracy for normal a > 0)
+__device__ __forceinline__ double fast_rsqrt(double a) {
+    double y;
+    asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
+    const double ha = 0.5 * a;
+    double e = fma(-ha * y, y, 0.5);
+    y = fma(y, e, y);
+    e = fma(-ha * y, y, 0.5);
+    return fma(y, e, y);
+}
+// sin and cos of 2*pi*c for |c| <~ 2^20: quarter-turn reduction (exact) + degree-15/16 polynomials in r = c - q/4
+__device__ __forceinline__ void sincos_cycles(double c, double &sn, double &cs) {
+    const double q = rint(4.0 * c);
+    const double r = fma(-0.25, q, c);
+    const int qi = (int)q;
+    const double r2 = r * r;
+    double ps = -0.7181223017785006, pc = 0.28200596845579123;
+    ps = fma(ps, r2, 3.819952584848282);   pc = fma(pc, r2, -1.714390711088672);
+    ps = fma(ps, r2, -15.09464257682299);  pc = fma(pc, r2, 7.903536371318469);
+    ps = fma(ps, r2, 42.058693944897655);  pc = fma(pc, r2, -26.4262567833744);
+    ps = fma(ps, r2, -76.70585975306139);  pc = fma(pc, r2, 60.24464137187666);
+    ps = fma(ps, r2, 81.60524927607506);   pc = fma(pc, r2, -85.45681720669373);
+    ps = fma(ps, r2, -41.34170224039976);  pc = fma(pc, r2, 64.9393940226683);
+    ps = fma(ps, r2, 6.283185307179586);   pc = fma(pc, r2, -19.739208802178716);
+    ps *= r;                               pc = fma(pc, r2, 1.0);
+    const bool swap = qi & 1;
+    const double a = swap ? pc : ps, b = swap ? ps : pc;
+    sn = (qi & 2) ? -a : a;
+    cs = ((qi + 1) & 2) ? -b : b;
+}
 
 // robust bracketed Newton (rare path: cold-start failures, turnover neighbourhood)
 __device__ __noinline__ double solve_bracketed(double c1, double c2, double c3, double delta, double xl, double xh,
@@ -460,7 +503,7 @@ __device__ __noinline__ double solve_bracketed(double c1, double c2, double c3, 
 //   s = 1/sqrt|fdot|,  u = 1/X = 3 fddot^2 s^6 / (2 pi)
 __device__ __forceinline__ void spa_G2(double fdot, double fddot, double &gre, double &gim) {
     const double af = fabs(fdot);
-    const double s = rsqrt(af);
+    const double s = fast_rsqrt(af);
     const double s2 = s * s;
     const double u = 0.477464829275686 * (fddot * fddot) * (s2 * s2 * s2); // 3/(2 pi)
     double re, im;
@@ -495,13 +538,14 @@ __device__ __forceinline__ void spa_G2(double fdot, double fddot, double &gre, d
 struct __align__(16) Entry {
     double xa, xb;
     double ypr, ypi, ymr, ymi;
-    long long start, end;
+    double dm, dn;
+    int spos, epos, sneg, eneg; // tile-local bin ranges covered on the +f / -f side (empty if s > e)
     int mode, dir, ja, jb;
-    int m, n, mirror, pad;
+    int jlo, jhi, mirror, pad;  // segment range the +f bins of this tile can fall in
 };
 
 template <bool WRITE_H, bool LIKE>
-__global__ void __launch_bounds__(SUM_THREADS, 2) mode_sum_kernel(SumParams p) {
+__global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int s_list[SUM_THREADS];
     __shared__ int s_wcount[SUM_THREADS / 32];
@@ -583,38 +627,61 @@ __global__ void __launch_bounds__(SUM_THREADS, 2) mode_sum_kernel(SumParams p) {
             const emrifd_branch_t b = br[rr];
             const int k = b.mode;
             Entry e;
-            e.xa = b.xa; e.xb = b.xb; e.start = b.start; e.end = b.end;
+            e.xa = b.xa; e.xb = b.xb;
             e.mode = k; e.dir = b.dir; e.ja = b.ja; e.jb = b.jb;
-            e.m = marr[k]; e.n = narr[k];
-            e.mirror = (e.m > 0) && p.include_minus_m; e.pad = 0;
+            const int mi = marr[k], ni = narr[k];
+            e.dm = (double)mi; e.dn = (double)ni;
+            e.mirror = (mi > 0) && p.include_minus_m; e.pad = 0;
             const double2 yp = ylm[k], ym = ylm[K + k];
             e.ypr = yp.x; e.ypi = yp.y; e.ymr = ym.x; e.ymi = ym.y;
+            // tile-local covered ranges: +f bins have full-grid index zero + jt0 + lb, -f bins zero - jt0 - lb
+            const long long ntile = jt1 - jt0 + 1;
+            long long lo = b.start - pos_lo, hi = b.end - pos_lo;
+            e.spos = (int)(lo < 0 ? 0 : (lo > ntile ? ntile : lo));
+            e.epos = (int)(hi > ntile - 1 ? ntile - 1 : (hi < -1 ? -1 : hi));
+            lo = neg_hi - b.end; hi = neg_hi - b.start;
+            e.sneg = (int)(lo < 0 ? 0 : (lo > ntile ? ntile : lo));
+            if (jt0 == 0 && e.sneg == 0) e.sneg = 1; // f = 0 is handled on the + side
+            e.eneg = (int)(hi > ntile - 1 ? ntile - 1 : (hi < -1 ? -1 : hi));
+            // segment hints for the + side: one binary search per tile edge here instead of one per thread
+            e.jlo = b.ja; e.jhi = b.jb;
+            if (e.spos <= e.epos) {
+                int jj2[2];
+#pragma unroll
+                for (int w = 0; w < 2; w++) {
+                    const long long jb_ = jt0 + (w == 0 ? e.spos : e.epos);
+                    const double f = fpos ? fpos[jb_] : rmul((double)(int)jb_, val);
+                    int l2 = b.ja, h2 = b.jb;
+                    while (l2 < h2) {
+                        const int mid = (l2 + h2 + 1) >> 1;
+                        const double Fk = radd(rmul(e.dm, sQ[mid * 16]), rmul(e.dn, sQ[mid * 16 + 4]));
+                        if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) l2 = mid; else h2 = mid - 1;
+                    }
+                    jj2[w] = l2;
+                }
+                e.jlo = jj2[0] < jj2[1] ? jj2[0] : jj2[1];
+                e.jhi = jj2[0] < jj2[1] ? jj2[1] : jj2[0];
+            }
             ent[tid] = e;
         }
         __syncthreads();
 
         // ---- evaluate: every thread walks its SUM_BPT consecutive bins along each listed branch ----
         if (nb > 0) {
+            const int tb0 = tid * SUM_BPT;
             for (int li = 0; li < count; li++) {
                 const Entry &E = ent[li];
-                const long long st = E.start, en = E.end;
 #pragma unroll 1
                 for (int side = 0; side < 2; side++) {
-                    int bl, bh;
-                    if (side == 0) { // +f bins: full-grid index zero + j
-                        const long long lo = st - (zero + j0), hi = en - (zero + j0);
-                        bl = lo > 0 ? (int)(lo < SUM_BPT ? lo : SUM_BPT) : 0;
-                        bh = hi < nb - 1 ? (int)(hi < -1 ? -1 : hi) : nb - 1;
-                    } else {         // -f bins: full-grid index zero - j  (j = 0 is handled on the + side)
-                        const long long lo = (zero - j0) - en, hi = (zero - j0) - st;
-                        bl = lo > 0 ? (int)(lo < SUM_BPT ? lo : SUM_BPT) : 0;
-                        if (j0 == 0 && bl == 0) bl = 1;
-                        bh = hi < nb - 1 ? (int)(hi < -1 ? -1 : hi) : nb - 1;
-                    }
+                    const int s_ = side == 0 ? E.spos : E.sneg, e_ = side == 0 ? E.epos : E.eneg;
+                    const int bl = s_ - tb0 > 0 ? s_ - tb0 : 0;
+                    const int bh = e_ - tb0 < nb - 1 ? e_ - tb0 : nb - 1;
                     if (bl > bh) continue;
                     const double sgn = side == 0 ? 1.0 : -1.0;
                     const int k = E.mode, dir = E.dir, ja = E.ja, jb = E.jb;
-                    const double dm = (double)E.m, dn = (double)E.n, sdir = (double)dir;
+                    const double dm = E.dm, dn = E.dn, sdir = (double)dir;
+                    double *accd = acc + side * 2 * SUM_BPT * SUM_THREADS + tid;       // direct term -> this side
+                    double *accm = acc + (1 - side) * 2 * SUM_BPT * SUM_THREADS + tid; // mirrored -m term -> other side
                     // per-segment state
                     int j = -1;
                     double segA = 0, segB = 0; // frequency at the time-start / time-end of the current sub-interval
@@ -624,11 +691,11 @@ __global__ void __launch_bounds__(SUM_THREADS, 2) mode_sum_kernel(SumParams p) {
                     bool warm = false;
                     for (int b = bl; b <= bh; b++) {
                         const long long jj = j0 + b;
-                        const double f = sgn * (fpos ? fpos[jj] : rmul((double)jj, val));
+                        const double f = sgn * (fpos ? fpos[jj] : rmul((double)(int)jj, val));
                         // ---- segment lookup: binary search on the first bin, short walk afterwards ----
                         bool inside = (j >= 0) && (dir > 0 ? (f >= segA && f < segB) : (f <= segA && f > segB));
                         if (!inside) {
-                            int lo = ja, hi = jb;
+                            int lo = side == 0 ? E.jlo : ja, hi = side == 0 ? E.jhi : jb;
                             if (j >= 0) { // walk from the previous segment
                                 lo = j;
                                 if (dir * sgn > 0) { while (lo < jb) { const double Fk = radd(rmul(dm, sQ[(lo + 1) * 16]), rmul(dn, sQ[(lo + 1) * 16 + 4])); if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo++; else break; } }
@@ -666,7 +733,7 @@ __global__ void __launch_bounds__(SUM_THREADS, 2) mode_sum_kernel(SumParams p) {
                             const double gh = xh0 * fma(xh0, fma(xh0, c3, c2), c1) - delta;
                             x = xl0 - gl * (xh0 - xl0) * fast_rcp(gh - gl);
                         }
-                        const double tol = 1e-9 * hj;
+                        const double tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
                         bool ok = false;
                         double rr = 0.0;
 #pragma unroll 1
@@ -678,7 +745,7 @@ __global__ void __launch_bounds__(SUM_THREADS, 2) mode_sum_kernel(SumParams p) {
                             x -= dx;
                             if (fabs(dx) <= tol) { ok = true; break; }
                         }
-                        const double slack = 1e-6 * hj;
+                        const double slack = 1e-5 * hj;
                         if (!(ok && x >= xl0 - slack && x <= xh0 + slack)) {
                             x = solve_bracketed(c1, c2, c3, delta, xl0, xh0, sdir, hj);
                             rr = fast_rcp(fma(x, fma(3.0 * c3, x, 2.0 * c2), c1));
@@ -704,16 +771,16 @@ __global__ void __launch_bounds__(SUM_THREADS, 2) mode_sum_kernel(SumParams p) {
                         const double poly = fma(f, x, -EMRIFD_INV2PI_HI * fma(dm, pp, dn * pr));
                         cyc += (poly - rint(poly)) + small;
                         double sn, cs;
-                        sincospi(2.0 * cyc, &sn, &cs);
+                        sincos_cycles(cyc, sn, cs);
                         const double agr = ReA * Gre - ImA * Gim, agi = ReA * Gim + ImA * Gre;
                         const double Cr = agr * cs - agi * sn, Ci = agr * sn + agi * cs;
                         // direct term lands on the bin of this side, the mirrored -m term on the other side
-                        const int cd = side * 2, cm = 2 - cd;
-                        ACC(cd, b) += E.ypr * Cr - E.ypi * Ci;
-                        ACC(cd + 1, b) += E.ypr * Ci + E.ypi * Cr;
+                        double *ad = accd + b * SUM_THREADS, *am = accm + b * SUM_THREADS;
+                        ad[0] += E.ypr * Cr - E.ypi * Ci;
+                        ad[SUM_BPT * SUM_THREADS] += E.ypr * Ci + E.ypi * Cr;
                         if (E.mirror) {
-                            ACC(cm, b) += E.ymr * Cr + E.ymi * Ci;
-                            ACC(cm + 1, b) += E.ymi * Cr - E.ymr * Ci;
+                            am[0] += E.ymr * Cr + E.ymi * Ci;
+                            am[SUM_BPT * SUM_THREADS] += E.ymi * Cr - E.ymr * Ci;
                         }
                     }
                 }
@@ -968,7 +1035,10 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaMemset(h->d_status, 0, sizeof(int));
     for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
     for (int i = 0; i < 64; i++) { cudaEventCreate(&h->ev_a[i]); cudaEventCreate(&h->ev_b[i]); }
-    const int big = (int)sum_smem_bytes(EMRIFD_MAX_KNOTS);
+    int optin = 0;
+    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    const int big = optin - 2048; // static smem of the kernel (< 2 KB) comes out of the same budget
+    h->max_dyn_smem = big;
     cudaFuncSetAttribute(mode_sum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -1109,6 +1179,7 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, const double *t,
         p.partial = h->d_partial;
     }
     const size_t smem = sum_smem_bytes(Lmax);
+    if ((int64_t)smem > h->max_dyn_smem) return set_err(h, EMRIFD_ERR_TOO_MANY_KNOTS, "trajectory too long for the shared-memory staging of the mode-sum kernel");
     dim3 grid((unsigned)ntiles, (unsigned)B);
     int ev = -1;
     if (h->timing && h->ev_n < 64) { ev = h->ev_n++; cudaEventRecord(h->ev_a[ev], h->stream); }
