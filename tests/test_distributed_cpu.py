@@ -1,0 +1,109 @@
+"""world_size-2 gloo tests of the multi-GPU host logic (walker sharding, bin sharding + all_reduce).
+The compute step is played by the CPU oracle (tests may use it); the GPU path plugs its kernels into
+the same helpers (distributed.gpu_bin_sharded_loglike, bench.py)."""
+import os
+import socket
+import sys
+
+import numpy as np
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _free_port():
+    s = socket.socket()
+    s.bind(("127.0.0.1", 0))
+    p = s.getsockname()[1]
+    s.close()
+    return p
+
+
+def _worker(rank, world, port, q):
+    sys.path.insert(0, ROOT)
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    os.environ["MASTER_ADDR"], os.environ["MASTER_PORT"] = "127.0.0.1", str(port)
+    os.environ["OMP_NUM_THREADS"] = "2"
+    import torch.distributed as dist
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    try:
+        from helpers import make_item, oracle_waveform
+        from oracle.oracle import Oracle
+        from emri_frequencydomainwaveforms_b200 import distributed as D
+        from emri_frequencydomainwaveforms_b200.waveform import FastSchwarzschildEccentricFlux
+        gen = FastSchwarzschildEccentricFlux(sum_kwargs=dict(pad_output=True, output_type="fd", odd_len=True))
+        orc = Oracle("f64")
+        it = make_item(gen, "plunge", dt=100.0)
+        N = it["N"]
+        n = (N + 1) // 2
+        hp, hc, coeff, br, nbr = oracle_waveform(orc, it)
+        rng = np.random.default_rng(0)
+        w = np.full((2, n), 2.0e19)
+        dw = (np.stack([hp[n - 1:], hc[n - 1:]]) + 1e-21 * (rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n)))) * w
+        full = orc.loglike(dw, np.stack([hp[n - 1:], hc[n - 1:]]), w)
+
+        # ---- frequency-bin sharding: slices balanced by work, all_reduce of the three sums ----
+        work = D.bin_work_histogram(br, it["m_arr"], N)
+        assert work.sum() == orc.last_n_eval            # the histogram counts every stationary point once
+        slices = D.balanced_bin_slices(work, world)
+        assert slices[0][0] == 0 and sum(c for _, c in slices) == n and slices[1][0] == slices[0][1]
+
+        def partial(j_lo, j_cnt):
+            a, b, *_ = oracle_waveform(orc, it, out_lo=n - 1 + j_lo, out_n=j_cnt)
+            return orc.loglike(dw[:, j_lo:j_lo + j_cnt], np.stack([a, b]), w[:, j_lo:j_lo + j_cnt])[None, :]
+
+        red = D.bin_sharded_sums(partial, slices).numpy()[0]
+        cost = [work[lo:lo + c].sum() for lo, c in slices]
+
+        # ---- walker sharding: 5 walkers over 2 ranks, gathered on every rank ----
+        params = np.arange(5, dtype=np.float64)[:, None] * 0.01
+
+        def ll_block(p):
+            out = []
+            for row in p:
+                it2 = dict(it, Phi_phi=it["Phi_phi"] + row[0])
+                a, b, *_ = oracle_waveform(orc, it2, out_lo=n - 1, out_n=n)
+                out.append(orc.loglike(dw, np.stack([a, b]), w)[0])
+            return np.asarray(out)
+
+        gathered = D.walker_sharded_loglike(params, ll_block)
+        ref = ll_block(params) if rank == 0 else None
+        q.put((rank, full, red, cost, gathered, ref))
+    finally:
+        dist.destroy_process_group()
+
+
+@pytest.mark.timeout(300)
+def test_walker_and_bin_sharding_gloo_world2():
+    import torch.multiprocessing as mp
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    res = sorted([q.get(timeout=240) for _ in procs], key=lambda x: x[0])
+    for p in procs:
+        p.join(timeout=60)
+        assert p.exitcode == 0
+    (_, full0, red0, cost0, g0, ref0), (_, full1, red1, cost1, g1, _) = res
+    assert np.array_equal(red0, red1)                                  # every rank holds the reduced sums
+    assert np.allclose(red0, full0, rtol=1e-12, atol=1e-12 * abs(full0[2]))
+    assert abs(cost0[0] - cost0[1]) <= 0.05 * (cost0[0] + cost0[1])    # work-balanced, not bin-balanced
+    assert np.array_equal(g0, g1) and g0.shape == (5,)
+    assert np.allclose(g0, ref0, rtol=1e-13)
+
+
+def test_shard_helpers():
+    from emri_frequencydomainwaveforms_b200 import distributed as D
+    for n in (0, 1, 5, 16, 1024):
+        for world in (1, 2, 4, 8):
+            blocks = [D.shard_range(n, world, r) for r in range(world)]
+            assert blocks[0][0] == 0 and blocks[-1][1] == n
+            assert all(blocks[r][1] == blocks[r + 1][0] for r in range(world - 1))
+            sizes = [b - a for a, b in blocks]
+            assert max(sizes) - min(sizes) <= 1
+    work = np.zeros(1000, dtype=np.int64)
+    work[100:200] = 50
+    sl = D.balanced_bin_slices(work, 4)
+    assert sum(c for _, c in sl) == 1000 and all(100 <= lo <= 200 for lo, _ in sl[1:])
