@@ -37,14 +37,17 @@ SURVEY_FLOPS_PER_MBE = 300.0
 # ---------------------------------------------------------------------------------------------
 # synthetic workload (host side, outside every timed region: the trajectory ODE stays on the host)
 # ---------------------------------------------------------------------------------------------
-def draw_walkers(n_distinct, n_total, seed, T=T_YR, dt=DT, eps=EPS):
+def draw_walkers(n_distinct, n_total, seed, T=T_YR, dt=DT, eps=EPS, workload="plunge"):
     from emri_frequencydomainwaveforms_b200.waveform import FastSchwarzschildEccentricFlux, viewing_angles
     from emri_frequencydomainwaveforms_b200.utils.utility import get_p_at_t
     gen = FastSchwarzschildEccentricFlux(sum_kwargs=dict(pad_output=True, output_type="fd", odd_len=True))
     rng = np.random.default_rng(seed)
     base = []
     tries = 0
-    while len(base) < n_distinct and tries < 50 * n_distinct:
+    if workload == "cfg1":   # BASELINE.json configs[0]: M=1e6, mu=10, p0=12, e0=0.35 (does not plunge within 1 yr: sparse support)
+        it = gen.prepare(1e6, 10.0, 12.0, 0.35, np.pi / 3, -np.pi / 2, dist=1.0, T=T, dt=dt, eps=eps)
+        base.append(it)
+    while len(base) < n_distinct and tries < 50 * n_distinct and workload != "cfg1":
         tries += 1
         M = np.exp(rng.uniform(np.log(1e5), np.log(1e7)))
         mu = M * np.exp(rng.uniform(np.log(1e-6), np.log(1e-4)))
@@ -183,6 +186,8 @@ def main():
     ap.add_argument("--distinct", type=int, default=8, help="distinct (M, mu, e0, p0) draws per GPU (phases vary per walker)")
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", default="plunge", choices=["plunge", "cfg1"],
+                    help="plunge: the headline batch of plunging draws (FP64-bound); cfg1: configs[0] system, sparse support (HBM-bound)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "b200" else 0)
     if args.impl == "reference":
@@ -210,7 +215,7 @@ def main():
     N = grid_len()
     n = (N + 1) // 2
     val = 1.0 / (N * DT)
-    items = draw_walkers(args.distinct, B, SEED + 1000 * rank)
+    items = draw_walkers(args.distinct, B, SEED + 1000 * rank, workload=args.workload)
     pb = engine.PackedBatch(items)
     db = engine.DeviceBatch(pb, h)
     pb.walkers["out_off"] = np.arange(B, dtype=np.int64) * n

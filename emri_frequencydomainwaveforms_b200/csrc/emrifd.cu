@@ -16,6 +16,7 @@
 #include <stdint.h>
 #include <stdio.h>
 #include <string.h>
+#include <stdlib.h>
 #include <math.h>
 #include <new>
 
@@ -33,6 +34,7 @@
 #define SUM_MINB 2 /* resident CTAs per SM the register allocation is tuned for */
 #endif
 #define SUM_TILE (SUM_THREADS * SUM_BPT)
+#define ACC_STRIDE (SUM_THREADS + 4) /* row stride of the smem accumulators: conflict-free own-slot and transposed access */
 #define SPL_THREADS 128
 #define SEG_THREADS 128
 #define SMEM_PER_KNOT 21 /* doubles: t, 16 track coefficients, 4 reduced knot phases */
@@ -573,12 +575,12 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
 
     // dynamic smem: accumulators [4][SUM_BPT][SUM_THREADS] | entry cache | T[L] | Q[L][16] | U[L][4]
     double *acc = reinterpret_cast<double *>(smraw);
-    Entry *ent = reinterpret_cast<Entry *>(acc + 4 * SUM_BPT * SUM_THREADS);
+    Entry *ent = reinterpret_cast<Entry *>(acc + 4 * SUM_BPT * ACC_STRIDE);
     double *sT = reinterpret_cast<double *>(ent + SUM_THREADS);
     double *sQ = sT + L, *sU = sT + 17 * L;
-#define ACC(c, b) acc[((c) * SUM_BPT + (b)) * SUM_THREADS + tid]
+#define ACC(c, b) acc[((c) * SUM_BPT + (b)) * ACC_STRIDE + tid]
 #pragma unroll
-    for (int i = 0; i < 4 * SUM_BPT; i++) acc[i * SUM_THREADS + tid] = 0.0;
+    for (int i = 0; i < 4 * SUM_BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
 
     const int nrec = K * MAXBR;
     bool staged = false;
@@ -682,8 +684,8 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                     const double sgn = side == 0 ? 1.0 : -1.0;
                     const int k = E.mode, dir = E.dir, ja = E.ja, jb = E.jb;
                     const double dm = E.dm, dn = E.dn, sdir = (double)dir;
-                    double *accd = acc + side * 2 * SUM_BPT * SUM_THREADS + tid;       // direct term -> this side
-                    double *accm = acc + (1 - side) * 2 * SUM_BPT * SUM_THREADS + tid; // mirrored -m term -> other side
+                    double *accd = acc + side * 2 * SUM_BPT * ACC_STRIDE + tid;       // direct term -> this side
+                    double *accm = acc + (1 - side) * 2 * SUM_BPT * ACC_STRIDE + tid; // mirrored -m term -> other side
                     // per-segment state
                     int j = -1;
                     double segA = 0, segB = 0; // frequency at the time-start / time-end of the current sub-interval
@@ -777,12 +779,12 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                         const double agr = ReA * Gre - ImA * Gim, agi = ReA * Gim + ImA * Gre;
                         const double Cr = agr * cs - agi * sn, Ci = agr * sn + agi * cs;
                         // direct term lands on the bin of this side, the mirrored -m term on the other side
-                        double *ad = accd + b * SUM_THREADS, *am = accm + b * SUM_THREADS;
+                        double *ad = accd + b * ACC_STRIDE, *am = accm + b * ACC_STRIDE;
                         ad[0] += E.ypr * Cr - E.ypi * Ci;
-                        ad[SUM_BPT * SUM_THREADS] += E.ypr * Ci + E.ypi * Cr;
+                        ad[SUM_BPT * ACC_STRIDE] += E.ypr * Ci + E.ypi * Cr;
                         if (E.mirror) {
                             am[0] += E.ymr * Cr + E.ymi * Ci;
-                            am[SUM_BPT * SUM_THREADS] += E.ymi * Cr - E.ymr * Ci;
+                            am[SUM_BPT * ACC_STRIDE] += E.ymi * Cr - E.ymr * Ci;
                         }
                     }
                 }
@@ -792,10 +794,18 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
     }
 
     // ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
+    // Transposed read-out: in iteration i thread t finalises tile-local bin i*SUM_THREADS + t, so a warp stores
+    // 32 consecutive bins (512 B per array, fully coalesced) and reads the data stream the same way.
     double a0 = 0, a1 = 0, a2 = 0;
-    for (int b = 0; b < nb; b++) {
-        const long long j = j0 + b;
-        double wpr = ACC(0, b), wpi = ACC(1, b), wmr = ACC(2, b), wmi = ACC(3, b);
+    const int ntile = (int)(jt1 - jt0 + 1);
+#pragma unroll 1
+    for (int i = 0; i < SUM_BPT; i++) {
+        const int lb = i * SUM_THREADS + tid;
+        if (lb >= ntile) break;
+        const long long j = jt0 + lb;
+        const int own = lb / SUM_BPT, bb = lb % SUM_BPT;
+        const double *ap = acc + bb * ACC_STRIDE + own;
+        double wpr = ap[0], wpi = ap[SUM_BPT * ACC_STRIDE], wmr = ap[2 * SUM_BPT * ACC_STRIDE], wmi = ap[3 * SUM_BPT * ACC_STRIDE];
         if (j == 0) { wpr += wmr; wpi += wmi; wmr = wpr; wmi = wpi; }
         const double pr_ = 0.5 * (-wmr - wpr), pi_ = 0.5 * (-wmi + wpi);
         const double xr_ = 0.5 * (wmi + wpi), xi_ = 0.5 * (-wmr + wpr);
@@ -955,7 +965,7 @@ __global__ void __launch_bounds__(256) fma_bench_kernel(double *out, int iters, 
 // host side
 // ==========================================================================================
 static size_t sum_smem_bytes(int L) {
-    return sizeof(double) * 4 * SUM_BPT * SUM_THREADS + sizeof(Entry) * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
+    return sizeof(double) * 4 * SUM_BPT * ACC_STRIDE + sizeof(Entry) * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
 
 static int ensure_bytes(emrifd_handle *h, void **ptr, int64_t *cap, int64_t need, bool pinned_host = false) {
