@@ -30,7 +30,11 @@ sys.path.insert(0, ROOT)
 
 SEED = 2601996          # check_mode_by_mode.py:47-48
 T_YR, DT, EPS = 1.0, 10.0, 1e-2
-FLOPS_PER_EVAL = 330.0  # FP64 flop per stationary-point evaluation of OUR kernel (DESIGN.md section 5 itemises it)
+# Algorithmic FP64 flop per stationary-point evaluation: SURVEY.md section 8(d)'s itemisation (cubic solve 60,
+# 4 Horner splines 24, fdot/fddot 20, arg + divisions 25, K_1/3 factor 70, phase + sincos 65, complex products 36).
+# One evaluation serves BOTH signs of m (the mirrored term is the conjugate), so we charge 300 per evaluation, not
+# per SURVEY "MBE" (mode, sign of m, bin); the MBE-convention figure is reported separately.
+FLOPS_PER_EVAL = 300.0
 SURVEY_FLOPS_PER_MBE = 300.0
 
 
@@ -168,9 +172,13 @@ def run_reference(args):
     print(json.dumps(line))
 
 
-def workload_config(batch):
-    return {"workload": "configs[4]/[1]: synthetic parameter draws (M 1e5-1e7, eta 1e-6-1e-4, e0 0.001-0.7, p0 set to plunge at 0.99 T), "
-                        "FD waveform on f>=0 + PSD-weighted likelihood, T=1 yr, dt=10 s, eps=1e-2, N=3155815",
+def workload_config(batch, workload="plunge"):
+    desc = ("configs[4]/[1]: synthetic parameter draws (M 1e5-1e7, eta 1e-6-1e-4, e0 0.001-0.7, p0 set to plunge at 0.99 T), "
+            "FD waveform on f>=0 + PSD-weighted likelihood, T=1 yr, dt=10 s, eps=1e-2, N=3155815")
+    if workload == "cfg1":
+        desc = ("configs[0] system (M=1e6, mu=10, p0=12, e0=0.35; no plunge within 1 yr, sparse support), walkers differ in initial phases, "
+                "FD waveform on f>=0 + PSD-weighted likelihood, T=1 yr, dt=10 s, eps=1e-2, N=3155815")
+    return {"workload": desc,
             "walkers_per_gpu_per_step": batch, "T_yr": T_YR, "dt_s": DT, "eps": EPS, "N": grid_len(),
             "l2": "per-step output (B x 50.5 MB) and inputs exceed the 126 MB L2; no explicit flush needed",
             "parallelism": "walker-sharded, no data-path collective"}
@@ -326,27 +334,39 @@ def main():
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
     alg_bytes = 80.0 * n * B       # 32 B/bin h+,hx written + 48 B/bin whitened data and noise factor read
     ach_gbs = alg_bytes / (k_avg_ms * 1e-3) / 1e9
-    ach_gflops = FLOPS_PER_EVAL * evals / (k_avg_ms * 1e-3) / 1e9
+    ach_tflops = FLOPS_PER_EVAL * evals / (k_avg_ms * 1e-3) / 1e12
+    fp64_peak = gfl.value / 1e3
     value = world * B * args.steps / (ms_dev * 1e-3)
     e2e_value = world * B * args.steps / (ms_e2e_wall * 1e-3)
+    # DRAM traffic of the dominant kernel from the committed ncu --set full capture (scaled by batch), else null
+    traffic = None
+    try:
+        tr = json.load(open(os.path.join(ROOT, "profiles", "traffic.json")))[args.workload]
+        traffic = tr["dram_bytes_per_launch"] * B / tr["batch"]
+    except Exception:
+        pass
+    roof_hbm = {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
+                "traffic": traffic, "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src}
+    roof_fp64 = {"bound": "fp64", "achieved": ach_tflops, "peak": fp64_peak, "unit": "TFLOP/s", "frac": ach_tflops / fp64_peak,
+                 "traffic": traffic, "flops_per_eval": FLOPS_PER_EVAL, "stationary_point_evals_per_launch": evals,
+                 "mbe_per_launch": mbe, "achieved_mbe_convention_300_per_mbe": SURVEY_FLOPS_PER_MBE * mbe / (k_avg_ms * 1e-3) / 1e12,
+                 "peak_source": "emrifd_bench_fp64_fma: CUDA-core DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
+                                "no tensor cores on this path)"}
+    binding, other = (roof_fp64, roof_hbm) if roof_fp64["frac"] >= roof_hbm["frac"] else (roof_hbm, roof_fp64)
+    common = {"kernel": "mode_sum_kernel<true,true>", "kernel_ms": k_avg_ms, "kernel_share_of_step": k_avg_ms / (ms_dev / args.steps)}
+    binding = dict(binding, **common)
 
     line = {
         "metric": "fd_waveform_likelihoods_per_s", "value": value, "unit": "walkers/s", "n_gpus": world, "steps": args.steps,
         "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
-        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(B),
+        "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": workload_config(B, args.workload),
         "e2e": {"value": e2e_value, "unit": "walkers/s", "h2d_bytes_per_step": pb.h2d_bytes(), "d2h_bytes_per_step": int(like_host.nbytes),
                 "ms_per_step": ms_e2e_wall / args.steps,
                 "call": "emrifd_loglike_batch_host (host packed sparse inputs -> H2D -> spline/segment/sum+likelihood -> D2H ll)"},
         "gpu_launches": int(launches),
         "clocks": clocks,
-        "roofline": {"bound": "hbm", "achieved": ach_gbs, "peak": hbm_peak, "unit": "GB/s", "frac": ach_gbs / hbm_peak,
-                     "traffic": None, "kernel": "mode_sum_kernel<true,true>", "kernel_ms": k_avg_ms,
-                     "kernel_share_of_step": k_avg_ms / (ms_dev / args.steps),
-                     "algorithmic_bytes_per_launch": alg_bytes, "peak_source": peak_src},
-        "roofline_fp64": {"achieved": ach_gflops, "peak": gfl.value, "unit": "GFLOP/s", "frac": ach_gflops / gfl.value,
-                          "flops_per_eval": FLOPS_PER_EVAL, "stationary_point_evals_per_launch": evals, "mbe_per_launch": mbe,
-                          "achieved_survey_300_per_mbe": SURVEY_FLOPS_PER_MBE * mbe / (k_avg_ms * 1e-3) / 1e9,
-                          "peak_source": "emrifd_bench_fp64_fma (DFMA micro-benchmark, measured in this run)"},
+        "roofline": binding,
+        "roofline_other_roof": other,
         "work": {"evals_per_walker": evals / B, "mbe_per_walker": mbe / B, "modes_per_walker": pb.n_modes / B,
                  "knots_per_walker": pb.n_knots / B},
     }

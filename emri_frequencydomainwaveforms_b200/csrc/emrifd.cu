@@ -35,7 +35,6 @@
 #endif
 #define SUM_TILE (SUM_THREADS * SUM_BPT)
 #define ACC_STRIDE (SUM_THREADS + 4) /* row stride of the smem accumulators: conflict-free own-slot and transposed access */
-#define SPL_THREADS 128
 #define SEG_THREADS 128
 #define SMEM_PER_KNOT 21 /* doubles: t, 16 track coefficients, 4 reduced knot phases */
 
@@ -103,8 +102,15 @@ struct SplineParams {
     int Lgen, Rgen;
 };
 
-template <bool GENERIC>
-__global__ void __launch_bounds__(SPL_THREADS) spline_build_kernel(SplineParams p, int *status) {
+// One CTA = 32 rows of one walker.  Warp 0: one row per lane; warp 1 lane 0 factorises the (shared) tridiagonal
+// matrix while warp 0 stages its rows into shared memory, so the serial pivot chain overlaps the loads.
+// TILED: y and the forward-sweep intermediates live in shared memory [L][32] (fits for L <~ 400); otherwise
+// y is re-read from global memory and the intermediates are parked in the c1 slot of the output.
+// Every operation is individually rounded in the oracle's order (oracle/emrifd_oracle.c orc_spline_build).
+#define SPL_ROWS 32
+#define SPL_CTA 64
+template <bool GENERIC, bool TILED>
+__global__ void __launch_bounds__(SPL_CTA) spline_build_kernel(SplineParams p, int *status) {
     extern __shared__ double sm[];
     int L, K, R;
     const double *t;
@@ -118,100 +124,111 @@ __global__ void __launch_bounds__(SPL_THREADS) spline_build_kernel(SplineParams 
         t = p.t + wd.knot_off; coeff = p.coeff + wd.coeff_off;
         teuk_off = wd.teuk_off; knot_off = wd.knot_off;
     }
-    if ((int)(blockIdx.x * SPL_THREADS) >= R) return;
-    double *sh = sm, *sw = sm + L, *sinv = sm + 2 * L, *scup = sm + 3 * L;
+    const int r0 = blockIdx.x * SPL_ROWS;
+    if (r0 >= R) return;
+    double *sh = sm, *srh = sm + L, *sw = sm + 2 * L, *sinv = sm + 3 * L, *scup = sm + 4 * L;
+    double *sy = sm + 5 * L, *sb = sy + (TILED ? L * SPL_ROWS : 0);
     __shared__ int bad;
-    if (threadIdx.x == 0) bad = 0;
+    const int tid = threadIdx.x, lr = tid & 31, r = r0 + lr;
+    if (tid == 0) bad = 0;
     __syncthreads();
-    for (int j = threadIdx.x; j < L - 1; j += SPL_THREADS) {
-        double hj = rsub(t[j + 1], t[j]);
+    for (int j = tid; j < L - 1; j += SPL_CTA) {
+        const double hj = rsub(t[j + 1], t[j]);
         sh[j] = hj;
+        srh[j] = rdiv(1.0, hj);
         if (!(hj > 0.0)) bad = 1;
     }
     __syncthreads();
     if (bad) {
-        if (threadIdx.x == 0) atomicMin(status, EMRIFD_ERR_KNOT_ORDER);
+        if (tid == 0) atomicMin(status, EMRIFD_ERR_KNOT_ORDER);
         return;
     }
     const double dd0 = rsub(t[2], t[0]), ddn = rsub(t[L - 1], t[L - 3]);
-    if (threadIdx.x == 0) {
-        // shared factorisation of the tridiagonal matrix (identical for every row of this walker)
+    // row source
+    const double *yb = nullptr;
+    long long ks = 1;
+    if (r < R) {
+        if (GENERIC) { yb = p.ygen + (long long)r * p.rs; ks = p.ks; }
+        else if (r < K)     { yb = p.teuk + 2 * (teuk_off + r); ks = 2 * K; }
+        else if (r < 2 * K) { yb = p.teuk + 2 * (teuk_off + (r - K)) + 1; ks = 2 * K; }
+        else {
+            const int q = r - 2 * K;
+            const double *b = q == 0 ? p.trk0 : q == 1 ? p.trk1 : q == 2 ? p.trk2 : p.trk3;
+            yb = b + knot_off; ks = 1;
+        }
+    }
+    if (tid == 32) {
+        // LU without pivoting: inv_0 = 1/d_0; w_i = a_i*inv_{i-1}; d'_i = d_i - w_i*c_{i-1}; inv_i = 1/d'_i
         double dprev = sh[1];
         scup[0] = dd0; sinv[0] = rdiv(1.0, dprev); sw[0] = 0.0;
+        double invp = sinv[0], cupp = dd0;
         for (int i = 1; i < L; i++) {
             double a, d, c;
             if (i < L - 1) { a = sh[i]; d = rmul(2.0, radd(sh[i - 1], sh[i])); c = sh[i - 1]; }
             else           { a = ddn;   d = sh[L - 3];                         c = 0.0; }
-            scup[i] = c;
-            double wi = rdiv(a, dprev);
-            sw[i] = wi;
-            dprev = rsub(d, rmul(wi, scup[i - 1]));
-            sinv[i] = rdiv(1.0, dprev);
+            const double wi = rmul(a, invp);
+            dprev = rsub(d, rmul(wi, cupp));
+            invp = rdiv(1.0, dprev);
+            scup[i] = c; sw[i] = wi; sinv[i] = invp;
+            cupp = c;
         }
+    } else if (TILED && tid < 32 && r < R) {
+        for (int j = 0; j < L; j++) sy[j * SPL_ROWS + lr] = yb[(long long)j * ks];
     }
     __syncthreads();
-    const int r = blockIdx.x * SPL_THREADS + threadIdx.x;
-    if (r >= R) return;
-    // row source
-    const double *yb;
-    long long ks;
-    if (GENERIC) { yb = p.ygen + (long long)r * p.rs; ks = p.ks; }
-    else if (r < K)     { yb = p.teuk + 2 * (teuk_off + r); ks = 2 * K; }
-    else if (r < 2 * K) { yb = p.teuk + 2 * (teuk_off + (r - K)) + 1; ks = 2 * K; }
-    else {
-        const int q = r - 2 * K;
-        const double *b = q == 0 ? p.trk0 : q == 1 ? p.trk1 : q == 2 ? p.trk2 : p.trk3;
-        yb = b + knot_off; ks = 1;
-    }
-#define Y(j) yb[(long long)(j) * ks]
+    if (tid >= 32 || r >= R) return;
+#define Y(j) (TILED ? sy[(j) * SPL_ROWS + lr] : yb[(long long)(j) * ks])
 #define CO(j, c) coeff[((long long)(j) * R + r) * 4 + (c)]
-    // forward sweep; intermediate b'_i parked in the c1 slot of the output
-    double sprev;
+#define BPW(i, v) do { if (TILED) sb[(i) * SPL_ROWS + lr] = (v); else CO(i, 1) = (v); } while (0)
+#define BPR(i) (TILED ? sb[(i) * SPL_ROWS + lr] : CO(i, 1))
+    // forward sweep
+    double sprev, dm, dp;
     {
-        double y0 = Y(0), y1 = Y(1), y2 = Y(2);
-        double d0 = rdiv(rsub(y1, y0), sh[0]), d1 = rdiv(rsub(y2, y1), sh[1]);
-        double num = radd(rmul(rmul(radd(sh[0], rmul(2.0, dd0)), sh[1]), d0), rmul(rmul(sh[0], sh[0]), d1));
+        const double y0 = Y(0), y1 = Y(1), y2 = Y(2);
+        dm = rmul(rsub(y1, y0), srh[0]);
+        dp = rmul(rsub(y2, y1), srh[1]);
+        const double num = radd(rmul(rmul(radd(sh[0], rmul(2.0, dd0)), sh[1]), dm), rmul(rmul(sh[0], sh[0]), dp));
         sprev = rdiv(num, dd0);
-        CO(0, 1) = sprev;
+        BPW(0, sprev);
     }
     {
-        double ym = Y(0), yc = Y(1);
+        double yc = Y(1);
         for (int i = 1; i < L - 1; i++) {
-            double yp = Y(i + 1);
-            double dm = rdiv(rsub(yc, ym), sh[i - 1]), dp = rdiv(rsub(yp, yc), sh[i]);
-            double b = rmul(3.0, radd(rmul(sh[i], dm), rmul(sh[i - 1], dp)));
+            const double yp = Y(i + 1);
+            dp = rmul(rsub(yp, yc), srh[i]);
+            const double b = rmul(3.0, radd(rmul(sh[i], dm), rmul(sh[i - 1], dp)));
             sprev = rsub(b, rmul(sw[i], sprev));
-            CO(i, 1) = sprev;
-            ym = yc; yc = yp;
+            BPW(i, sprev);
+            if (i < L - 2) dm = dp;
+            yc = yp;
         }
     }
     {
-        double ya = Y(L - 3), yb2 = Y(L - 2), yc = Y(L - 1);
-        double dm = rdiv(rsub(yb2, ya), sh[L - 3]), dp = rdiv(rsub(yc, yb2), sh[L - 2]);
-        double hl2 = sh[L - 2], hl3 = sh[L - 3];
-        double num = radd(rmul(rmul(hl2, hl2), dm), rmul(rmul(radd(rmul(2.0, ddn), hl2), hl3), dp));
-        double b = rdiv(num, ddn);
+        const double hl2 = sh[L - 2], hl3 = sh[L - 3];
+        const double num = radd(rmul(rmul(hl2, hl2), dm), rmul(rmul(radd(rmul(2.0, ddn), hl2), hl3), dp));
+        const double b = rdiv(num, ddn);
         sprev = rsub(b, rmul(sw[L - 1], sprev));
     }
     // back substitution + coefficients
     double snext = rmul(sprev, sinv[L - 1]);
     double ynext = Y(L - 1);
-    CO(L - 1, 0) = ynext; CO(L - 1, 1) = snext; CO(L - 1, 2) = 0.0; CO(L - 1, 3) = 0.0;
+    *reinterpret_cast<double4 *>(&CO(L - 1, 0)) = make_double4(ynext, snext, 0.0, 0.0);
     for (int i = L - 2; i >= 0; i--) {
-        double bi = CO(i, 1);
-        double si = rmul(rsub(bi, rmul(scup[i], snext)), sinv[i]);
-        double yi = Y(i);
-        double hi = sh[i];
-        double dl = rdiv(rsub(ynext, yi), hi);
-        double tau = rdiv(rsub(radd(si, snext), rmul(2.0, dl)), hi);
-        double c2 = rsub(rdiv(rsub(dl, si), hi), tau);
-        double c3 = rdiv(tau, hi);
-        double4 q = make_double4(yi, si, c2, c3);
-        *reinterpret_cast<double4 *>(&CO(i, 0)) = q;
+        const double bi = BPR(i);
+        const double si = rmul(rsub(bi, rmul(scup[i], snext)), sinv[i]);
+        const double yi = Y(i);
+        const double rhi = srh[i];
+        const double dl = rmul(rsub(ynext, yi), rhi);
+        const double tau = rmul(rsub(radd(si, snext), rmul(2.0, dl)), rhi);
+        const double c2 = rsub(rmul(rsub(dl, si), rhi), tau);
+        const double c3 = rmul(tau, rhi);
+        *reinterpret_cast<double4 *>(&CO(i, 0)) = make_double4(yi, si, c2, c3);
         snext = si; ynext = yi;
     }
 #undef Y
 #undef CO
+#undef BPW
+#undef BPR
 }
 
 __global__ void spline_eval_kernel(const double *__restrict__ t, const double *__restrict__ coeff, int L, int R,
@@ -278,12 +295,23 @@ __device__ __forceinline__ void push_sub(emrifd_branch_t *br, int &nb, int &over
 }
 
 __global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *status) {
+    extern __shared__ double sm[]; // t[L] | (f_phi quad, f_r quad)[L][8]: staged once, the per-mode loop reads smem only
     const emrifd_walker_t wd = p.w[blockIdx.y];
-    const int k = blockIdx.x * SEG_THREADS + threadIdx.x;
     const int L = wd.L, K = wd.K, R = 2 * K + 4;
-    if (k >= K) return;
+    if ((int)(blockIdx.x * SEG_THREADS) >= K) return;
     const double *t = p.t + wd.knot_off;
     const double *coeff = p.coeff + wd.coeff_off;
+    double *st = sm, *sq = sm + L;
+    for (int i = threadIdx.x; i < L; i += SEG_THREADS) st[i] = t[i];
+    for (int i = threadIdx.x; i < 2 * L; i += SEG_THREADS) {
+        const int jj = i >> 1, q = i & 1;
+        const double4 c = *reinterpret_cast<const double4 *>(coeff + ((long long)jj * R + 2 * K + q) * 4);
+        double *d = sq + jj * 8 + q * 4;
+        d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
+    }
+    __syncthreads();
+    const int k = blockIdx.x * SEG_THREADS + threadIdx.x;
+    if (k >= K) return;
     const int mi = p.m[wd.mode_off + k], ni = p.n[wd.mode_off + k];
     const double dm = (double)mi, dn = (double)ni;
     emrifd_branch_t *out = p.br + (wd.mode_off + k) * MAXBR;
@@ -293,17 +321,14 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *
         br[q].start = 0; br[q].end = -1; br[q].xa = 0; br[q].xb = 0; br[q].Fa = 0; br[q].Fb = 0;
     }
     int nb = 0, overflow = 0;
-    double4 cp = *reinterpret_cast<const double4 *>(coeff + ((long long)0 * R + 2 * K) * 4);
-    double4 cr = *reinterpret_cast<const double4 *>(coeff + ((long long)0 * R + 2 * K + 1) * 4);
     for (int j = 0; j < L - 1; j++) {
-        const double4 cp1 = *reinterpret_cast<const double4 *>(coeff + ((long long)(j + 1) * R + 2 * K) * 4);
-        const double4 cr1 = *reinterpret_cast<const double4 *>(coeff + ((long long)(j + 1) * R + 2 * K + 1) * 4);
-        const double hj = rsub(t[j + 1], t[j]);
-        const double c0 = radd(rmul(dm, cp.x), rmul(dn, cr.x));
-        const double c1 = radd(rmul(dm, cp.y), rmul(dn, cr.y));
-        const double c2 = radd(rmul(dm, cp.z), rmul(dn, cr.z));
-        const double c3 = radd(rmul(dm, cp.w), rmul(dn, cr.w));
-        const double Fnext = radd(rmul(dm, cp1.x), rmul(dn, cr1.x));
+        const double *c = sq + j * 8;
+        const double hj = rsub(st[j + 1], st[j]);
+        const double c0 = radd(rmul(dm, c[0]), rmul(dn, c[4]));
+        const double c1 = radd(rmul(dm, c[1]), rmul(dn, c[5]));
+        const double c2 = radd(rmul(dm, c[2]), rmul(dn, c[6]));
+        const double c3 = radd(rmul(dm, c[3]), rmul(dn, c[7]));
+        const double Fnext = radd(rmul(dm, c[8]), rmul(dn, c[12]));
         double xr[2];
         int nr = 0;
         const double qa = rmul(3.0, c3), qb = rmul(2.0, c2), qc = c1;
@@ -329,7 +354,6 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *
             xa = x; Fa = Fx;
         }
         push_sub(br, nb, overflow, k, j, xa, Fa, hj, Fnext);
-        cp = cp1; cr = cr1;
     }
     if (nb > 0) br[nb - 1].closed_end = 1;
     long long evals = 0;
@@ -964,6 +988,10 @@ __global__ void __launch_bounds__(256) fma_bench_kernel(double *out, int iters, 
 // ==========================================================================================
 // host side
 // ==========================================================================================
+static size_t spline_smem_bytes(int L, bool tiled) {
+    return sizeof(double) * (size_t)L * (5 + (tiled ? 2 * SPL_ROWS : 0));
+}
+
 static size_t sum_smem_bytes(int L) {
     return sizeof(double) * 4 * SUM_BPT * ACC_STRIDE + sizeof(Entry) * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
@@ -1051,6 +1079,11 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const int big = optin - 2048; // static smem of the kernel (< 2 KB) comes out of the same budget
     h->max_dyn_smem = big;
+    cudaFuncSetAttribute(spline_build_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(spline_build_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(spline_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(spline_build_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 8 * EMRIFD_MAX_KNOTS);
     cudaFuncSetAttribute(mode_sum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -1088,15 +1121,14 @@ int emrifd_spline_build(emrifd_handle_t *h, const double *t, const double *y, in
                         int64_t row_stride, int64_t knot_stride, double *coeff) {
     if (!h || !t || !y || !coeff || R <= 0) return set_err(h, EMRIFD_ERR_INVALID, "spline_build: bad argument");
     if (L < 4) return set_err(h, EMRIFD_ERR_TOO_FEW_KNOTS, "not-a-knot spline needs at least 4 knots");
-    if (L > 6000) return set_err(h, EMRIFD_ERR_TOO_MANY_KNOTS, "spline_build: more than 6000 knots");
     cudaSetDevice(h->device);
     SplineParams p; memset(&p, 0, sizeof(p));
     p.t = t; p.coeff = coeff; p.ygen = y; p.rs = row_stride; p.ks = knot_stride; p.Lgen = (int)L; p.Rgen = (int)R;
-    const size_t smem = sizeof(double) * 4 * (size_t)L;
-    if (smem > 48 * 1024)
-        CUDA_TRY(h, cudaFuncSetAttribute(spline_build_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    dim3 grid((unsigned)((R + SPL_THREADS - 1) / SPL_THREADS), 1);
-    spline_build_kernel<true><<<grid, SPL_THREADS, smem, h->stream>>>(p, h->d_status);
+    dim3 grid((unsigned)((R + SPL_ROWS - 1) / SPL_ROWS), 1);
+    const size_t tiled = spline_smem_bytes((int)L, true), plain = spline_smem_bytes((int)L, false);
+    if ((int64_t)tiled <= h->max_dyn_smem) spline_build_kernel<true, true><<<grid, SPL_CTA, tiled, h->stream>>>(p, h->d_status);
+    else if ((int64_t)plain <= h->max_dyn_smem) spline_build_kernel<true, false><<<grid, SPL_CTA, plain, h->stream>>>(p, h->d_status);
+    else return set_err(h, EMRIFD_ERR_TOO_MANY_KNOTS, "spline_build: too many knots for the shared-memory factorisation");
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -1119,8 +1151,10 @@ static int batch_spline_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, con
     SplineParams p; memset(&p, 0, sizeof(p));
     p.w = h->d_walkers; p.t = t; p.teuk = teuk; p.trk0 = f_phi; p.trk1 = f_r; p.trk2 = Phi_phi; p.trk3 = Phi_r; p.coeff = coeff;
     const int R = 2 * Kmax + 4;
-    dim3 grid((unsigned)((R + SPL_THREADS - 1) / SPL_THREADS), (unsigned)B);
-    spline_build_kernel<false><<<grid, SPL_THREADS, sizeof(double) * 4 * (size_t)Lmax, h->stream>>>(p, h->d_status);
+    dim3 grid((unsigned)((R + SPL_ROWS - 1) / SPL_ROWS), (unsigned)B);
+    const size_t tiled = spline_smem_bytes(Lmax, true), plain = spline_smem_bytes(Lmax, false);
+    if ((int64_t)tiled <= h->max_dyn_smem) spline_build_kernel<false, true><<<grid, SPL_CTA, tiled, h->stream>>>(p, h->d_status);
+    else spline_build_kernel<false, false><<<grid, SPL_CTA, plain, h->stream>>>(p, h->d_status);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -1137,7 +1171,7 @@ int emrifd_batch_spline(emrifd_handle_t *h, const emrifd_walker_t *walkers, int6
     return batch_spline_dev(h, B, Lmax, Kmax, t, teuk, f_phi, f_r, Phi_phi, Phi_r, coeff);
 }
 
-static int batch_segment_dev(emrifd_handle *h, int64_t B, int Kmax, const double *t, const double *coeff,
+static int batch_segment_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const double *t, const double *coeff,
                              const int32_t *m_arr, const int32_t *n_arr, int64_t N, double val, const double *fpos,
                              emrifd_branch_t *branches, int64_t *n_eval) {
     SegParams p;
@@ -1146,7 +1180,7 @@ static int batch_segment_dev(emrifd_handle *h, int64_t B, int Kmax, const double
     p.g.N = N; p.g.zero = (N - 1) / 2; p.g.val = val; p.g.fpos = fpos;
     if (n_eval) CUDA_TRY(h, cudaMemsetAsync(n_eval, 0, sizeof(int64_t) * 2 * (size_t)B, h->stream));
     dim3 grid((unsigned)((Kmax + SEG_THREADS - 1) / SEG_THREADS), (unsigned)B);
-    segment_kernel<<<grid, SEG_THREADS, 0, h->stream>>>(p, h->d_status);
+    segment_kernel<<<grid, SEG_THREADS, sizeof(double) * 9 * (size_t)Lmax, h->stream>>>(p, h->d_status);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -1161,7 +1195,7 @@ int emrifd_batch_segment(emrifd_handle_t *h, const emrifd_walker_t *walkers, int
     if ((rc = check_grid(h, N, val, fpos))) return rc;
     cudaSetDevice(h->device);
     if ((rc = upload_walkers(h, walkers, B))) return rc;
-    return batch_segment_dev(h, B, Kmax, t, coeff, m_arr, n_arr, N, val, fpos, branches, n_eval);
+    return batch_segment_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, N, val, fpos, branches, n_eval);
 }
 
 static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, const double *t, const double *coeff,
@@ -1237,7 +1271,7 @@ int emrifd_fd_waveform_batch(emrifd_handle_t *h, const emrifd_walker_t *walkers,
     cudaSetDevice(h->device);
     if ((rc = upload_walkers(h, walkers, B))) return rc;
     if ((rc = batch_spline_dev(h, B, Lmax, Kmax, t, teuk, f_phi, f_r, Phi_phi, Phi_r, coeff))) return rc;
-    if ((rc = batch_segment_dev(h, B, Kmax, t, coeff, m_arr, n_arr, N, val, fpos, branches, nullptr))) return rc;
+    if ((rc = batch_segment_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, N, val, fpos, branches, nullptr))) return rc;
     return batch_sum_dev(h, B, Lmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, 0, (N + 1) / 2, hp, hc, like_out);
 }
 
@@ -1340,7 +1374,7 @@ int emrifd_loglike_batch_host(emrifd_handle_t *h, const emrifd_walker_t *walkers
     double *dout = (double *)(d + o_out);
     if ((rc = batch_spline_dev(h, B, Lmax, Kmax, (double *)(d + o_t), (double *)(d + o_te), (double *)(d + o_fp), (double *)(d + o_fr),
                                (double *)(d + o_pp), (double *)(d + o_pr), coeff))) return rc;
-    if ((rc = batch_segment_dev(h, B, Kmax, (double *)(d + o_t), coeff, (int32_t *)(d + o_m), (int32_t *)(d + o_n), N, val, fpos_dev, br, nullptr))) return rc;
+    if ((rc = batch_segment_dev(h, B, Lmax, Kmax, (double *)(d + o_t), coeff, (int32_t *)(d + o_m), (int32_t *)(d + o_n), N, val, fpos_dev, br, nullptr))) return rc;
     if ((rc = batch_sum_dev(h, B, Lmax, (double *)(d + o_t), coeff, (int32_t *)(d + o_m), (int32_t *)(d + o_n), (double *)(d + o_y), br,
                             N, val, fpos_dev, flags | EMRIFD_MASK_POSITIVE, 0, (N + 1) / 2, hp_dev, hc_dev, dout))) return rc;
     double *hres = (double *)(hs + in_bytes);

@@ -92,15 +92,20 @@ int orc_num_threads(void) {
 /* y is [R][L] row-major; coeff out is [L][R][4] = (y, c1, c2, c3)      */
 /* ------------------------------------------------------------------ */
 int orc_spline_build(const double *t, const double *y, int L, int R, double *coeff) {
+    /* Frozen operation order (the CUDA kernel reproduces it bit for bit):
+         rh_j = 1/h_j;  delta_j = (y_{j+1}-y_j)*rh_j;
+         LU without pivoting: inv_0 = 1/d_0;  w_i = a_i*inv_{i-1};  d'_i = d_i - w_i*c_{i-1};  inv_i = 1/d'_i;
+         forward  b'_i = b_i - w_i*b'_{i-1};  back  s_i = (b'_i - c_i*s_{i+1})*inv_i;
+         tau = (s_i + s_{i+1} - 2 delta_i)*rh_i;  c2 = (delta_i - s_i)*rh_i - tau;  c3 = tau*rh_i. */
     if (L < 4) return -2;
-    double *h = (double *)malloc(sizeof(double) * L * 4);
-    double *w = h + L, *inv = w + L, *cup = inv + L;
+    double *h = (double *)malloc(sizeof(double) * L * 5);
+    double *w = h + L, *inv = w + L, *cup = inv + L, *rh = cup + L;
     for (int j = 0; j < L - 1; j++) {
         h[j] = t[j + 1] - t[j];
         if (!(h[j] > 0.0)) { free(h); return -3; }
+        rh[j] = 1.0 / h[j];
     }
     const double dd0 = t[2] - t[0], ddn = t[L - 1] - t[L - 3];
-    /* tridiagonal rows: sub a_i, diag d_i, super c_i */
     double dprev = h[1]; /* d_0 */
     cup[0] = dd0;
     inv[0] = 1.0 / dprev;
@@ -109,7 +114,7 @@ int orc_spline_build(const double *t, const double *y, int L, int R, double *coe
         double a, d;
         if (i < L - 1) { a = h[i]; d = 2.0 * (h[i - 1] + h[i]); cup[i] = h[i - 1]; }
         else           { a = ddn;  d = h[L - 3];                 cup[i] = 0.0; }
-        w[i] = a / dprev;
+        w[i] = a * inv[i - 1];
         dprev = d - w[i] * cup[i - 1];
         inv[i] = 1.0 / dprev;
     }
@@ -117,32 +122,28 @@ int orc_spline_build(const double *t, const double *y, int L, int R, double *coe
     for (int r = 0; r < R; r++) {
         const double *yr = y + (size_t)r * L;
         double *s = (double *)malloc(sizeof(double) * L);
-        /* forward sweep */
-        {
-            double d0 = (yr[1] - yr[0]) / h[0], d1 = (yr[2] - yr[1]) / h[1];
-            s[0] = ((h[0] + 2.0 * dd0) * h[1] * d0 + h[0] * h[0] * d1) / dd0;
-        }
+        double dm = (yr[1] - yr[0]) * rh[0], dp = (yr[2] - yr[1]) * rh[1];
+        s[0] = ((h[0] + 2.0 * dd0) * h[1] * dm + h[0] * h[0] * dp) / dd0;
         for (int i = 1; i < L - 1; i++) {
-            double dm = (yr[i] - yr[i - 1]) / h[i - 1], dp = (yr[i + 1] - yr[i]) / h[i];
+            dp = (yr[i + 1] - yr[i]) * rh[i];
             double b = 3.0 * (h[i] * dm + h[i - 1] * dp);
             s[i] = b - w[i] * s[i - 1];
+            if (i < L - 2) dm = dp; /* at the end: dm = delta_{L-3}, dp = delta_{L-2} */
         }
         {
-            double dm = (yr[L - 2] - yr[L - 3]) / h[L - 3], dp = (yr[L - 1] - yr[L - 2]) / h[L - 2];
             double b = (h[L - 2] * h[L - 2] * dm + (2.0 * ddn + h[L - 2]) * h[L - 3] * dp) / ddn;
             s[L - 1] = b - w[L - 1] * s[L - 2];
         }
-        /* back substitution */
         s[L - 1] = s[L - 1] * inv[L - 1];
         for (int i = L - 2; i >= 0; i--) s[i] = (s[i] - cup[i] * s[i + 1]) * inv[i];
         for (int i = 0; i < L - 1; i++) {
-            double dl = (yr[i + 1] - yr[i]) / h[i];
-            double tau = (s[i] + s[i + 1] - 2.0 * dl) / h[i];
+            double dl = (yr[i + 1] - yr[i]) * rh[i];
+            double tau = (s[i] + s[i + 1] - 2.0 * dl) * rh[i];
             double *c = coeff + ((size_t)i * R + r) * 4;
             c[0] = yr[i];
             c[1] = s[i];
-            c[2] = (dl - s[i]) / h[i] - tau;
-            c[3] = tau / h[i];
+            c[2] = (dl - s[i]) * rh[i] - tau;
+            c[3] = tau * rh[i];
         }
         double *c = coeff + ((size_t)(L - 1) * R + r) * 4;
         c[0] = yr[L - 1]; c[1] = s[L - 1]; c[2] = 0.0; c[3] = 0.0;
