@@ -33,14 +33,14 @@ def bin_work_histogram(branches, m_arr, N):
     diff = np.zeros(npos + 1, dtype=np.int64)
     b = branches.reshape(-1)
     ok = b["end"] >= b["start"]
-    for s, e in zip(b["start"][ok], b["end"][ok]):
-        s, e = max(int(s), 0), min(int(e), N - 1)
-        if e >= zero:                      # +f part: j in [max(s,zero)-zero, e-zero]
-            diff[max(s, zero) - zero] += 1
-            diff[e - zero + 1] -= 1
-        if s < zero:                       # -f part: j in [zero-min(e,zero-1), zero-s]
-            diff[zero - min(e, zero - 1)] += 1
-            diff[zero - s + 1] -= 1
+    s = np.maximum(b["start"][ok], 0)
+    e = np.minimum(b["end"][ok], N - 1)
+    pos = e >= zero                        # +f part: j in [max(s, zero) - zero, e - zero]
+    np.add.at(diff, np.maximum(s[pos], zero) - zero, 1)
+    np.add.at(diff, e[pos] - zero + 1, -1)
+    neg = s < zero                         # -f part: j in [zero - min(e, zero - 1), zero - s]
+    np.add.at(diff, zero - np.minimum(e[neg], zero - 1), 1)
+    np.add.at(diff, zero - s[neg] + 1, -1)
     return np.cumsum(diff[:-1])
 
 
@@ -101,8 +101,10 @@ def bin_sharded_sums(compute_partial, slices, group=None, device="cpu"):
 
 
 # ---- GPU conveniences ---------------------------------------------------------------------------
-def gpu_bin_sharded_loglike(db, N, val=0.0, fpos_dev=None, include_minus_m=True, group=None):
-    """Frequency-bin sharded likelihood of a DeviceBatch replicated on every rank (NCCL all_reduce of [B,3])."""
+def gpu_bin_sharded_loglike(db, N, val=0.0, fpos_dev=None, include_minus_m=True, group=None, slices=None):
+    """Frequency-bin sharded likelihood of a DeviceBatch replicated on every rank (NCCL all_reduce of [B,3]).
+    ``slices``: reuse a previous work-balanced partition (e.g. across MCMC steps, where the work distribution
+    barely moves) instead of rebuilding it from the work-list (a device->host copy + host histogram)."""
     import torch
     import torch.distributed as dist
     from . import _lib
@@ -116,8 +118,9 @@ def gpu_bin_sharded_loglike(db, N, val=0.0, fpos_dev=None, include_minus_m=True,
     h.check(h.lib.emrifd_batch_segment(h.h, pb.walkers.ctypes.data, pb.B, db.t.data_ptr(), db.coeff.data_ptr(),
                                        db.m.data_ptr(), db.n.data_ptr(), int(N), float(val), _lib.ptr(fpos_dev),
                                        db.branches.data_ptr(), None))
-    work = bin_work_histogram(db.branches_host(), pb.m, N)
-    slices = balanced_bin_slices(work, world)
+    if slices is None:
+        work = bin_work_histogram(db.branches_host(), pb.m, N)
+        slices = balanced_bin_slices(work, world)
 
     def partial(j_lo, j_cnt):
         out = torch.zeros((pb.B, 3), dtype=torch.float64, device=h.torch_device)

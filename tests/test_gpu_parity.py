@@ -270,3 +270,24 @@ def test_error_codes(generator, torch_cuda):
         engine.run_waveform(engine.DeviceBatch(engine.PackedBatch([short]), h), 1001, 1e-5)    # < 4 knots
     with pytest.raises(ValueError):
         engine.run_loglike(engine.DeviceBatch(engine.PackedBatch([it]), _lib.Handle()), it["N"], 1.0 / (it["N"] * 10.0))  # no data set
+
+
+def test_all_modes_high_mode_count(generator, oracle_quad, torch_cuda):
+    """config-4 flavour: every (l, m, n) of the amplitude basis (K = 3843 -> 15372 work-list slots, 61 compaction
+    chunks per CTA), high eccentricity, negative-frequency harmonics (m f_phi + n f_r < 0) on the -f side."""
+    it = generator.prepare(3e5, 30.0, 9.5, 0.68, 0.9, -np.pi / 2, dist=1.0, Phi_phi0=0.2, Phi_r0=2.0, T=0.03, dt=50.0,
+                           mode_selection="all")
+    from helpers import grid_size
+    it["T"], it["dt"] = 0.03, 50.0
+    it["N"] = grid_size(it["t"], 0.03, 50.0)
+    assert it["teuk_modes"].shape[1] == 3843
+    hp_o, hc_o, coeff_o, br_o, nbr_o = oracle_waveform(oracle_quad, it)
+    s, out = _gpu_sum(it, torch_cuda)
+    br_g = s.last_batch.branches_host()
+    assert np.array_equal(s.last_batch.coeff_host(0), coeff_o)
+    for key in ("dir", "ja", "jb", "start", "end", "xa", "xb", "Fa", "Fb"):
+        assert np.array_equal(br_g[key], br_o[key]), key
+    zero = (it["N"] - 1) // 2
+    assert (br_o["end"][br_o["end"] >= br_o["start"]] < zero).any()          # some harmonics live at negative frequency
+    assert rel_err(out[0], hp_o) <= TOL_BIN and rel_err(out[1], hc_o) <= TOL_BIN
+    assert np.array_equal(out[0] != 0, hp_o != 0)
