@@ -51,6 +51,8 @@ struct emrifd_handle {
     int stage_next;
     double *d_partial; // likelihood partial sums
     int64_t partial_cap;
+    long long *d_chunk; // per-chunk bin hulls
+    int64_t chunk_cap;
     const double *d_data; // whitened data [2][n]
     const double *d_wfac; // noise factor  [2][n]
     int64_t n_data;
@@ -463,6 +465,8 @@ struct SumParams {
     const double *wf;  // [2][n_data]
     long long n_data;
     double *partial;   // [B][ntiles][3]
+    const long long *chunk_rng; // [B][cpw][2] hull of positive bins per record chunk
+    int cpw;
 };
 
 
@@ -572,6 +576,38 @@ struct __align__(16) Entry {
     int jlo, jhi, mirror, pad;  // segment range the +f bins of this tile can fall in
 };
 
+// Hull of the positive-bin indices touched by each chunk of SUM_THREADS work-list records (either through the +f
+// or the -f side): lets mode_sum_kernel skip a whole chunk (no ballot, no barrier pair) when its tile is outside.
+__global__ void __launch_bounds__(SUM_THREADS) chunk_range_kernel(const emrifd_walker_t *w, const emrifd_branch_t *brs,
+                                                                   long long zero, long long *rng, int cpw) {
+    __shared__ long long s_lo[SUM_THREADS / 32], s_hi[SUM_THREADS / 32];
+    const emrifd_walker_t wd = w[blockIdx.y];
+    const int nrec = wd.K * MAXBR, r = blockIdx.x * SUM_THREADS + threadIdx.x;
+    long long lo = 0x7fffffffffffffffLL, hi = -1;
+    if (r < nrec) {
+        const emrifd_branch_t *b = brs + wd.mode_off * MAXBR + r;
+        const long long s0 = b->start, e0 = b->end;
+        if (e0 >= s0) {
+            if (e0 >= zero) { lo = (s0 > zero ? s0 : zero) - zero; hi = e0 - zero; }
+            if (s0 <= zero) {
+                const long long a = zero - (e0 < zero ? e0 : zero), c = zero - s0;
+                lo = a < lo ? a : lo; hi = c > hi ? c : hi;
+            }
+        }
+    }
+    for (int o = 16; o > 0; o >>= 1) {
+        const long long l2 = __shfl_down_sync(0xffffffffu, lo, o), h2 = __shfl_down_sync(0xffffffffu, hi, o);
+        lo = l2 < lo ? l2 : lo; hi = h2 > hi ? h2 : hi;
+    }
+    if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        for (int q = 1; q < SUM_THREADS / 32; q++) { lo = s_lo[q] < lo ? s_lo[q] : lo; hi = s_hi[q] > hi ? s_hi[q] : hi; }
+        long long *o = rng + ((long long)blockIdx.y * cpw + blockIdx.x) * 2;
+        o[0] = lo; o[1] = hi;
+    }
+}
+
 template <bool WRITE_H, bool LIKE>
 __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
@@ -611,7 +647,9 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
     const double val = p.g.val;
     const double *fpos = p.g.fpos;
 
-    for (int base = 0; base < nrec; base += SUM_THREADS) {
+    const long long *crng = p.chunk_rng + (long long)blockIdx.y * p.cpw * 2;
+    for (int base = 0, ch = 0; base < nrec; base += SUM_THREADS, ch++) {
+        if (crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0) continue; // block-uniform: nothing of this chunk touches the tile
         // ---- ordered compaction of this chunk's records that overlap the tile ------------------
         const int r = base + tid;
         bool pred = false;
@@ -818,6 +856,7 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
     }
 
     // ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
+    __syncthreads(); // accumulators are read by other threads below (every chunk may have been skipped)
     // Transposed read-out: in iteration i thread t finalises tile-local bin i*SUM_THREADS + t, so a warp stores
     // 32 consecutive bins (512 B per array, fully coalesced) and reads the data stream the same way.
     double a0 = 0, a1 = 0, a2 = 0;
@@ -1096,7 +1135,7 @@ int emrifd_destroy(emrifd_handle_t *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_partial); cudaFree(h->d_ws);
+    cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk);
     if (h->h_ws) cudaFreeHost(h->h_ws);
     for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); cudaEventDestroy(h->stage_ev[i]); }
     for (int i = 0; i < 64; i++) { cudaEventDestroy(h->ev_a[i]); cudaEventDestroy(h->ev_b[i]); }
@@ -1198,7 +1237,7 @@ int emrifd_batch_segment(emrifd_handle_t *h, const emrifd_walker_t *walkers, int
     return batch_segment_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, N, val, fpos, branches, n_eval);
 }
 
-static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, const double *t, const double *coeff,
+static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const double *t, const double *coeff,
                          const int32_t *m_arr, const int32_t *n_arr, const double *ylm, const emrifd_branch_t *branches,
                          int64_t N, double val, const double *fpos, int flags, int64_t j_lo, int64_t j_cnt,
                          double *hp, double *hc, double *like_out) {
@@ -1223,6 +1262,15 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, const double *t,
         int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * 3 * ntiles * B);
         if (rc) return rc;
         p.partial = h->d_partial;
+    }
+    const int cpw = (Kmax * MAXBR + SUM_THREADS - 1) / SUM_THREADS;
+    {
+        int rc = ensure_bytes(h, (void **)&h->d_chunk, &h->chunk_cap, (int64_t)sizeof(long long) * 2 * cpw * B);
+        if (rc) return rc;
+        dim3 cgrid((unsigned)cpw, (unsigned)B);
+        chunk_range_kernel<<<cgrid, SUM_THREADS, 0, h->stream>>>(h->d_walkers, branches, (N - 1) / 2, h->d_chunk, cpw);
+        h->launches++;
+        p.chunk_rng = h->d_chunk; p.cpw = cpw;
     }
     const size_t smem = sum_smem_bytes(Lmax);
     if ((int64_t)smem > h->max_dyn_smem) return set_err(h, EMRIFD_ERR_TOO_MANY_KNOTS, "trajectory too long for the shared-memory staging of the mode-sum kernel");
@@ -1254,7 +1302,7 @@ int emrifd_batch_sum(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t
     if ((rc = check_grid(h, N, val, fpos))) return rc;
     cudaSetDevice(h->device);
     if ((rc = upload_walkers(h, walkers, B))) return rc;
-    return batch_sum_dev(h, B, Lmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, j_lo, j_cnt, hp, hc, like_out);
+    return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, j_lo, j_cnt, hp, hc, like_out);
 }
 
 int emrifd_fd_waveform_batch(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,
@@ -1272,7 +1320,7 @@ int emrifd_fd_waveform_batch(emrifd_handle_t *h, const emrifd_walker_t *walkers,
     if ((rc = upload_walkers(h, walkers, B))) return rc;
     if ((rc = batch_spline_dev(h, B, Lmax, Kmax, t, teuk, f_phi, f_r, Phi_phi, Phi_r, coeff))) return rc;
     if ((rc = batch_segment_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, N, val, fpos, branches, nullptr))) return rc;
-    return batch_sum_dev(h, B, Lmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, 0, (N + 1) / 2, hp, hc, like_out);
+    return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, 0, (N + 1) / 2, hp, hc, like_out);
 }
 
 int emrifd_batch_status(emrifd_handle_t *h) {
@@ -1375,7 +1423,7 @@ int emrifd_loglike_batch_host(emrifd_handle_t *h, const emrifd_walker_t *walkers
     if ((rc = batch_spline_dev(h, B, Lmax, Kmax, (double *)(d + o_t), (double *)(d + o_te), (double *)(d + o_fp), (double *)(d + o_fr),
                                (double *)(d + o_pp), (double *)(d + o_pr), coeff))) return rc;
     if ((rc = batch_segment_dev(h, B, Lmax, Kmax, (double *)(d + o_t), coeff, (int32_t *)(d + o_m), (int32_t *)(d + o_n), N, val, fpos_dev, br, nullptr))) return rc;
-    if ((rc = batch_sum_dev(h, B, Lmax, (double *)(d + o_t), coeff, (int32_t *)(d + o_m), (int32_t *)(d + o_n), (double *)(d + o_y), br,
+    if ((rc = batch_sum_dev(h, B, Lmax, Kmax, (double *)(d + o_t), coeff, (int32_t *)(d + o_m), (int32_t *)(d + o_n), (double *)(d + o_y), br,
                             N, val, fpos_dev, flags | EMRIFD_MASK_POSITIVE, 0, (N + 1) / 2, hp_dev, hc_dev, dout))) return rc;
     double *hres = (double *)(hs + in_bytes);
     CUDA_TRY(h, cudaMemcpyAsync(hres, dout, sizeof(double) * 3 * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
