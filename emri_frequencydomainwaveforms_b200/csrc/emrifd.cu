@@ -746,8 +746,8 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                     const double sgn = side == 0 ? 1.0 : -1.0;
                     const int k = E.mode, dir = E.dir, ja = E.ja, jb = E.jb;
                     const double dm = E.dm, dn = E.dn, sdir = (double)dir;
-                    double *accd = acc + side * 2 * SUM_BPT * ACC_STRIDE + tid;       // direct term -> this side
-                    double *accm = acc + (1 - side) * 2 * SUM_BPT * ACC_STRIDE + tid; // mirrored -m term -> other side
+                    const int offd = side * 2 * SUM_BPT * ACC_STRIDE + tid;       // direct term -> this side
+                    const int offm = (1 - side) * 2 * SUM_BPT * ACC_STRIDE + tid; // mirrored -m term -> other side
                     // per-segment state
                     int j = -1;
                     double segA = 0, segB = 0; // frequency at the time-start / time-end of the current sub-interval
@@ -799,7 +799,8 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                             const double gh = xh0 * fma(xh0, fma(xh0, c3, c2), c1) - delta;
                             x = xl0 - gl * (xh0 - xl0) * fast_rcp(gh - gl);
                         }
-                        const double tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
+                        const double tol = 1e-6 * hj;
+                        // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
                         bool ok = false;
                         double rr = 0.0;
 #pragma unroll 1
@@ -841,12 +842,12 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                         const double agr = ReA * Gre - ImA * Gim, agi = ReA * Gim + ImA * Gre;
                         const double Cr = agr * cs - agi * sn, Ci = agr * sn + agi * cs;
                         // direct term lands on the bin of this side, the mirrored -m term on the other side
-                        double *ad = accd + b * ACC_STRIDE, *am = accm + b * ACC_STRIDE;
-                        ad[0] += E.ypr * Cr - E.ypi * Ci;
-                        ad[SUM_BPT * ACC_STRIDE] += E.ypr * Ci + E.ypi * Cr;
+                        const int id = offd + b * ACC_STRIDE, im_ = offm + b * ACC_STRIDE;
+                        acc[id] += E.ypr * Cr - E.ypi * Ci;
+                        acc[id + SUM_BPT * ACC_STRIDE] += E.ypr * Ci + E.ypi * Cr;
                         if (E.mirror) {
-                            am[0] += E.ymr * Cr + E.ymi * Ci;
-                            am[SUM_BPT * ACC_STRIDE] += E.ymi * Cr - E.ymr * Ci;
+                            acc[im_] += E.ymr * Cr + E.ymi * Ci;
+                            acc[im_ + SUM_BPT * ACC_STRIDE] += E.ymi * Cr - E.ymr * Ci;
                         }
                     }
                 }
@@ -861,10 +862,10 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
     // 32 consecutive bins (512 B per array, fully coalesced) and reads the data stream the same way.
     double a0 = 0, a1 = 0, a2 = 0;
     const int ntile = (int)(jt1 - jt0 + 1);
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < SUM_BPT; i++) {
         const int lb = i * SUM_THREADS + tid;
-        if (lb >= ntile) break;
+        if (lb >= ntile) continue;
         const long long j = jt0 + lb;
         const int own = lb / SUM_BPT, bb = lb % SUM_BPT;
         const double *ap = acc + bb * ACC_STRIDE + own;
