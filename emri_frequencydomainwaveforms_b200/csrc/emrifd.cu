@@ -576,6 +576,94 @@ struct __align__(16) Entry {
     int jlo, jhi, mirror, pad;  // segment range the +f bins of this tile can fall in
 };
 
+// ---- evaluation of W (1 or 2) bins of one segment in straight-line code: the W independent dependency chains
+//      (amplitude Horner, SPA factor, phase, sincos) interleave in the instruction stream (ILP without more warps) ----
+__device__ __forceinline__ void spa_fix(double fdot, double fddot, double s, double u, double &re, double &im) {
+    // rare path of the SPA factor: X = 1/u < 1024 (late inspiral, turnover neighbourhood); returns R/sqrt|fdot|
+    if (u <= 0.03125) {
+        const double w = u * u;
+        double pr = k13_asym_re[6], pi = k13_asym_im[6];
+#pragma unroll
+        for (int k = 5; k >= 0; k--) { pr = fma(pr, w, k13_asym_re[k]); pi = fma(pi, w, k13_asym_im[k]); }
+        re = pr * s; im = u * pi * s;
+    } else if (u <= 1.0) {
+        k13_mid(1.0 / u, re, im);
+        re *= s; im *= s;
+    } else {
+        const double af = fabs(fdot);
+        const double X = 2.0943951023931953 * af * af * af / (fddot * fddot);
+        k13_small_S(X, re, im);
+        const double sc = cbrt(1.4472025091165353 / fabs(fddot));
+        re *= sc; im *= sc;
+    }
+}
+
+template <int W>
+__device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f)[W], const double c1, const double d2,
+                                          const double d3, const double4 qa, const double4 qb, const double tj,
+                                          const double *__restrict__ q, const double *__restrict__ u4, const double dm,
+                                          const double dn, const Entry &E, double *__restrict__ acc, const int id0,
+                                          const int im0) {
+    double Cr[W], Ci[W], re[W], im[W], s[W], uu[W], fd[W], fdd[W], sn[W], cs[W], ReA[W], ImA[W];
+    const double q9 = q[9], q10 = q[10], q11 = q[11], q13 = q[13], q14 = q[14], q15 = q[15];
+    const double u0 = u4[0], u1 = u4[1], u2 = u4[2], u3 = u4[3];
+    const double mu_hi = fma(dm, u0, dn * u2), mu_lo = fma(dm, u1, dn * u3);
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const double xi = x[i], fi = f[i];
+        ReA[i] = fma(xi, fma(xi, fma(xi, qa.w, qa.z), qa.y), qa.x);
+        ImA[i] = fma(xi, fma(xi, fma(xi, qb.w, qb.z), qb.y), qb.x);
+        fd[i] = fma(xi, fma(d3, xi, d2), c1);
+        fdd[i] = fma(2.0 * d3, xi, d2);
+        // SPA factor, common path (X >= 1024): s = 1/sqrt|fdot|, u = 1/X = 3 fddot^2 s^6/(2 pi)
+        s[i] = fast_rsqrt(fabs(fd[i]));
+        const double s2 = s[i] * s[i];
+        uu[i] = 0.477464829275686 * (fdd[i] * fdd[i]) * (s2 * s2 * s2);
+        const double w = uu[i] * uu[i];
+        re[i] = fma(w, fma(w, k13_asym_re[2], k13_asym_re[1]), 1.0) * s[i];
+        im[i] = uu[i] * fma(w, fma(w, k13_asym_im[2], k13_asym_im[1]), k13_asym_im[0]) * s[i];
+        // phase in cycles
+        const double pp = xi * fma(xi, fma(xi, q11, q10), q9);
+        const double pr = xi * fma(xi, fma(xi, q15, q14), q13);
+        double p0 = fi * tj;
+        const double e0 = fma(fi, tj, -p0);
+        p0 -= rint(p0);
+        double cyc = p0 - mu_hi;
+        cyc -= rint(cyc);
+        const double poly = fma(fi, xi, -EMRIFD_INV2PI_HI * fma(dm, pp, dn * pr));
+        cyc += (poly - rint(poly)) + (e0 - mu_lo);
+        sincos_cycles(cyc, sn[i], cs[i]);
+    }
+#pragma unroll
+    for (int i = 0; i < W; i++)
+        if (!(uu[i] <= 0.0009765625)) spa_fix(fd[i], fdd[i], s[i], uu[i], re[i], im[i]);
+    const double ypr = E.ypr, ypi = E.ypi;
+    const bool mirror = E.mirror;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        // G = e^{+-i 3pi/4} (re + i im)
+        const double r2 = 0.7071067811865476;
+        const double gre = (-re[i] - im[i]) * r2;
+        double gim = (re[i] - im[i]) * r2;
+        if (fd[i] < 0.0) gim = -gim;
+        const double agr = ReA[i] * gre - ImA[i] * gim, agi = ReA[i] * gim + ImA[i] * gre;
+        Cr[i] = agr * cs[i] - agi * sn[i];
+        Ci[i] = agr * sn[i] + agi * cs[i];
+        const int id = id0 + i * ACC_STRIDE;
+        acc[id] += ypr * Cr[i] - ypi * Ci[i];
+        acc[id + SUM_BPT * ACC_STRIDE] += ypr * Ci[i] + ypi * Cr[i];
+    }
+    if (mirror) {
+        const double ymr = E.ymr, ymi = E.ymi;
+#pragma unroll
+        for (int i = 0; i < W; i++) {
+            const int im_ = im0 + i * ACC_STRIDE;
+            acc[im_] += ymr * Cr[i] + ymi * Ci[i];
+            acc[im_ + SUM_BPT * ACC_STRIDE] += ymi * Cr[i] - ymr * Ci[i];
+        }
+    }
+}
+
 // Hull of the positive-bin indices touched by each chunk of SUM_THREADS work-list records (either through the +f
 // or the -f side): lets mode_sum_kernel skip a whole chunk (no ballot, no barrier pair) when its tile is outside.
 __global__ void __launch_bounds__(SUM_THREADS) chunk_range_kernel(const emrifd_walker_t *w, const emrifd_branch_t *brs,
@@ -636,7 +724,9 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
     // dynamic smem: accumulators [4][SUM_BPT][SUM_THREADS] | entry cache | T[L] | Q[L][16] | U[L][4]
     double *acc = reinterpret_cast<double *>(smraw);
     Entry *ent = reinterpret_cast<Entry *>(acc + 4 * SUM_BPT * ACC_STRIDE);
-    double *sT = reinterpret_cast<double *>(ent + SUM_THREADS);
+    double *sX = reinterpret_cast<double *>(ent + SUM_THREADS); // roots of the current entry  [SUM_BPT][SUM_THREADS]
+    int *sJ = reinterpret_cast<int *>(sX + SUM_BPT * SUM_THREADS);  // their segment indices   [SUM_BPT][SUM_THREADS]
+    double *sT = reinterpret_cast<double *>(sJ + SUM_BPT * SUM_THREADS);
     double *sQ = sT + L, *sU = sT + 17 * L;
 #define ACC(c, b) acc[((c) * SUM_BPT + (b)) * ACC_STRIDE + tid]
 #pragma unroll
@@ -748,106 +838,99 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                     const double dm = E.dm, dn = E.dn, sdir = (double)dir;
                     const int offd = side * 2 * SUM_BPT * ACC_STRIDE + tid;       // direct term -> this side
                     const int offm = (1 - side) * 2 * SUM_BPT * ACC_STRIDE + tid; // mirrored -m term -> other side
-                    // per-segment state
-                    int j = -1;
-                    double segA = 0, segB = 0; // frequency at the time-start / time-end of the current sub-interval
-                    double tj = 0, hj = 0, xl0 = 0, xh0 = 0, c0 = 0, c1 = 0, c2 = 0, c3 = 0;
-                    double4 qa = make_double4(0, 0, 0, 0), qb = qa;
-                    double xprev = 0, fprev = 0, rprev = 0;
-                    bool warm = false;
-                    for (int b = bl; b <= bh; b++) {
-                        const long long jj = j0 + b;
-                        const double f = sgn * (fpos ? fpos[jj] : rmul((double)(int)jj, val));
-                        // ---- segment lookup: binary search on the first bin, short walk afterwards ----
-                        bool inside = (j >= 0) && (dir > 0 ? (f >= segA && f < segB) : (f <= segA && f > segB));
-                        if (!inside) {
-                            int lo = side == 0 ? E.jlo : ja, hi = side == 0 ? E.jhi : jb;
-                            if (j >= 0) { // walk from the previous segment
-                                lo = j;
-                                if (dir * sgn > 0) { while (lo < jb) { const double Fk = radd(rmul(dm, sQ[(lo + 1) * 16]), rmul(dn, sQ[(lo + 1) * 16 + 4])); if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo++; else break; } }
-                                else { while (lo > ja) { const double Fk = radd(rmul(dm, sQ[lo * 16]), rmul(dn, sQ[lo * 16 + 4])); if (dir > 0 ? (Fk > f) : (Fk < f)) lo--; else break; } }
-                            } else {
-                                while (lo < hi) {
-                                    const int mid = (lo + hi + 1) >> 1;
-                                    const double Fk = radd(rmul(dm, sQ[mid * 16]), rmul(dn, sQ[mid * 16 + 4]));
-                                    if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo = mid; else hi = mid - 1;
+                    // ---- stage 1: segment + root for each of this thread's bins (sequential: warm start) ----
+                    // (deliberately uninitialised: j < 0 forces the segment lookup, which sets all of it, before any read)
+                    {
+                        int j = -1;
+                        double segA, segB; // frequency at the time-start / time-end of the current sub-interval
+                        double hj, xl0, xh0, c0, c1, c2, c3;
+                        double xprev, fprev, rprev;
+                        bool warm = false;
+                        for (int b = bl; b <= bh; b++) {
+                            const long long jj = j0 + b;
+                            const double f = sgn * (fpos ? fpos[jj] : rmul((double)(int)jj, val));
+                            bool inside = (j >= 0) && (dir > 0 ? (f >= segA && f < segB) : (f <= segA && f > segB));
+                            if (!inside) {
+                                int lo = side == 0 ? E.jlo : ja, hi = side == 0 ? E.jhi : jb;
+                                if (j >= 0) { // walk from the previous segment
+                                    lo = j;
+                                    if (dir * sgn > 0) { while (lo < jb) { const double Fk = radd(rmul(dm, sQ[(lo + 1) * 16]), rmul(dn, sQ[(lo + 1) * 16 + 4])); if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo++; else break; } }
+                                    else { while (lo > ja) { const double Fk = radd(rmul(dm, sQ[lo * 16]), rmul(dn, sQ[lo * 16 + 4])); if (dir > 0 ? (Fk > f) : (Fk < f)) lo--; else break; } }
+                                } else {
+                                    while (lo < hi) {
+                                        const int mid = (lo + hi + 1) >> 1;
+                                        const double Fk = radd(rmul(dm, sQ[mid * 16]), rmul(dn, sQ[mid * 16 + 4]));
+                                        if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo = mid; else hi = mid - 1;
+                                    }
                                 }
+                                j = lo;
+                                const double *q = sQ + j * 16;
+                                hj = sT[j + 1] - sT[j];
+                                c0 = radd(rmul(dm, q[0]), rmul(dn, q[4]));
+                                c1 = fma(dm, q[1], dn * q[5]);
+                                c2 = fma(dm, q[2], dn * q[6]);
+                                c3 = fma(dm, q[3], dn * q[7]);
+                                xl0 = (j == ja) ? E.xa : 0.0;
+                                xh0 = (j == jb) ? E.xb : hj;
+                                segA = (j == ja) ? fma(xl0, fma(xl0, fma(xl0, c3, c2), c1), c0) : c0;
+                                segB = (j == jb) ? fma(xh0, fma(xh0, fma(xh0, c3, c2), c1), c0)
+                                                 : radd(rmul(dm, q[16]), rmul(dn, q[20]));
+                                warm = false;
                             }
-                            j = lo;
-                            const double *q = sQ + j * 16;
-                            qa = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + k) * 4);
-                            qb = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + K + k) * 4);
-                            tj = sT[j]; hj = sT[j + 1] - tj;
-                            c0 = radd(rmul(dm, q[0]), rmul(dn, q[4]));
-                            c1 = fma(dm, q[1], dn * q[5]);
-                            c2 = fma(dm, q[2], dn * q[6]);
-                            c3 = fma(dm, q[3], dn * q[7]);
-                            xl0 = (j == ja) ? E.xa : 0.0;
-                            xh0 = (j == jb) ? E.xb : hj;
-                            // sub-interval frequency bounds for the cheap "still inside" test
-                            segA = (j == ja) ? fma(xl0, fma(xl0, fma(xl0, c3, c2), c1), c0) : c0;
-                            segB = (j == jb) ? fma(xh0, fma(xh0, fma(xh0, c3, c2), c1), c0)
-                                             : radd(rmul(dm, q[16]), rmul(dn, q[20]));
-                            warm = false;
-                        }
-                        const double delta = f - c0;
-                        // ---- root of x(c1 + x(c2 + x c3)) = delta: warm-started Newton, robust fallback ----
-                        double x;
-                        if (warm) x = fma(f - fprev, rprev, xprev);
-                        else {
-                            const double gl = xl0 * fma(xl0, fma(xl0, c3, c2), c1) - delta;
-                            const double gh = xh0 * fma(xh0, fma(xh0, c3, c2), c1) - delta;
-                            x = xl0 - gl * (xh0 - xl0) * fast_rcp(gh - gl);
-                        }
-                        const double tol = 1e-6 * hj;
-                        // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
-                        bool ok = false;
-                        double rr = 0.0;
+                            const double delta = f - c0;
+                            double x;
+                            if (warm) x = fma(f - fprev, rprev, xprev);
+                            else {
+                                const double gl = xl0 * fma(xl0, fma(xl0, c3, c2), c1) - delta;
+                                const double gh = xh0 * fma(xh0, fma(xh0, c3, c2), c1) - delta;
+                                x = xl0 - gl * (xh0 - xl0) * fast_rcp(gh - gl);
+                            }
+                            const double tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
+                            bool ok = false;
+                            double rr = 0.0;
 #pragma unroll 1
-                        for (int it = 0; it < 6; it++) {
-                            const double gx = x * fma(x, fma(x, c3, c2), c1) - delta;
-                            const double dg = fma(x, fma(3.0 * c3, x, 2.0 * c2), c1);
-                            rr = fast_rcp(dg);
-                            const double dx = gx * rr;
-                            x -= dx;
-                            if (fabs(dx) <= tol) { ok = true; break; }
+                            for (int it = 0; it < 6; it++) {
+                                const double gx = x * fma(x, fma(x, c3, c2), c1) - delta;
+                                const double dg = fma(x, fma(3.0 * c3, x, 2.0 * c2), c1);
+                                rr = fast_rcp(dg);
+                                const double dx = gx * rr;
+                                x -= dx;
+                                if (fabs(dx) <= tol) { ok = true; break; }
+                            }
+                            const double slack = 1e-5 * hj;
+                            if (!(ok && x >= xl0 - slack && x <= xh0 + slack)) {
+                                x = solve_bracketed(c1, c2, c3, delta, xl0, xh0, sdir, hj);
+                                rr = fast_rcp(fma(x, fma(3.0 * c3, x, 2.0 * c2), c1));
+                            }
+                            xprev = x; fprev = f; rprev = rr; warm = true;
+                            sX[b * SUM_THREADS + tid] = x;
+                            sJ[b * SUM_THREADS + tid] = j;
                         }
-                        const double slack = 1e-5 * hj;
-                        if (!(ok && x >= xl0 - slack && x <= xh0 + slack)) {
-                            x = solve_bracketed(c1, c2, c3, delta, xl0, xh0, sdir, hj);
-                            rr = fast_rcp(fma(x, fma(3.0 * c3, x, 2.0 * c2), c1));
-                        }
-                        xprev = x; fprev = f; rprev = rr; warm = true;
-                        // ---- amplitude, SPA factor, phase ----
-                        const double ReA = fma(x, fma(x, fma(x, qa.w, qa.z), qa.y), qa.x);
-                        const double ImA = fma(x, fma(x, fma(x, qb.w, qb.z), qb.y), qb.x);
-                        const double fdot = fma(x, fma(3.0 * c3, x, 2.0 * c2), c1);
-                        const double fddot = fma(6.0 * c3, x, 2.0 * c2);
-                        double Gre, Gim;
-                        spa_G2(fdot, fddot, Gre, Gim);
+                    }
+                    // ---- stage 2: evaluate the bins two at a time (same segment) in straight-line code ----
+                    for (int b = bl; b <= bh;) {
+                        const int j = sJ[b * SUM_THREADS + tid];
+                        const bool two = (b < bh) && (sJ[(b + 1) * SUM_THREADS + tid] == j);
                         const double *q = sQ + j * 16;
-                        const double pp = x * fma(x, fma(x, q[11], q[10]), q[9]);
-                        const double pr = x * fma(x, fma(x, q[15], q[14]), q[13]);
-                        double p0 = f * tj;
-                        const double e0 = fma(f, tj, -p0);
-                        p0 -= rint(p0);
-                        const double *u = sU + j * 4;
-                        double cyc = p0 - fma(dm, u[0], dn * u[2]);
-                        cyc -= rint(cyc);
-                        const double small = e0 - fma(dm, u[1], dn * u[3]);
-                        const double poly = fma(f, x, -EMRIFD_INV2PI_HI * fma(dm, pp, dn * pr));
-                        cyc += (poly - rint(poly)) + small;
-                        double sn, cs;
-                        sincos_cycles(cyc, sn, cs);
-                        const double agr = ReA * Gre - ImA * Gim, agi = ReA * Gim + ImA * Gre;
-                        const double Cr = agr * cs - agi * sn, Ci = agr * sn + agi * cs;
-                        // direct term lands on the bin of this side, the mirrored -m term on the other side
-                        const int id = offd + b * ACC_STRIDE, im_ = offm + b * ACC_STRIDE;
-                        acc[id] += E.ypr * Cr - E.ypi * Ci;
-                        acc[id + SUM_BPT * ACC_STRIDE] += E.ypr * Ci + E.ypi * Cr;
-                        if (E.mirror) {
-                            acc[im_] += E.ymr * Cr + E.ymi * Ci;
-                            acc[im_ + SUM_BPT * ACC_STRIDE] += E.ymi * Cr - E.ymr * Ci;
+                        const double4 qa = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + k) * 4);
+                        const double4 qb = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + K + k) * 4);
+                        const double c1 = fma(dm, q[1], dn * q[5]);
+                        const double d2 = 2.0 * fma(dm, q[2], dn * q[6]);
+                        const double d3 = 3.0 * fma(dm, q[3], dn * q[7]);
+                        const double tj = sT[j];
+                        const long long jj = j0 + b;
+                        const int id0 = offd + b * ACC_STRIDE, im0 = offm + b * ACC_STRIDE;
+                        if (two) {
+                            const double x2[2] = {sX[b * SUM_THREADS + tid], sX[(b + 1) * SUM_THREADS + tid]};
+                            const double f2[2] = {sgn * (fpos ? fpos[jj] : rmul((double)(int)jj, val)),
+                                                  sgn * (fpos ? fpos[jj + 1] : rmul((double)(int)(jj + 1), val))};
+                            eval_bins<2>(x2, f2, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
+                            b += 2;
+                        } else {
+                            const double x1[1] = {sX[b * SUM_THREADS + tid]};
+                            const double f1[1] = {sgn * (fpos ? fpos[jj] : rmul((double)(int)jj, val))};
+                            eval_bins<1>(x1, f1, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
+                            b += 1;
                         }
                     }
                 }
@@ -1033,7 +1116,7 @@ static size_t spline_smem_bytes(int L, bool tiled) {
 }
 
 static size_t sum_smem_bytes(int L) {
-    return sizeof(double) * 4 * SUM_BPT * ACC_STRIDE + sizeof(Entry) * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
+    return sizeof(double) * 4 * SUM_BPT * ACC_STRIDE + 12 * SUM_BPT * SUM_THREADS + sizeof(Entry) * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
 
 static int ensure_bytes(emrifd_handle *h, void **ptr, int64_t *cap, int64_t need, bool pinned_host = false) {
