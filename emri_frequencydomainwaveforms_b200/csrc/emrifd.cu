@@ -531,6 +531,24 @@ __device__ __noinline__ double solve_bracketed(double c1, double c2, double c3, 
     return x;
 }
 
+// out-of-line slow path of the root solve: first bin of a thread, segment change, or a fast step that did not converge
+__device__ __noinline__ double solve_slow(double c1, double c2, double c3, double delta, double xlo, double xhi, double tol,
+                                          double sdir) {
+    const double gl = xlo * fma(xlo, fma(xlo, c3, c2), c1) - delta;
+    const double gh = xhi * fma(xhi, fma(xhi, c3, c2), c1) - delta;
+    double x = xlo - gl * (xhi - xlo) * fast_rcp(gh - gl);
+    for (int it = 0; it < 6; it++) {
+        const double gx = x * fma(x, fma(x, c3, c2), c1) - delta;
+        const double dx = gx * fast_rcp(fma(x, fma(3.0 * c3, x, 2.0 * c2), c1));
+        x -= dx;
+        if (fabs(dx) <= tol) {
+            if (x >= xlo && x <= xhi) return x;
+            break;
+        }
+    }
+    return solve_bracketed(c1, c2, c3, delta, xlo, xhi, sdir, tol * 1e6);
+}
+
 // SPA factor from fdot, fddot without divisions on the common path:
 //   s = 1/sqrt|fdot|,  u = 1/X = 3 fddot^2 s^6 / (2 pi)
 __device__ __forceinline__ void spa_G2(double fdot, double fddot, double &gre, double &gim) {
@@ -724,13 +742,19 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
     // dynamic smem: accumulators [4][SUM_BPT][SUM_THREADS] | entry cache | T[L] | Q[L][16] | U[L][4]
     double *acc = reinterpret_cast<double *>(smraw);
     Entry *ent = reinterpret_cast<Entry *>(acc + 4 * SUM_BPT * ACC_STRIDE);
-    double *sX = reinterpret_cast<double *>(ent + SUM_THREADS); // roots of the current entry  [SUM_BPT][SUM_THREADS]
+    double *sF = reinterpret_cast<double *>(ent + SUM_THREADS); // exact bin frequencies        [SUM_BPT][SUM_THREADS]
+    double *sX = sF + SUM_BPT * SUM_THREADS;                    // roots of the current entry  [SUM_BPT][SUM_THREADS]
     int *sJ = reinterpret_cast<int *>(sX + SUM_BPT * SUM_THREADS);  // their segment indices   [SUM_BPT][SUM_THREADS]
     double *sT = reinterpret_cast<double *>(sJ + SUM_BPT * SUM_THREADS);
     double *sQ = sT + L, *sU = sT + 17 * L;
 #define ACC(c, b) acc[((c) * SUM_BPT + (b)) * ACC_STRIDE + tid]
 #pragma unroll
     for (int i = 0; i < 4 * SUM_BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
+#pragma unroll
+    for (int b = 0; b < SUM_BPT; b++) {
+        const long long jj = j0 + b;
+        sF[b * SUM_THREADS + tid] = (b < nb) ? (p.g.fpos ? p.g.fpos[jj] : rmul((double)(int)jj, p.g.val)) : 0.0;
+    }
 
     const int nrec = K * MAXBR;
     bool staged = false;
@@ -836,101 +860,104 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                     const double sgn = side == 0 ? 1.0 : -1.0;
                     const int k = E.mode, dir = E.dir, ja = E.ja, jb = E.jb;
                     const double dm = E.dm, dn = E.dn, sdir = (double)dir;
+                    const double *cmode = coeff + (long long)k * 4; // quads of Re A_k at knot 0; Im A_k is K*4 doubles further
                     const int offd = side * 2 * SUM_BPT * ACC_STRIDE + tid;       // direct term -> this side
                     const int offm = (1 - side) * 2 * SUM_BPT * ACC_STRIDE + tid; // mirrored -m term -> other side
-                    // ---- stage 1: segment + root for each of this thread's bins (sequential: warm start) ----
-                    // (deliberately uninitialised: j < 0 forces the segment lookup, which sets all of it, before any read)
+                    // ---- stage 1: segment + root for each of this thread's bins.  Hot path = straight-line:
+                    //      second-order extrapolation from the previous bin + ONE Newton step; everything else
+                    //      (first bin, segment change, slow convergence) goes through the out-of-line slow path ----
                     {
                         int j = -1;
-                        double segA, segB; // frequency at the time-start / time-end of the current sub-interval
-                        double hj, xl0, xh0, c0, c1, c2, c3;
-                        double xprev, fprev, rprev;
-                        bool warm = false;
-                        for (int b = bl; b <= bh; b++) {
-                            const long long jj = j0 + b;
-                            const double f = sgn * (fpos ? fpos[jj] : rmul((double)(int)jj, val));
-                            bool inside = (j >= 0) && (dir > 0 ? (f >= segA && f < segB) : (f <= segA && f > segB));
-                            if (!inside) {
-                                int lo = side == 0 ? E.jlo : ja, hi = side == 0 ? E.jhi : jb;
-                                if (j >= 0) { // walk from the previous segment
-                                    lo = j;
-                                    if (dir * sgn > 0) { while (lo < jb) { const double Fk = radd(rmul(dm, sQ[(lo + 1) * 16]), rmul(dn, sQ[(lo + 1) * 16 + 4])); if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo++; else break; } }
-                                    else { while (lo > ja) { const double Fk = radd(rmul(dm, sQ[lo * 16]), rmul(dn, sQ[lo * 16 + 4])); if (dir > 0 ? (Fk > f) : (Fk < f)) lo--; else break; } }
-                                } else {
-                                    while (lo < hi) {
-                                        const int mid = (lo + hi + 1) >> 1;
-                                        const double Fk = radd(rmul(dm, sQ[mid * 16]), rmul(dn, sQ[mid * 16 + 4]));
-                                        if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo = mid; else hi = mid - 1;
-                                    }
-                                }
-                                j = lo;
-                                const double *q = sQ + j * 16;
-                                hj = sT[j + 1] - sT[j];
-                                c0 = radd(rmul(dm, q[0]), rmul(dn, q[4]));
-                                c1 = fma(dm, q[1], dn * q[5]);
-                                c2 = fma(dm, q[2], dn * q[6]);
-                                c3 = fma(dm, q[3], dn * q[7]);
-                                xl0 = (j == ja) ? E.xa : 0.0;
-                                xh0 = (j == jb) ? E.xb : hj;
-                                segA = (j == ja) ? fma(xl0, fma(xl0, fma(xl0, c3, c2), c1), c0) : c0;
-                                segB = (j == jb) ? fma(xh0, fma(xh0, fma(xh0, c3, c2), c1), c0)
-                                                 : radd(rmul(dm, q[16]), rmul(dn, q[20]));
-                                warm = false;
-                            }
-                            const double delta = f - c0;
-                            double x;
-                            if (warm) x = fma(f - fprev, rprev, xprev);
-                            else {
-                                const double gl = xl0 * fma(xl0, fma(xl0, c3, c2), c1) - delta;
-                                const double gh = xh0 * fma(xh0, fma(xh0, c3, c2), c1) - delta;
-                                x = xl0 - gl * (xh0 - xl0) * fast_rcp(gh - gl);
-                            }
-                            const double tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
+                        double segA, segB;            // frequency at the time-start / time-end of the current sub-interval
+                        double c0, c1, c2, c3, d2, d3; // f_mn cubic on the segment, d2 = 2 c2, d3 = 3 c3
+                        double xlo_s, xhi_s, tol;      // slackened bracket and Newton tolerance
+                        double xprev = 0.0, fprev = 0.0, rprev = 0.0;
+                        const double *pF = sF + tid + bl * SUM_THREADS;
+                        double *pX = sX + tid + bl * SUM_THREADS;
+                        int *pJ = sJ + tid + bl * SUM_THREADS;
+                        for (int b = bl; b <= bh; b++, pF += SUM_THREADS, pX += SUM_THREADS, pJ += SUM_THREADS) {
+                            const double f = sgn * pF[0];
+                            const bool inside = (j >= 0) && (dir > 0 ? (f >= segA && f < segB) : (f <= segA && f > segB));
+                            double x, rr;
                             bool ok = false;
-                            double rr = 0.0;
-#pragma unroll 1
-                            for (int it = 0; it < 6; it++) {
+                            if (inside) {
+                                const double delta = f - c0;
+                                const double dxl = (f - fprev) * rprev;                 // first-order step
+                                const double curv = fma(2.0 * d3, xprev, d2) * rprev;  // fddot/fdot at the previous root
+                                x = fma(dxl, fma(-0.5 * curv, dxl, 1.0), xprev);        // second-order extrapolation
                                 const double gx = x * fma(x, fma(x, c3, c2), c1) - delta;
-                                const double dg = fma(x, fma(3.0 * c3, x, 2.0 * c2), c1);
-                                rr = fast_rcp(dg);
+                                rr = fast_rcp(fma(x, fma(d3, x, d2), c1));
                                 const double dx = gx * rr;
                                 x -= dx;
-                                if (fabs(dx) <= tol) { ok = true; break; }
+                                ok = (fabs(dx) <= tol) && (x >= xlo_s) && (x <= xhi_s);
                             }
-                            const double slack = 1e-5 * hj;
-                            if (!(ok && x >= xl0 - slack && x <= xh0 + slack)) {
-                                x = solve_bracketed(c1, c2, c3, delta, xl0, xh0, sdir, hj);
-                                rr = fast_rcp(fma(x, fma(3.0 * c3, x, 2.0 * c2), c1));
+                            if (!ok) {
+                                if (!inside) {
+                                    int lo = side == 0 ? E.jlo : ja, hi = side == 0 ? E.jhi : jb;
+                                    if (j >= 0) { // walk from the previous segment
+                                        lo = j;
+                                        if (dir * sgn > 0) { while (lo < jb) { const double Fk = radd(rmul(dm, sQ[(lo + 1) * 16]), rmul(dn, sQ[(lo + 1) * 16 + 4])); if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo++; else break; } }
+                                        else { while (lo > ja) { const double Fk = radd(rmul(dm, sQ[lo * 16]), rmul(dn, sQ[lo * 16 + 4])); if (dir > 0 ? (Fk > f) : (Fk < f)) lo--; else break; } }
+                                    } else {
+                                        while (lo < hi) {
+                                            const int mid = (lo + hi + 1) >> 1;
+                                            const double Fk = radd(rmul(dm, sQ[mid * 16]), rmul(dn, sQ[mid * 16 + 4]));
+                                            if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo = mid; else hi = mid - 1;
+                                        }
+                                    }
+                                    j = lo;
+                                    const double *q = sQ + j * 16;
+                                    const double hj = sT[j + 1] - sT[j];
+                                    c0 = radd(rmul(dm, q[0]), rmul(dn, q[4]));
+                                    c1 = fma(dm, q[1], dn * q[5]);
+                                    c2 = fma(dm, q[2], dn * q[6]);
+                                    c3 = fma(dm, q[3], dn * q[7]);
+                                    d2 = 2.0 * c2; d3 = 3.0 * c3;
+                                    const double xl0 = (j == ja) ? E.xa : 0.0;
+                                    const double xh0 = (j == jb) ? E.xb : hj;
+                                    segA = (j == ja) ? fma(xl0, fma(xl0, fma(xl0, c3, c2), c1), c0) : c0;
+                                    segB = (j == jb) ? fma(xh0, fma(xh0, fma(xh0, c3, c2), c1), c0)
+                                                     : radd(rmul(dm, q[16]), rmul(dn, q[20]));
+                                    tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
+                                    xlo_s = xl0 - 1e-5 * hj; xhi_s = xh0 + 1e-5 * hj;
+                                }
+                                x = solve_slow(c1, c2, c3, f - c0, xlo_s, xhi_s, tol, sdir);
+                                rr = fast_rcp(fma(x, fma(d3, x, d2), c1));
                             }
-                            xprev = x; fprev = f; rprev = rr; warm = true;
-                            sX[b * SUM_THREADS + tid] = x;
-                            sJ[b * SUM_THREADS + tid] = j;
+                            xprev = x; fprev = f; rprev = rr;
+                            pX[0] = x;
+                            pJ[0] = j;
                         }
                     }
                     // ---- stage 2: evaluate the bins two at a time (same segment) in straight-line code ----
-                    for (int b = bl; b <= bh;) {
-                        const int j = sJ[b * SUM_THREADS + tid];
-                        const bool two = (b < bh) && (sJ[(b + 1) * SUM_THREADS + tid] == j);
-                        const double *q = sQ + j * 16;
-                        const double4 qa = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + k) * 4);
-                        const double4 qb = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + K + k) * 4);
-                        const double c1 = fma(dm, q[1], dn * q[5]);
-                        const double d2 = 2.0 * fma(dm, q[2], dn * q[6]);
-                        const double d3 = 3.0 * fma(dm, q[3], dn * q[7]);
-                        const double tj = sT[j];
-                        const long long jj = j0 + b;
-                        const int id0 = offd + b * ACC_STRIDE, im0 = offm + b * ACC_STRIDE;
-                        if (two) {
-                            const double x2[2] = {sX[b * SUM_THREADS + tid], sX[(b + 1) * SUM_THREADS + tid]};
-                            const double f2[2] = {sgn * (fpos ? fpos[jj] : rmul((double)(int)jj, val)),
-                                                  sgn * (fpos ? fpos[jj + 1] : rmul((double)(int)(jj + 1), val))};
-                            eval_bins<2>(x2, f2, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
-                            b += 2;
-                        } else {
-                            const double x1[1] = {sX[b * SUM_THREADS + tid]};
-                            const double f1[1] = {sgn * (fpos ? fpos[jj] : rmul((double)(int)jj, val))};
-                            eval_bins<1>(x1, f1, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
-                            b += 1;
+                    {
+                        const double *pF = sF + tid + bl * SUM_THREADS;
+                        const double *pX = sX + tid + bl * SUM_THREADS;
+                        const int *pJ = sJ + tid + bl * SUM_THREADS;
+                        int id0 = offd + bl * ACC_STRIDE, im0 = offm + bl * ACC_STRIDE;
+                        for (int b = bl; b <= bh;) {
+                            const int j = pJ[0];
+                            const bool two = (b < bh) && (pJ[SUM_THREADS] == j);
+                            const double *q = sQ + j * 16;
+                            const double4 qa = *reinterpret_cast<const double4 *>(cmode + (long long)j * (R * 4));
+                            const double4 qb = *reinterpret_cast<const double4 *>(cmode + (long long)j * (R * 4) + K * 4);
+                            const double c1 = fma(dm, q[1], dn * q[5]);
+                            const double d2 = 2.0 * fma(dm, q[2], dn * q[6]);
+                            const double d3 = 3.0 * fma(dm, q[3], dn * q[7]);
+                            const double tj = sT[j];
+                            if (two) {
+                                const double x2[2] = {pX[0], pX[SUM_THREADS]};
+                                const double f2[2] = {sgn * pF[0], sgn * pF[SUM_THREADS]};
+                                eval_bins<2>(x2, f2, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
+                                b += 2; pF += 2 * SUM_THREADS; pX += 2 * SUM_THREADS; pJ += 2 * SUM_THREADS;
+                                id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
+                            } else {
+                                const double x1[1] = {pX[0]};
+                                const double f1[1] = {sgn * pF[0]};
+                                eval_bins<1>(x1, f1, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
+                                b += 1; pF += SUM_THREADS; pX += SUM_THREADS; pJ += SUM_THREADS;
+                                id0 += ACC_STRIDE; im0 += ACC_STRIDE;
+                            }
                         }
                     }
                 }
@@ -1116,7 +1143,7 @@ static size_t spline_smem_bytes(int L, bool tiled) {
 }
 
 static size_t sum_smem_bytes(int L) {
-    return sizeof(double) * 4 * SUM_BPT * ACC_STRIDE + 12 * SUM_BPT * SUM_THREADS + sizeof(Entry) * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
+    return sizeof(double) * 4 * SUM_BPT * ACC_STRIDE + 20 * SUM_BPT * SUM_THREADS + sizeof(Entry) * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
 
 static int ensure_bytes(emrifd_handle *h, void **ptr, int64_t *cap, int64_t need, bool pinned_host = false) {
