@@ -719,7 +719,6 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ int s_list[SUM_THREADS];
     __shared__ int s_wcount[SUM_THREADS / 32];
-    __shared__ double s_red[3][SUM_THREADS / 32];
 
     const emrifd_walker_t wd = p.w[blockIdx.y];
     const int L = wd.L, K = wd.K, R = 2 * K + 4;
@@ -757,14 +756,40 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
     }
 
     const int nrec = K * MAXBR;
-    bool staged = false;
     const double val = p.g.val;
     const double *fpos = p.g.fpos;
 
+    // ---- does any work-list chunk touch this tile?  If so stage the shared tracks right away (knots, the four
+    //      track quads, reduced knot phases) so that the loads overlap the first record scan ----
     const long long *crng = p.chunk_rng + (long long)blockIdx.y * p.cpw * 2;
-    for (int base = 0, ch = 0; base < nrec; base += SUM_THREADS, ch++) {
+    bool any = false;
+    for (int ch = 0; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
+    if (any) {
+        const double *t = p.t + wd.knot_off;
+        for (int i = tid; i < L; i += SUM_THREADS) sT[i] = t[i];
+        for (int i = tid; i < L * 4; i += SUM_THREADS) {
+            const int jj = i >> 2, q = i & 3;
+            const double4 c = *reinterpret_cast<const double4 *>(coeff + ((long long)jj * R + 2 * K + q) * 4);
+            double *d = sQ + jj * 16 + q * 4;
+            d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
+            if (q >= 2) { // Phi/(2 pi) mod 1 as a double-double (hi, lo)
+                const double ph = c.x;
+                double a = ph * EMRIFD_INV2PI_HI;
+                double e = fma(ph, EMRIFD_INV2PI_HI, -a);
+                a -= rint(a);
+                e = fma(ph, EMRIFD_INV2PI_LO, e);
+                const double hi = a + e;
+                sU[jj * 4 + (q - 2) * 2 + 0] = hi;
+                sU[jj * 4 + (q - 2) * 2 + 1] = e - (hi - a);
+            }
+        }
+    }
+    __syncthreads();
+
+    bool used = false; // the entry cache holds a previous chunk that some warp may still be evaluating
+    for (int base = 0, ch = 0; any && base < nrec; base += SUM_THREADS, ch++) {
         if (crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0) continue; // block-uniform: nothing of this chunk touches the tile
-        // ---- ordered compaction of this chunk's records that overlap the tile ------------------
+        // ---- ordered compaction of this chunk's records that overlap the tile ----
         const int r = base + tid;
         bool pred = false;
         if (r < nrec) {
@@ -772,47 +797,25 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
             pred = (e0 >= s0) && ((s0 <= pos_hi && e0 >= pos_lo) || (s0 <= neg_hi && e0 >= neg_lo));
         }
         const unsigned bal = __ballot_sync(0xffffffffu, pred);
+        if (used) __syncthreads(); // every warp is done with the previous chunk's entries (and with s_wcount / s_list)
         if (lane == 0) s_wcount[wid] = __popc(bal);
         __syncthreads();
         int off = 0, count = 0;
 #pragma unroll
         for (int q = 0; q < SUM_THREADS / 32; q++) { const int c = s_wcount[q]; if (q < wid) off += c; count += c; }
         if (pred) s_list[off + __popc(bal & ((1u << lane) - 1))] = r;
-        if (count == 0) { __syncthreads(); continue; } // block-uniform
-        if (!staged) {
-            // stage the shared tracks once: knots, the four track quads, reduced knot phases
-            const double *t = p.t + wd.knot_off;
-            for (int i = tid; i < L; i += SUM_THREADS) sT[i] = t[i];
-            for (int i = tid; i < L * 4; i += SUM_THREADS) {
-                const int jj = i >> 2, q = i & 3;
-                const double4 c = *reinterpret_cast<const double4 *>(coeff + ((long long)jj * R + 2 * K + q) * 4);
-                double *d = sQ + jj * 16 + q * 4;
-                d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
-                if (q >= 2) { // Phi/(2 pi) mod 1 as a double-double (hi, lo)
-                    const double ph = c.x;
-                    double a = ph * EMRIFD_INV2PI_HI;
-                    double e = fma(ph, EMRIFD_INV2PI_HI, -a);
-                    a -= rint(a);
-                    e = fma(ph, EMRIFD_INV2PI_LO, e);
-                    const double hi = a + e;
-                    sU[jj * 4 + (q - 2) * 2 + 0] = hi;
-                    sU[jj * 4 + (q - 2) * 2 + 1] = e - (hi - a);
-                }
-            }
-            staged = true;
-        }
         __syncthreads();
-        if (tid < count) { // fill the entry cache
-            const int rr = s_list[tid];
-            const emrifd_branch_t b = br[rr];
+        if (count == 0) continue; // block-uniform
+        if (tid < count) { // fill the entry cache (ordered: deterministic summation order)
+            const emrifd_branch_t b = br[s_list[tid]];
             const int k = b.mode;
+            const int mi = marr[k], ni = narr[k];
+            const double2 yp = ylm[k], ym = ylm[K + k];
             Entry e;
             e.xa = b.xa; e.xb = b.xb;
-            e.mode = k; e.dir = b.dir; e.ja = b.ja; e.jb = b.jb;
-            const int mi = marr[k], ni = narr[k];
+            e.mode = b.mode; e.dir = b.dir; e.ja = b.ja; e.jb = b.jb;
             e.dm = (double)mi; e.dn = (double)ni;
             e.mirror = (mi > 0) && p.include_minus_m; e.pad = 0;
-            const double2 yp = ylm[k], ym = ylm[K + k];
             e.ypr = yp.x; e.ypi = yp.y; e.ymr = ym.x; e.ymi = ym.y;
             // tile-local covered ranges: +f bins have full-grid index zero + jt0 + lb, -f bins zero - jt0 - lb
             const long long ntile = jt1 - jt0 + 1;
@@ -845,6 +848,7 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
             ent[tid] = e;
         }
         __syncthreads();
+        used = true;
 
         // ---- evaluate: every thread walks its SUM_BPT consecutive bins along each listed branch ----
         if (nb > 0) {
@@ -963,18 +967,18 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                 }
             }
         }
-        __syncthreads();
     }
 
     // ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
-    __syncthreads(); // accumulators are read by other threads below (every chunk may have been skipped)
-    // Transposed read-out: in iteration i thread t finalises tile-local bin i*SUM_THREADS + t, so a warp stores
-    // 32 consecutive bins (512 B per array, fully coalesced) and reads the data stream the same way.
+    // Warp-local transposed read-out: a warp owns 32*SUM_BPT consecutive bins (its lanes' bins); in iteration i lane l
+    // finalises bin 32*i + l of them, so the warp stores 512 contiguous bytes per array and reads the data stream the
+    // same way.  Only __syncwarp is needed: warps that finish early read out while the others still evaluate.
+    __syncwarp();
     double a0 = 0, a1 = 0, a2 = 0;
     const int ntile = (int)(jt1 - jt0 + 1);
 #pragma unroll
     for (int i = 0; i < SUM_BPT; i++) {
-        const int lb = i * SUM_THREADS + tid;
+        const int lb = wid * (32 * SUM_BPT) + i * 32 + lane;
         if (lb >= ntile) continue;
         const long long j = jt0 + lb;
         const int own = lb / SUM_BPT, bb = lb % SUM_BPT;
@@ -1012,20 +1016,16 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
         }
     }
 #undef ACC
-    if (LIKE) {
+    if (LIKE) { // per-warp partial sums (no CTA barrier); like_finalize_kernel adds them in a fixed order
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             a0 += __shfl_down_sync(0xffffffffu, a0, o);
             a1 += __shfl_down_sync(0xffffffffu, a1, o);
             a2 += __shfl_down_sync(0xffffffffu, a2, o);
         }
-        if (lane == 0) { s_red[0][wid] = a0; s_red[1][wid] = a1; s_red[2][wid] = a2; }
-        __syncthreads();
-        if (tid == 0) {
-            double t0 = 0, t1 = 0, t2 = 0;
-            for (int q = 0; q < SUM_THREADS / 32; q++) { t0 += s_red[0][q]; t1 += s_red[1][q]; t2 += s_red[2][q]; }
-            double *o = p.partial + ((long long)blockIdx.y * gridDim.x + blockIdx.x) * 3;
-            o[0] = t0; o[1] = t1; o[2] = t2;
+        if (lane == 0) {
+            double *o = p.partial + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * (SUM_THREADS / 32) + wid) * 3;
+            o[0] = a0; o[1] = a1; o[2] = a2;
         }
     }
 }
@@ -1370,7 +1370,7 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     p.dw = (const double2 *)h->d_data; p.wf = h->d_wfac; p.n_data = h->n_data;
     const int64_t ntiles = (j_cnt + SUM_TILE - 1) / SUM_TILE;
     if (like) {
-        int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * 3 * ntiles * B);
+        int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * 3 * ntiles * (SUM_THREADS / 32) * B);
         if (rc) return rc;
         p.partial = h->d_partial;
     }
@@ -1395,7 +1395,7 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     if (like) {
-        like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, ntiles, like_out);
+        like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, ntiles * (SUM_THREADS / 32), like_out);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
     }
