@@ -291,3 +291,50 @@ def test_all_modes_high_mode_count(generator, oracle_quad, torch_cuda):
     assert (br_o["end"][br_o["end"] >= br_o["start"]] < zero).any()          # some harmonics live at negative frequency
     assert rel_err(out[0], hp_o) <= TOL_BIN and rel_err(out[1], hc_o) <= TOL_BIN
     assert np.array_equal(out[0] != 0, hp_o != 0)
+
+
+def test_full_size_one_year_grid(generator, oracle_quad, torch_cuda):
+    """BASELINE size: T = 1 yr, dt = 10 s, N = 3 155 815, a plunging eps = 1e-2 system (~1e7 evaluations).
+    Bins are independent, so the binary128 oracle is run on every 64th bin (an explicit, still uniform and
+    symmetric f_arr built from the same doubles) and compared with the full-grid GPU result at the coincident
+    frequencies; size-independent properties cover the rest."""
+    from emri_frequencydomainwaveforms_b200.utils.utility import get_p_at_t
+    from emri_frequencydomainwaveforms_b200 import engine, _lib
+    from helpers import grid_size
+    M, mu, e0, T, dt = 8e5, 20.0, 0.4, 1.0, 10.0
+    p0 = get_p_at_t(generator.inspiral_generator, 0.99 * T, [M, mu, 0.0, e0, 1.0], xtol=1e-9)
+    it = generator.prepare(M, mu, p0, e0, 1.1, -np.pi / 2, dist=1.0, Phi_phi0=1.0, Phi_r0=2.0, T=T, dt=dt, eps=1e-2)
+    it["T"], it["dt"] = T, dt
+    N = it["N"] = grid_size(it["t"], T, dt)
+    assert N == 3155815
+    s, out = _gpu_sum(it, torch_cuda)                       # full two-sided output [2, N]
+    zero, n = (N - 1) // 2, (N + 1) // 2
+    # (1) against binary128 on the strided grid
+    step = 64
+    fpos = (np.arange(n, dtype=np.float64) * (1.0 / (N * dt)))[::step]
+    Ns = 2 * len(fpos) - 1
+    hp_o, hc_o, *_ = oracle_waveform(oracle_quad, it, N=Ns, fpos=fpos)
+    sel = zero + step * np.arange(-(len(fpos) - 1), len(fpos))
+    scale = np.max(np.abs(out[0]))
+    assert np.max(np.abs(out[0][sel] - hp_o)) <= TOL_BIN * scale and np.max(np.abs(out[1][sel] - hc_o)) <= TOL_BIN * scale
+    assert np.array_equal(out[0][sel] != 0, hp_o != 0)
+    # (2) Hermitian symmetry of both polarisations, exactly (the mirror is written by the owning thread)
+    assert np.array_equal(out[0][:zero], np.conj(out[0][zero + 1:][::-1])) and np.array_equal(out[1][:zero], np.conj(out[1][zero + 1:][::-1]))
+    # (3) mask_positive == upper half; (4) linearity in the mode set (two disjoint halves add up to the whole)
+    _, pos = _gpu_sum(it, torch_cuda, mask_positive=True)
+    assert np.array_equal(pos, out[:, zero:])
+    K = len(it["m_arr"])
+    halves = []
+    for idx in (np.arange(0, K, 2), np.arange(1, K, 2)):
+        sub = dict(it, teuk_modes=np.ascontiguousarray(it["teuk_modes"][:, idx]), m_arr=it["m_arr"][idx], n_arr=it["n_arr"][idx],
+                   ylms=np.concatenate([it["ylms"][idx], it["ylms"][K + idx]]))
+        halves.append(_gpu_sum(sub, torch_cuda, mask_positive=True)[1])
+    assert np.max(np.abs(halves[0] + halves[1] - pos)) <= 1e-14 * scale
+    # (5) fused likelihood at full size: ll(injection) = 0 and <h|h> equals the materialised inner product
+    h = _lib.get_handle()
+    w = torch_cuda.full((2, n), 1.0e19, dtype=torch_cuda.float64, device=h.torch_device)
+    dw = (torch_cuda.as_tensor(pos).to(h.torch_device) * w).contiguous()
+    h.check(h.lib.emrifd_set_data(h.h, dw.data_ptr(), w.data_ptr(), n))
+    like = engine.run_loglike(engine.DeviceBatch(engine.PackedBatch([it]), h), N, 1.0 / (N * dt)).cpu().numpy()[0]
+    hh = 4.0 * float((dw.abs() ** 2).sum().item())
+    assert abs(like[0]) <= 1e-12 * hh and abs(like[2] - hh) <= 1e-12 * hh and abs(like[1] - hh) <= 1e-12 * hh
