@@ -7,6 +7,10 @@
 * ``get_fd_waveform_fromFD`` -- FDutils.py:105-139: call the generator, keep f >= 0, zero outside
   ``non_zero_mask``.  When the mask is exactly ``frequency >= 0`` the generator is asked for
   ``mask_positive=True`` so no boolean gather pass is needed.
+* ``get_convolution`` / ``get_fd_windowed`` -- FDutils.py:35-47,66-101 (the step right
+  after the path when ``window_flag=1``): the reference's ``convolve(hstack((a[1:], a)), b, 'valid')/len(b)`` is
+  the circular convolution (a (*) b)/N, an O(N^2) direct sum there; here it is three cuFFT calls
+  (``torch.fft``; a library FFT, as in the reference's own commented FFT variant FDutils.py:83-85).
 """
 import os
 
@@ -34,11 +38,41 @@ def get_sensitivity(f):
     return out.cpu().numpy() if np.ndim(f) else float(out.cpu().numpy())
 
 
+def _as_dev(x, dtype):
+    import torch
+    from . import _lib
+    dev = _lib.get_handle().torch_device
+    if torch.is_tensor(x):
+        return x.to(device=dev, dtype=dtype)
+    return torch.as_tensor(np.asarray(x), dtype=dtype).to(dev)
+
+
+def get_convolution(a, b):
+    """``convolve(hstack((a[1:], a)), b, mode='valid') / len(b)`` (FDutils.py:35-47) for equal-length 1D arrays:
+    out[k] = (1/N) sum_j a[(k - j) mod N] b[j], evaluated as ifft(fft(a) fft(b)) / N on the GPU."""
+    import torch
+    a = _as_dev(a, torch.complex128)
+    b = _as_dev(b, torch.complex128)
+    if a.ndim != 1 or a.shape != b.shape:
+        raise ValueError("get_convolution needs two 1D arrays of equal length.")
+    return torch.fft.ifft(torch.fft.fft(a) * torch.fft.fft(b)) / a.shape[0]
+
+
+def get_fd_windowed(signal, window, window_in_fd=False):
+    """Convolve the FD channels [h+, hx] with the DFT of a time-domain window (FDutils.py:66-101)."""
+    import torch
+    if window is None:
+        return [signal[0], signal[1]]
+    fft_window = _as_dev(window, torch.complex128)
+    if not window_in_fd:
+        fft_window = torch.fft.fft(fft_window)
+    cw = torch.conj(fft_window)
+    return [get_convolution(cw, signal[0]), get_convolution(cw, signal[1])]
+
+
 class get_fd_waveform_fromFD:
     def __init__(self, waveform_generator, positive_frequency_mask, dt, non_zero_mask=None, window=None,
                  window_in_fd=False):
-        if window is not None:
-            raise ValueError("Windowed FD convolution is not on this path yet (SURVEY.md section 8f rank 2).")
         self.waveform_generator = waveform_generator
         self.positive_frequency_mask = positive_frequency_mask
         self.non_zero_mask = non_zero_mask
@@ -51,11 +85,12 @@ class get_fd_waveform_fromFD:
 
     def __call__(self, *args, **kwargs):
         import torch
-        if self._is_upper_half and not kwargs.get("mask_positive", False):
+        if self.window is None and self._is_upper_half and not kwargs.get("mask_positive", False):
             ch1, ch2 = self.waveform_generator(*args, mask_positive=True, **kwargs)
         else:
-            chans = self.waveform_generator(*args, **kwargs)
-            mask = torch.as_tensor(np.asarray(self.positive_frequency_mask), device=chans[0].device)
+            chans = get_fd_windowed(self.waveform_generator(*args, **kwargs), self.window, window_in_fd=self.window_in_fd)
+            pm = self.positive_frequency_mask
+            mask = torch.as_tensor(np.asarray(pm.cpu() if hasattr(pm, "cpu") else pm), device=chans[0].device)
             ch1, ch2 = chans[0][mask], chans[1][mask]
         if self.non_zero_mask is not None:
             nz = torch.as_tensor(np.asarray(self.non_zero_mask.cpu() if hasattr(self.non_zero_mask, "cpu")

@@ -338,3 +338,32 @@ def test_full_size_one_year_grid(generator, oracle_quad, torch_cuda):
     like = engine.run_loglike(engine.DeviceBatch(engine.PackedBatch([it]), h), N, 1.0 / (N * dt)).cpu().numpy()[0]
     hh = 4.0 * float((dw.abs() ** 2).sum().item())
     assert abs(like[0]) <= 1e-12 * hh and abs(like[2] - hh) <= 1e-12 * hh and abs(like[1] - hh) <= 1e-12 * hh
+
+
+def test_fd_window_convolution(torch_cuda):
+    """FDutils.get_convolution / get_fd_windowed (the step after the path when window_flag=1): FFT evaluation
+    == the reference's direct 'valid' convolution, and == DFT(window * IDFT(signal)) (FDutils.py:83-85)."""
+    from scipy.signal import convolve
+    from emri_frequencydomainwaveforms_b200.fdutils import get_convolution, get_fd_windowed, get_fd_waveform_fromFD
+    rng = np.random.default_rng(8)
+    n = 257
+    a = rng.normal(size=n) + 1j * rng.normal(size=n)
+    b = rng.normal(size=n) + 1j * rng.normal(size=n)
+    ref = convolve(np.hstack((a[1:], a)), b, mode="valid") / len(b)       # FDutils.py:47 verbatim
+    got = get_convolution(a, b).cpu().numpy()
+    assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))
+    window = np.hanning(n)
+    sig = [np.fft.fftshift(a), np.fft.fftshift(b)]
+    out = get_fd_windowed(sig, window)
+    ref0 = convolve(np.hstack((np.conj(np.fft.fft(window))[1:], np.conj(np.fft.fft(window)))), sig[0], mode="valid") / n
+    assert np.max(np.abs(out[0].cpu().numpy() - ref0)) <= 1e-12 * np.max(np.abs(ref0))
+    assert get_fd_windowed(sig, None)[1] is sig[1]
+
+    class Gen:                                                             # a generator returning [h+, hx] on the two-sided grid
+        def __call__(self, *args, **kw):
+            return [torch_cuda.as_tensor(sig[0]).cuda(), torch_cuda.as_tensor(sig[1]).cuda()]
+
+    freq = np.fft.fftshift(np.fft.fftfreq(n, 10.0))
+    ad = get_fd_waveform_fromFD(Gen(), freq >= 0.0, 10.0, window=window)
+    ch = ad()
+    assert ch[0].shape[0] == (n + 1) // 2 and np.max(np.abs(ch[0].cpu().numpy() - ref0[freq >= 0.0])) <= 1e-12 * np.max(np.abs(ref0))
