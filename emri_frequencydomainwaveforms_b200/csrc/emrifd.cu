@@ -646,24 +646,21 @@ __device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f
         double p0 = fi * tj;
         const double e0 = fma(fi, tj, -p0);
         p0 -= rint(p0);
-        double cyc = p0 - mu_hi;
-        cyc -= rint(cyc);
+        // |p0 - mu_hi| <~ 20 and |poly| <~ 1e4 cycles: summing them costs <= 1e-12 cycles of rounding, and the
+        // quarter-turn reduction inside sincos_cycles is exact for |c| < 2^20
         const double poly = fma(fi, xi, -EMRIFD_INV2PI_HI * fma(dm, pp, dn * pr));
-        cyc += (poly - rint(poly)) + (e0 - mu_lo);
+        const double cyc = ((p0 - mu_hi) + (e0 - mu_lo)) + poly;
         sincos_cycles(cyc, sn[i], cs[i]);
     }
 #pragma unroll
     for (int i = 0; i < W; i++)
         if (!(uu[i] <= 0.0009765625)) spa_fix(fd[i], fdd[i], s[i], uu[i], re[i], im[i]);
-    const double ypr = E.ypr, ypi = E.ypi;
+    const double ypr = E.ypr, ypi = E.ypi, sdir = (double)E.dir;
     const bool mirror = E.mirror;
 #pragma unroll
     for (int i = 0; i < W; i++) {
-        // G = e^{+-i 3pi/4} (re + i im)
-        const double r2 = 0.7071067811865476;
-        const double gre = (-re[i] - im[i]) * r2;
-        double gim = (re[i] - im[i]) * r2;
-        if (fd[i] < 0.0) gim = -gim;
+        // A * R (conjugated on falling branches); the e^{+-i 3pi/4} of G lives in the entry's harmonics
+        const double gre = re[i], gim = sdir * im[i];
         const double agr = ReA[i] * gre - ImA[i] * gim, agi = ReA[i] * gim + ImA[i] * gre;
         Cr[i] = agr * cs[i] - agi * sn[i];
         Ci[i] = agr * sn[i] + agi * cs[i];
@@ -816,7 +813,13 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
             e.mode = b.mode; e.dir = b.dir; e.ja = b.ja; e.jb = b.jb;
             e.dm = (double)mi; e.dn = (double)ni;
             e.mirror = (mi > 0) && p.include_minus_m; e.pad = 0;
-            e.ypr = yp.x; e.ypi = yp.y; e.ymr = ym.x; e.ymi = ym.y;
+            // G = e^{i 3pi/4} R/sqrt|fdot| on rising branches and its conjugate on falling ones (sign fdot == dir on a
+            // monotone branch): fold the constant rotation into Y_lm (direct term) and its conjugate into Y_l-m (mirrored term)
+            {
+                const double r2 = 0.7071067811865476, rr_ = -r2, ri_ = b.dir > 0 ? r2 : -r2;
+                e.ypr = yp.x * rr_ - yp.y * ri_; e.ypi = yp.x * ri_ + yp.y * rr_;
+                e.ymr = ym.x * rr_ + ym.y * ri_; e.ymi = ym.y * rr_ - ym.x * ri_;
+            }
             // tile-local covered ranges: +f bins have full-grid index zero + jt0 + lb, -f bins zero - jt0 - lb
             const long long ntile = jt1 - jt0 + 1;
             long long lo = b.start - pos_lo, hi = b.end - pos_lo;
