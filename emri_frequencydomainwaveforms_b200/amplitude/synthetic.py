@@ -34,18 +34,31 @@ class SyntheticAmplitude:
         self.unique_m = self.m_arr[first]
         self.inverse_lm = inverse
 
+    def _tables(self):
+        if not hasattr(self, "_cmode"):
+            l, m, n = self.l_arr.astype(np.float64), self.m_arr.astype(np.float64), self.n_arr.astype(np.float64)
+            self._cmode = (0.6 ** (l - 2.0)) / (1.0 + (l - m)) * np.exp(1j * (0.4 * l - 0.25 * m + 0.15 * n))
+            self._lidx = (self.l_arr - 2).astype(np.intp)
+            self._midx = self.m_arr.astype(np.intp)
+            self._nidx = (self.n_arr + self.nmax).astype(np.intp)
+        return self._cmode, self._lidx, self._midx, self._nidx
+
     def __call__(self, p, e, *args, specific_modes=None, **kwargs):
-        p = np.atleast_1d(np.asarray(p, dtype=np.float64))[:, None]
-        e = np.atleast_1d(np.asarray(e, dtype=np.float64))[:, None]
-        l = self.l_arr[None, :].astype(np.float64)
-        m = self.m_arr[None, :].astype(np.float64)
-        n = self.n_arr[None, :].astype(np.float64)
-        base = (1.0 / p) * p ** (-(l - 2.0) / 2.0) * (0.6 ** (l - 2.0)) / (1.0 + (l - m))
-        n0 = 2.5 * e / np.sqrt(1.0 - e) * (1.0 + 0.2 * m)
+        """A_lmn(p, e) = c_lm p^{-l/2} exp(-(n - n0)^2 / 2 sigma^2) exp(i (0.4 l - 0.25 m + 0.15 n + 8/p + e n / 6)),
+        n0 = 2.5 e (1 + 0.2 m)/sqrt(1 - e), sigma = 0.35 + 3.5 e -- evaluated through small separable tables
+        ([L, l], [L, m, n], [L, n]) that are gathered per mode."""
+        p = np.atleast_1d(np.asarray(p, dtype=np.float64))
+        e = np.atleast_1d(np.asarray(e, dtype=np.float64))
+        cmode, lidx, midx, nidx = self._tables()
+        lv = np.arange(2, self.lmax + 1, dtype=np.float64)
+        mv = np.arange(0, self.lmax + 1, dtype=np.float64)
+        nv = np.arange(-self.nmax, self.nmax + 1, dtype=np.float64)
+        P = p[:, None] ** (-lv[None, :] / 2.0)                                           # [L, l]
+        n0 = (2.5 * e / np.sqrt(1.0 - e))[:, None] * (1.0 + 0.2 * mv)[None, :]           # [L, m]
         sig = 0.35 + 3.5 * e
-        env = np.exp(-((n - n0) ** 2) / (2.0 * sig * sig))
-        ph = 0.4 * l - 0.25 * m + 0.15 * n + 8.0 / p + 0.5 * e * n / 3.0
-        out = base * env * np.exp(1j * ph)
+        ENV = np.exp(-((nv[None, None, :] - n0[:, :, None]) ** 2) / (2.0 * sig * sig)[:, None, None])   # [L, m, n]
+        EPH = np.exp(1j * ((e / 6.0)[:, None] * nv[None, :] + (8.0 / p)[:, None]))      # [L, n]
+        out = P[:, lidx] * ENV[:, midx, nidx] * (EPH[:, nidx] * cmode[None, :])
         if specific_modes is not None:
             res = {}
             for (ll, mm, nn) in specific_modes:

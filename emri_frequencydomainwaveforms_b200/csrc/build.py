@@ -16,7 +16,21 @@ def needs_build():
     return any(os.path.getmtime(d) > mt for d in DEPS)
 
 
+HOST_SRC = os.path.join(HERE, "emrihost.c")
+HOST_OUT = os.path.join(HERE, "libemrihost.so")
+
+
+def build_host(force=False):
+    """Native host-side producers (trajectory ODE, Schwarzschild frequencies): gcc + OpenMP, generic x86-64-v3."""
+    if not force and os.path.exists(HOST_OUT) and os.path.getmtime(HOST_OUT) >= os.path.getmtime(HOST_SRC):
+        return HOST_OUT
+    cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
+    subprocess.check_call([cc, "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared", "-Wall", HOST_SRC, "-o", HOST_OUT, "-lm"])
+    return HOST_OUT
+
+
 def build(force=False, verbose=False):
+    build_host(force)
     if not force and not needs_build():
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")

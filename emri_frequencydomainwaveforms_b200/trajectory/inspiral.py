@@ -13,6 +13,7 @@ it is an input producer, not part of the accelerated path.  Any object returning
 import numpy as np
 from scipy.integrate import solve_ivp
 
+from .. import _hostlib
 from ..utils.constants import MTSUN_SI, YRSID_SI
 from ..utils.utility import schwarzschild_frequencies
 
@@ -37,10 +38,11 @@ class EMRIInspiral:
     ``(t, p, e, x, Phi_phi, Phi_theta, Phi_r)`` with ``t`` in seconds starting at 0.
     """
 
-    def __init__(self, func="SchwarzEccFlux", rtol=1e-12, atol=1e-14, max_init_len=1000, **kwargs):
+    def __init__(self, func="SchwarzEccFlux", rtol=1e-12, atol=1e-14, max_init_len=1000, use_native=True, **kwargs):
         if func != "SchwarzEccFlux":
             raise ValueError("Only func='SchwarzEccFlux' is available on this path.")
         self.rtol, self.atol, self.max_init_len = rtol, atol, max_init_len
+        self.use_native = use_native   # csrc/emrihost.c (same ODE, same step control); False = SciPy twin
 
     def __call__(self, M, mu, a, p0, e0, x0, *args, Phi_phi0=0.0, Phi_theta0=0.0, Phi_r0=0.0,
                  T=1.0, dt=10.0, **kwargs):
@@ -54,6 +56,15 @@ class EMRIInspiral:
             raise ValueError("e0 must be in [0, 1).")
         if p0 < 6.0 + 2.0 * e0 + DIST_TO_SEPARATRIX:
             raise ValueError("p0 is inside the separatrix buffer (p0 < 6 + 2 e0 + 0.1).")
+        if self.use_native and _hostlib.load() is not None:
+            out, lens = _hostlib.trajectory_batch(M, mu, p0, e0, Phi_phi0, Phi_r0, T, self.rtol, self.atol, self.max_init_len)
+            n = int(lens[0])
+            if n == -2:
+                raise ValueError("trajectory longer than max_init_len")
+            if n < 2:
+                raise ValueError("trajectory integration failed")
+            t, p, e, Pp, Pr = (out[i][0, :n].copy() for i in range(5))
+            return (t, p, e, np.ones_like(t), Pp, Pp.copy(), Pr)
         q = mu / M
         Msec = M * MTSUN_SI
         t_end = T * YRSID_SI / Msec

@@ -21,13 +21,29 @@ class ModeSelector:
         zero_up = self.num_m_zero_up
         full = np.concatenate([teuk_modes, np.conj(teuk_modes[:, self.m0mask])], axis=1)
         power = np.abs(full * ylms[None, :]) ** 2
-        inds_sort = np.argsort(power, axis=1)[:, ::-1]
-        power_sorted = np.take_along_axis(power, inds_sort, axis=1)
-        cumsum = np.cumsum(power_sorted, axis=1)
-        thresh = cumsum[:, -1][:, None] * (1.0 - eps)
-        keep_sorted = np.ones_like(cumsum, dtype=bool)
-        keep_sorted[:, 1:] = cumsum[:, :-1] < thresh
-        picked = np.unique(inds_sort[keep_sorted])
+        picked = None
+        ntot = power.shape[1]
+        ktop = 768
+        if ntot > 4 * ktop:
+            # only the strongest few hundred harmonics can be picked: sort those, and check that they reach the threshold
+            part = np.argpartition(power, ntot - ktop, axis=1)[:, ntot - ktop:]
+            psub = np.take_along_axis(power, part, axis=1)
+            order = np.argsort(psub, axis=1)[:, ::-1]
+            inds_top = np.take_along_axis(part, order, axis=1)
+            cs = np.cumsum(np.take_along_axis(psub, order, axis=1), axis=1)
+            thresh = power.sum(axis=1)[:, None] * (1.0 - eps)
+            if np.all(cs[:, -1] >= thresh):
+                keep_sorted = np.ones_like(cs, dtype=bool)
+                keep_sorted[:, 1:] = cs[:, :-1] < thresh
+                picked = np.unique(inds_top[keep_sorted])
+        if picked is None:
+            inds_sort = np.argsort(power, axis=1)[:, ::-1]
+            power_sorted = np.take_along_axis(power, inds_sort, axis=1)
+            cumsum = np.cumsum(power_sorted, axis=1)
+            thresh = cumsum[:, -1][:, None] * (1.0 - eps)
+            keep_sorted = np.ones_like(cumsum, dtype=bool)
+            keep_sorted[:, 1:] = cumsum[:, :-1] < thresh
+            picked = np.unique(inds_sort[keep_sorted])
         # fold -m picks onto their +m partner
         m_nonzero_idx = np.where(self.m0mask)[0]
         neg = picked >= zero_up

@@ -154,3 +154,31 @@ def test_transform_container_contract():
     out = fill_and_transform(p6, fill_inds=np.array([2, 5, 6, 7, 8, 9, 10, 12]),
                              fill_values=np.array([0.0, 1.0, 2.45, np.pi / 3, np.pi / 3, np.pi / 3, np.pi / 3, 0.0]))
     assert np.allclose(out, p14, rtol=1e-15)
+
+
+def test_native_host_producers_match_python_twins():
+    """csrc/emrihost.c (native trajectory ODE + Schwarzschild frequencies) against the SciPy implementations."""
+    from scipy.interpolate import CubicSpline
+    from emri_frequencydomainwaveforms_b200 import _hostlib
+    from emri_frequencydomainwaveforms_b200.csrc import build
+    from emri_frequencydomainwaveforms_b200.trajectory.inspiral import EMRIInspiral
+    from emri_frequencydomainwaveforms_b200.utils.utility import schwarzschild_frequencies
+    build.build_host()
+    assert _hostlib.load() is not None
+    rng = np.random.default_rng(0)
+    e = rng.uniform(0, 0.75, 500)
+    p = 6 + 2 * e + 0.1 + rng.uniform(0, 12, 500)
+    a, b = schwarzschild_frequencies(p, e, native=True)
+    ra, rb = schwarzschild_frequencies(p, e, native=False)
+    assert np.max(np.abs(a / ra - 1)) < 5e-15 and np.max(np.abs(b / rb - 1)) < 5e-15
+    nat, py = EMRIInspiral(use_native=True), EMRIInspiral(use_native=False)
+    for (M, mu, p0, e0, T) in [(1e6, 10.0, 12.0, 0.35, 1.0), (1e6, 50.0, 9.0, 0.3, 0.25), (1e5, 1.0, 15.0, 0.6, 0.5)]:
+        tn, pn, en, _, Ppn, _, Prn = nat(M, mu, 0.0, p0, e0, 1.0, Phi_phi0=0.3, Phi_r0=1.1, T=T)
+        tp, pp, ep, _, Ppp, _, Prp = py(M, mu, 0.0, p0, e0, 1.0, Phi_phi0=0.3, Phi_r0=1.1, T=T)
+        assert abs(len(tn) - len(tp)) <= 2 and tn[0] == 0.0 and np.all(np.diff(tn) > 0)
+        assert abs(tn[-1] - tp[-1]) <= 1e-9 * tp[-1]                       # same end (T or the separatrix buffer)
+        assert abs(Ppn[-1] - Ppp[-1]) <= 1e-9 * abs(Ppp[-1]) and abs(Prn[-1] - Prp[-1]) <= 1e-9 * abs(Prp[-1])
+        tt = np.linspace(0, min(tn[-1], tp[-1]), 500)
+        assert np.max(np.abs(CubicSpline(tn, pn)(tt) - CubicSpline(tp, pp)(tt))) < 1e-7      # different knots, same orbit
+    with pytest.raises(ValueError):
+        nat(1e6, 10.0, 0.0, 6.5, 0.3, 1.0)
