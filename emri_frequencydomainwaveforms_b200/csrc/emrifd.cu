@@ -296,14 +296,21 @@ __device__ __forceinline__ void push_sub(emrifd_branch_t *br, int &nb, int &over
     br[nb++] = b;
 }
 
-__global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *status) {
-    extern __shared__ double sm[]; // t[L] | (f_phi quad, f_r quad)[L][8]: staged once, the per-mode loop reads smem only
+// Two phases per CTA (a group of `mpc` modes of one walker):
+//   A  one thread per (mode, segment): roots of fdot inside the segment and f there (sqrt / divisions in parallel);
+//   B  one thread per mode: merge the sub-intervals into monotone branches and turn their frequency ranges into bin
+//      ranges.  Both phases use exactly the oracle's operations (individually rounded), so the work-list is bit-exact.
+__global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *status, int mpc) {
+    extern __shared__ double sm[]; // t[L] | (f_phi quad, f_r quad)[L][8] | xr[mpc][L][2] | Fx[mpc][L][2] | nr[mpc][L]
     const emrifd_walker_t wd = p.w[blockIdx.y];
     const int L = wd.L, K = wd.K, R = 2 * K + 4;
-    if ((int)(blockIdx.x * SEG_THREADS) >= K) return;
+    const int k0 = blockIdx.x * mpc;
+    if (k0 >= K) return;
+    const int nm = (K - k0) < mpc ? (K - k0) : mpc;
     const double *t = p.t + wd.knot_off;
     const double *coeff = p.coeff + wd.coeff_off;
-    double *st = sm, *sq = sm + L;
+    double *st = sm, *sq = sm + L, *sxr = sm + 9 * L, *sFx = sxr + 2 * mpc * L;
+    int *snr = reinterpret_cast<int *>(sFx + 2 * mpc * L);
     for (int i = threadIdx.x; i < L; i += SEG_THREADS) st[i] = t[i];
     for (int i = threadIdx.x; i < 2 * L; i += SEG_THREADS) {
         const int jj = i >> 1, q = i & 1;
@@ -312,8 +319,45 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *
         d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
     }
     __syncthreads();
-    const int k = blockIdx.x * SEG_THREADS + threadIdx.x;
-    if (k >= K) return;
+    // ---- phase A ----
+    for (int item = threadIdx.x; item < nm * (L - 1); item += SEG_THREADS) {
+        const int kl = item / (L - 1), j = item - kl * (L - 1);
+        const double dm = (double)p.m[wd.mode_off + k0 + kl], dn = (double)p.n[wd.mode_off + k0 + kl];
+        const double *c = sq + j * 8;
+        const double hj = rsub(st[j + 1], st[j]);
+        const double c0 = radd(rmul(dm, c[0]), rmul(dn, c[4]));
+        const double c1 = radd(rmul(dm, c[1]), rmul(dn, c[5]));
+        const double c2 = radd(rmul(dm, c[2]), rmul(dn, c[6]));
+        const double c3 = radd(rmul(dm, c[3]), rmul(dn, c[7]));
+        double xr[2] = {0.0, 0.0};
+        int nr = 0;
+        const double qa = rmul(3.0, c3), qb = rmul(2.0, c2), qc = c1;
+        if (qa == 0.0) {
+            if (qb != 0.0) { double r0 = rdiv(-qc, qb); if (r0 > 0.0 && r0 < hj) xr[nr++] = r0; }
+        } else {
+            double disc = rsub(rmul(qb, qb), rmul(rmul(4.0, qa), qc));
+            if (disc >= 0.0) {
+                double sqd = __dsqrt_rn(disc);
+                double qq = (qb >= 0.0) ? rmul(-0.5, radd(qb, sqd)) : rmul(-0.5, rsub(qb, sqd));
+                double r0 = rdiv(qq, qa);
+                double r1 = (qq != 0.0) ? rdiv(qc, qq) : r0;
+                if (r0 > r1) { double tmp = r0; r0 = r1; r1 = tmp; }
+                if (r0 > 0.0 && r0 < hj) xr[nr++] = r0;
+                if (r1 > 0.0 && r1 < hj && r1 != r0) xr[nr++] = r1;
+            }
+        }
+        const int o = (kl * L + j) * 2;
+        snr[kl * L + j] = nr;
+        for (int q = 0; q < 2; q++) {
+            const double x = xr[q];
+            sxr[o + q] = x;
+            sFx[o + q] = radd(c0, rmul(x, radd(c1, rmul(x, radd(c2, rmul(x, c3))))));
+        }
+    }
+    __syncthreads();
+    // ---- phase B ----
+    if ((int)threadIdx.x >= nm) return;
+    const int kl = threadIdx.x, k = k0 + kl;
     const int mi = p.m[wd.mode_off + k], ni = p.n[wd.mode_off + k];
     const double dm = (double)mi, dn = (double)ni;
     emrifd_branch_t *out = p.br + (wd.mode_off + k) * MAXBR;
@@ -323,39 +367,20 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *
         br[q].start = 0; br[q].end = -1; br[q].xa = 0; br[q].xb = 0; br[q].Fa = 0; br[q].Fb = 0;
     }
     int nb = 0, overflow = 0;
+    double Fk = radd(rmul(dm, sq[0]), rmul(dn, sq[4]));
     for (int j = 0; j < L - 1; j++) {
         const double *c = sq + j * 8;
         const double hj = rsub(st[j + 1], st[j]);
-        const double c0 = radd(rmul(dm, c[0]), rmul(dn, c[4]));
-        const double c1 = radd(rmul(dm, c[1]), rmul(dn, c[5]));
-        const double c2 = radd(rmul(dm, c[2]), rmul(dn, c[6]));
-        const double c3 = radd(rmul(dm, c[3]), rmul(dn, c[7]));
         const double Fnext = radd(rmul(dm, c[8]), rmul(dn, c[12]));
-        double xr[2];
-        int nr = 0;
-        const double qa = rmul(3.0, c3), qb = rmul(2.0, c2), qc = c1;
-        if (qa == 0.0) {
-            if (qb != 0.0) { double r0 = rdiv(-qc, qb); if (r0 > 0.0 && r0 < hj) xr[nr++] = r0; }
-        } else {
-            double disc = rsub(rmul(qb, qb), rmul(rmul(4.0, qa), qc));
-            if (disc >= 0.0) {
-                double sq = __dsqrt_rn(disc);
-                double qq = (qb >= 0.0) ? rmul(-0.5, radd(qb, sq)) : rmul(-0.5, rsub(qb, sq));
-                double r0 = rdiv(qq, qa);
-                double r1 = (qq != 0.0) ? rdiv(qc, qq) : r0;
-                if (r0 > r1) { double tmp = r0; r0 = r1; r1 = tmp; }
-                if (r0 > 0.0 && r0 < hj) xr[nr++] = r0;
-                if (r1 > 0.0 && r1 < hj && r1 != r0) xr[nr++] = r1;
-            }
-        }
-        double xa = 0.0, Fa = c0;
+        const int nr = snr[kl * L + j];
+        double xa = 0.0, Fa = Fk;
         for (int q = 0; q < nr; q++) {
-            double x = xr[q];
-            double Fx = radd(c0, rmul(x, radd(c1, rmul(x, radd(c2, rmul(x, c3))))));
+            const double x = sxr[(kl * L + j) * 2 + q], Fx = sFx[(kl * L + j) * 2 + q];
             push_sub(br, nb, overflow, k, j, xa, Fa, x, Fx);
             xa = x; Fa = Fx;
         }
         push_sub(br, nb, overflow, k, j, xa, Fa, hj, Fnext);
+        Fk = Fnext;
     }
     if (nb > 0) br[nb - 1].closed_end = 1;
     long long evals = 0;
@@ -665,16 +690,16 @@ __device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f
         Cr[i] = agr * cs[i] - agi * sn[i];
         Ci[i] = agr * sn[i] + agi * cs[i];
         const int id = id0 + i * ACC_STRIDE;
-        acc[id] += ypr * Cr[i] - ypi * Ci[i];
-        acc[id + SUM_BPT * ACC_STRIDE] += ypr * Ci[i] + ypi * Cr[i];
+        acc[id] = fma(ypr, Cr[i], fma(-ypi, Ci[i], acc[id]));
+        acc[id + SUM_BPT * ACC_STRIDE] = fma(ypr, Ci[i], fma(ypi, Cr[i], acc[id + SUM_BPT * ACC_STRIDE]));
     }
     if (mirror) {
         const double ymr = E.ymr, ymi = E.ymi;
 #pragma unroll
         for (int i = 0; i < W; i++) {
             const int im_ = im0 + i * ACC_STRIDE;
-            acc[im_] += ymr * Cr[i] + ymi * Ci[i];
-            acc[im_ + SUM_BPT * ACC_STRIDE] += ymi * Cr[i] - ymr * Ci[i];
+            acc[im_] = fma(ymr, Cr[i], fma(ymi, Ci[i], acc[im_]));
+            acc[im_ + SUM_BPT * ACC_STRIDE] = fma(ymi, Cr[i], fma(-ymr, Ci[i], acc[im_ + SUM_BPT * ACC_STRIDE]));
         }
     }
 }
@@ -1236,7 +1261,7 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaFuncSetAttribute(spline_build_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(spline_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(spline_build_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, 9 * 8 * EMRIFD_MAX_KNOTS);
+    cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -1332,8 +1357,12 @@ static int batch_segment_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, co
     p.n_eval = (long long *)n_eval;
     p.g.N = N; p.g.zero = (N - 1) / 2; p.g.val = val; p.g.fpos = fpos;
     if (n_eval) CUDA_TRY(h, cudaMemsetAsync(n_eval, 0, sizeof(int64_t) * 2 * (size_t)B, h->stream));
-    dim3 grid((unsigned)((Kmax + SEG_THREADS - 1) / SEG_THREADS), (unsigned)B);
-    segment_kernel<<<grid, SEG_THREADS, sizeof(double) * 9 * (size_t)Lmax, h->stream>>>(p, h->d_status);
+    // modes per CTA: as many as fit next to the staged tracks (8 at L <= ~600, fewer for very long trajectories)
+    int mpc = (int)((h->max_dyn_smem - 72 * (int64_t)Lmax) / (36 * (int64_t)Lmax));
+    mpc = mpc > 8 ? 8 : mpc;
+    if (mpc < 1) return set_err(h, EMRIFD_ERR_TOO_MANY_KNOTS, "trajectory too long for the segmentation kernel");
+    dim3 grid((unsigned)((Kmax + mpc - 1) / mpc), (unsigned)B);
+    segment_kernel<<<grid, SEG_THREADS, (size_t)(72 + 36 * mpc) * (size_t)Lmax, h->stream>>>(p, h->d_status, mpc);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
