@@ -103,17 +103,19 @@ def run_waveform(db, N, val=0.0, fpos_dev=None, include_minus_m=True, mask_posit
     import torch
     h, pb = db.handle, db.pb
     n_out = (N + 1) // 2 if mask_positive else N
-    pb.walkers["out_off"] = np.arange(pb.B, dtype=np.int64) * n_out
-    hp = torch.empty((pb.B, n_out), dtype=torch.complex128, device=h.torch_device)
-    hc = torch.empty((pb.B, n_out), dtype=torch.complex128, device=h.torch_device)
+    # one [B, 2, n_out] buffer: walker w writes h+ at w*2*n_out and hx n_out further (= vstack((h+, hx)) per walker)
+    pb.walkers["out_off"] = np.arange(pb.B, dtype=np.int64) * (2 * n_out)
+    out = torch.empty((pb.B, 2, n_out), dtype=torch.complex128, device=h.torch_device)
+    hp, hc = out[:, 0, :], out[:, 1, :]
     like_out = torch.empty((pb.B, 3), dtype=torch.float64, device=h.torch_device) if like else None
     flags = (INCLUDE_MINUS_M if include_minus_m else 0) | (MASK_POSITIVE if mask_positive else 0)
     rc = h.lib.emrifd_fd_waveform_batch(
         h.h, pb.walkers.ctypes.data, pb.B, db.t.data_ptr(), db.teuk.data_ptr(), db.f_phi.data_ptr(),
         db.f_r.data_ptr(), db.Phi_phi.data_ptr(), db.Phi_r.data_ptr(), db.m.data_ptr(), db.n.data_ptr(),
         db.ylm.data_ptr(), int(N), float(val), _lib.ptr(fpos_dev), flags, db.coeff.data_ptr(),
-        db.branches.data_ptr(), hp.data_ptr(), hc.data_ptr(), _lib.ptr(like_out))
+        db.branches.data_ptr(), out.data_ptr(), out.data_ptr() + 16 * n_out, _lib.ptr(like_out))
     h.check(rc)
+    db.last_out = out   # [B, 2, n_out]: row w is vstack((h+, hx)) of walker w
     return hp, hc, like_out
 
 

@@ -40,6 +40,13 @@ class FDInterpolatedModeSum:
     def handle(self):
         return _lib.get_handle(self._device)
 
+    def __getstate__(self):
+        # picklable by reconstruction (the reference forks pool workers that each own a generator, emri_pe.py:545):
+        # device buffers and the handle are per process and are rebuilt lazily
+        d = dict(self.__dict__)
+        d.update(frequency=None, waveform=None, last_batch=None)
+        return d
+
     # -- few.utils.baseclasses.SummationBase.__call__ (output sizing) ------------
     def __call__(self, t, *args, T=1.0, dt=10.0, **kwargs):
         t_host = _np(t)
@@ -94,5 +101,5 @@ class FDInterpolatedModeSum:
                                         mask_positive=mask_positive)
         h.status()
         self.last_batch = db
-        self.waveform = torch.cat([hp, hc], dim=0)   # vstack((h+, hx)): [2, N] or [2, (N+1)/2]
+        self.waveform = db.last_out[0]   # vstack((h+, hx)): [2, N] or [2, (N+1)/2], written in place by the kernel
         return self.waveform

@@ -367,3 +367,36 @@ def test_fd_window_convolution(torch_cuda):
     ad = get_fd_waveform_fromFD(Gen(), freq >= 0.0, 10.0, window=window)
     ch = ad()
     assert ch[0].shape[0] == (n + 1) // 2 and np.max(np.abs(ch[0].cpu().numpy() - ref0[freq >= 0.0])) <= 1e-12 * np.max(np.abs(ref0))
+
+
+def test_long_trajectory_paths(generator, oracle_quad, torch_cuda):
+    """L = 700 knots: the spline kernel's non-tiled variant (forward-sweep intermediates parked in the output), fewer
+    modes per CTA in the segmentation kernel and a 118 KB track staging area in the mode-sum kernel."""
+    from scipy.interpolate import CubicSpline
+    from emri_frequencydomainwaveforms_b200.utils.utility import schwarzschild_frequencies
+    from emri_frequencydomainwaveforms_b200.utils.constants import MTSUN_SI
+    it = make_item(generator, "plunge", dt=40.0)
+    t0 = it["t"]
+    # refine the knot vector (geometric mix keeps the clustering near the end), re-evaluate everything on it
+    u = np.linspace(0.0, 1.0, 700)
+    t = np.interp(u, np.linspace(0.0, 1.0, len(t0)), t0)
+    p, e = CubicSpline(t0, it["p"])(t), np.clip(CubicSpline(t0, it["e"])(t), 0.0, None)
+    K = len(it["m_arr"])
+    amp = generator.amplitude_generator
+    idx = [int(np.where((amp.l_arr == l) & (amp.m_arr == m) & (amp.n_arr == n))[0][0]) for l, m, n in zip(it["l_arr"], it["m_arr"], it["n_arr"])]
+    om_phi, om_r = schwarzschild_frequencies(p, e)
+    long_it = dict(it, t=t, p=p, e=e, teuk_modes=np.ascontiguousarray(amp(p, e)[:, idx]), Phi_phi=CubicSpline(t0, it["Phi_phi"])(t),
+                   Phi_r=CubicSpline(t0, it["Phi_r"])(t), f_phi=om_phi / (2 * np.pi * it["M"] * MTSUN_SI), f_r=om_r / (2 * np.pi * it["M"] * MTSUN_SI))
+    assert long_it["teuk_modes"].shape == (700, K)
+    hp_o, hc_o, coeff_o, br_o, nbr_o = oracle_waveform(oracle_quad, long_it)
+    s, out = _gpu_sum(long_it, torch_cuda)
+    assert np.array_equal(s.last_batch.coeff_host(0), coeff_o)
+    br_g = s.last_batch.branches_host()
+    for key in ("dir", "ja", "jb", "start", "end", "xa", "xb", "Fa", "Fb"):
+        assert np.array_equal(br_g[key], br_o[key]), key
+    assert rel_err(out[0], hp_o) <= TOL_BIN and rel_err(out[1], hc_o) <= TOL_BIN
+    # beyond EMRIFD_MAX_KNOTS the C-ABI refuses with an error code (-> ValueError), it does not crash
+    big = dict(long_it, t=np.linspace(0, 1e7, 1100), p=np.linspace(10, 9, 1100), e=np.full(1100, 0.2), teuk_modes=np.ones((1100, K), dtype=complex),
+               Phi_phi=np.linspace(0, 1e4, 1100), Phi_r=np.linspace(0, 7e3, 1100))
+    with pytest.raises(ValueError):
+        _gpu_sum(big, torch_cuda)
