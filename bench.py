@@ -332,7 +332,10 @@ def main():
         pass
     hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "MEASURED_PEAKS.json hbm_gbs (of measured)" if "hbm_gbs" in peaks else "B200_PROFILING.md fallback 6650 GB/s (of fallback)"
-    alg_bytes = 80.0 * n * B       # 32 B/bin h+,hx written + 48 B/bin whitened data and noise factor read
+    # Algorithmic bytes of the dominant kernel: the 32 B/bin of h+, hx that must be written (SURVEY 8d "waveform").  The
+    # fused likelihood's 48 B/bin of data reads are NOT charged: tiles no harmonic touches take their sum |d~|^2 from a
+    # table precomputed at emrifd_set_data, so most of those reads never happen (charging them gave frac > 1).
+    alg_bytes = 32.0 * n * B
     ach_gbs = alg_bytes / (k_avg_ms * 1e-3) / 1e9
     ach_tflops = FLOPS_PER_EVAL * evals / (k_avg_ms * 1e-3) / 1e12
     fp64_peak = gfl.value / 1e3
