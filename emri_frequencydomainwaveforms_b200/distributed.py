@@ -44,14 +44,19 @@ def bin_work_histogram(branches, m_arr, N):
     return np.cumsum(diff[:-1])
 
 
-def balanced_bin_slices(work, world, base_cost=0.02):
+def balanced_bin_slices(work, world, base_cost=0.02, align=1024):
     """Cut [0, len(work)) into ``world`` contiguous slices of equal cost; every bin costs ``base_cost``
-    (store / data read) plus its evaluations.  Returns [(j_lo, j_cnt)] * world."""
+    (store / data read) plus its evaluations.  Slice starts are multiples of ``align`` (the mode-sum kernel's tile
+    size: tiles then coincide with the precomputed per-tile sum|d~|^2 table, so empty tiles stay on the fast path).
+    Returns [(j_lo, j_cnt)] * world."""
     cost = np.asarray(work, dtype=np.float64) + base_cost
     c = np.concatenate([[0.0], np.cumsum(cost)])
     edges = [0]
     for r in range(1, world):
-        edges.append(int(np.searchsorted(c, c[-1] * r / world)))
+        e = int(np.searchsorted(c, c[-1] * r / world))
+        if align > 1:
+            e = int(round(e / align)) * align
+        edges.append(min(e, len(cost)))
     edges.append(len(cost))
     edges = np.maximum.accumulate(edges)
     return [(int(edges[r]), int(edges[r + 1] - edges[r])) for r in range(world)]

@@ -105,5 +105,10 @@ def test_shard_helpers():
             assert max(sizes) - min(sizes) <= 1
     work = np.zeros(1000, dtype=np.int64)
     work[100:200] = 50
-    sl = D.balanced_bin_slices(work, 4)
+    sl = D.balanced_bin_slices(work, 4, align=1)
     assert sum(c for _, c in sl) == 1000 and all(100 <= lo <= 200 for lo, _ in sl[1:])
+    work = np.zeros(100000, dtype=np.int64)
+    work[20000:30000] = 7
+    sl = D.balanced_bin_slices(work, 8)                        # tile-aligned starts (mode-sum tiles of 1024 bins)
+    assert sum(c for _, c in sl) == 100000 and all(lo % 1024 == 0 for lo, _ in sl)
+    assert all(19000 <= lo <= 31000 for lo, _ in sl[1:])
