@@ -23,6 +23,7 @@ def load():
         lib.emrihost_trajectory.argtypes = [C.c_double] * 9 + [C.c_int] + [_dp] * 7
         lib.emrihost_trajectory.restype = C.c_int
         lib.emrihost_trajectory_batch.argtypes = [C.c_int64] + [_dp] * 6 + [C.c_double] * 3 + [C.c_int] + [_dp] * 7 + [_ip]
+        lib.emrihost_trajectory_batch_mt.argtypes = lib.emrihost_trajectory_batch.argtypes + [C.c_int]
         lib.emrihost_num_threads.restype = C.c_int
         _lib = lib
     return _lib
@@ -37,13 +38,18 @@ def frequencies(p, e):
     return a, b
 
 
-def trajectory_batch(M, mu, p0, e0, Phi_phi0, Phi_r0, T, rtol, atol, max_len):
-    """Integrate nb walkers in parallel (OpenMP).  Returns (arrays [nb, max_len] x 7: t, p, e, Phi_phi, Phi_r, f_phi, f_r; lens [nb])."""
+def trajectory_batch(M, mu, p0, e0, Phi_phi0, Phi_r0, T, rtol, atol, max_len, nthreads=1):
+    """Integrate nb walkers (nthreads > 1: a per-call pthread team).  Returns (arrays [nb, max_len] x 7: t, p, e, Phi_phi,
+    Phi_r, f_phi [Hz], f_r [Hz]; lens [nb], negative = error code)."""
     lib = load()
     f = lambda x: np.ascontiguousarray(np.atleast_1d(x), dtype=np.float64)
     M, mu, p0, e0, Phi_phi0, Phi_r0 = map(f, (M, mu, p0, e0, Phi_phi0, Phi_r0))
     nb = len(M)
-    out = [np.zeros((nb, max_len)) for _ in range(7)]
+    out = [np.empty((nb, max_len)) for _ in range(7)]
     lens = np.zeros(nb, dtype=np.int32)
-    lib.emrihost_trajectory_batch(nb, M, mu, p0, e0, Phi_phi0, Phi_r0, float(T), float(rtol), float(atol), int(max_len), *out, lens)
+    if nthreads > 1 and nb > 1:
+        lib.emrihost_trajectory_batch_mt(nb, M, mu, p0, e0, Phi_phi0, Phi_r0, float(T), float(rtol), float(atol), int(max_len),
+                                         *out, lens, int(nthreads))
+    else:
+        lib.emrihost_trajectory_batch(nb, M, mu, p0, e0, Phi_phi0, Phi_r0, float(T), float(rtol), float(atol), int(max_len), *out, lens)
     return out, lens

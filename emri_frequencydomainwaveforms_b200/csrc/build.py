@@ -25,7 +25,7 @@ def build_host(force=False):
     if not force and os.path.exists(HOST_OUT) and os.path.getmtime(HOST_OUT) >= os.path.getmtime(HOST_SRC):
         return HOST_OUT
     cc = "/usr/bin/gcc" if os.path.exists("/usr/bin/gcc") else "gcc"
-    subprocess.check_call([cc, "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared", "-Wall", HOST_SRC, "-o", HOST_OUT, "-lm"])
+    subprocess.check_call([cc, "-O3", "-march=x86-64-v3", "-fopenmp", "-fPIC", "-shared", "-Wall", HOST_SRC, "-o", HOST_OUT, "-lm", "-lpthread"])
     return HOST_OUT
 
 

@@ -1196,6 +1196,209 @@ __global__ void __launch_bounds__(256) loglike_partial_kernel(const double2 *__r
     }
 }
 
+// ==========================================================================================
+// Ylm, mode selection by power and mode compaction on the device.
+//
+// Selection (few.utils.modeselector.ModeSelector semantics), frozen spec shared with the numpy
+// restatement oracle/oracle.py::mode_select_ref:
+//   power_i = |A_i Y_i|^2 over the M stored modes plus the -m copies (conj(A) Y_{l,-m}) of the m > 0 ones, every
+//   operation individually rounded; total = sum in the fixed order (256 strided partials, shuffle tree, 8 warps);
+//   order: descending power, ties by ascending index; entry s of that order is kept iff s == 0 or the sequential
+//   cumulative sum of the entries before it is < total * (1 - eps); a kept -m copy keeps its +m partner; a walker's
+//   kept set is the union over its time samples.
+// One CTA per time sample.  Entries with power < total * eps / (2 Mtot) cannot be reached by the cumulative sum before
+// it crosses the threshold (together they hold < eps/2 of the total), so only the survivors are sorted: a few hundred
+// at eps = 1e-2 instead of 7137.
+// ==========================================================================================
+#define SEL_THREADS 256
+#define SEL_CAP 8192 /* >= M + Mneg (7137 for l <= 10, |n| <= 30) */
+
+struct SelParams {
+    const double2 *teuk;     // [nsamp][M]
+    const int *samp_walker;  // [nsamp]
+    const double2 *ylm;      // [B][M + Mneg]
+    const int *neg_src;      // [Mneg] index of the +m mode each -m copy belongs to
+    int M, Mneg;
+    double eps;
+    unsigned char *flags;    // [B][M], zero-initialised by the caller
+};
+
+__device__ __forceinline__ double sel_power(const SelParams &p, const double2 *A, const double2 *Y, int i) {
+    const double2 a = A[i < p.M ? i : p.neg_src[i - p.M]];
+    const double ai = i < p.M ? a.y : -a.y; // -m copy: conj(A)
+    const double2 y = Y[i];
+    const double re = rsub(rmul(a.x, y.x), rmul(ai, y.y)), im = radd(rmul(a.x, y.y), rmul(ai, y.x));
+    return radd(rmul(re, re), rmul(im, im));
+}
+
+__global__ void __launch_bounds__(SEL_THREADS) mode_select_kernel(SelParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    double *key = reinterpret_cast<double *>(smraw);                         // [SEL_CAP]
+    unsigned short *idx = reinterpret_cast<unsigned short *>(key + SEL_CAP); // [SEL_CAP]
+    __shared__ double s_red[SEL_THREADS / 32];
+    __shared__ double s_total;
+    __shared__ int s_count, s_end;
+    const int samp = blockIdx.x, w = p.samp_walker[samp], Mtot = p.M + p.Mneg;
+    const double2 *A = p.teuk + (long long)samp * p.M;
+    const double2 *Y = p.ylm + (long long)w * Mtot;
+    double part = 0.0;
+    for (int i = threadIdx.x; i < Mtot; i += SEL_THREADS) part = radd(part, sel_power(p, A, Y, i));
+    for (int o = 16; o > 0; o >>= 1) part = radd(part, __shfl_down_sync(0xffffffffu, part, o));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = part;
+    if (threadIdx.x == 0) s_count = 0;
+    __syncthreads();
+    if (threadIdx.x == 0) { double t = 0; for (int q = 0; q < SEL_THREADS / 32; q++) t = radd(t, s_red[q]); s_total = t; }
+    __syncthreads();
+    const double total = s_total;
+    const double cut = p.eps >= 1e-9 ? rmul(total, rdiv(p.eps, 2.0 * (double)Mtot)) : 0.0;
+    // survivors of the pre-filter, compacted in arbitrary order (the sort below is a total order)
+    for (int i = threadIdx.x; i < Mtot; i += SEL_THREADS) {
+        const double pw = sel_power(p, A, Y, i);
+        if (!(pw < cut)) { const int s = atomicAdd(&s_count, 1); key[s] = pw; idx[s] = (unsigned short)i; }
+    }
+    __syncthreads();
+    const int cnt = s_count;
+    int n2 = 2;
+    while (n2 < cnt) n2 <<= 1;
+    for (int i = cnt + threadIdx.x; i < n2; i += SEL_THREADS) { key[i] = -1.0; idx[i] = 0xffff; } // padding sorts last
+    // bitonic sort: descending key, ascending index among equal keys
+    for (int k = 2; k <= n2; k <<= 1) {
+        for (int j = k >> 1; j > 0; j >>= 1) {
+            __syncthreads();
+            for (int i = threadIdx.x; i < n2; i += SEL_THREADS) {
+                const int ixj = i ^ j;
+                if (ixj > i) {
+                    const double a = key[i], b = key[ixj];
+                    const unsigned short ia = idx[i], ib = idx[ixj];
+                    const bool a_first = a > b || (a == b && ia < ib);
+                    if (((i & k) == 0) != a_first) { key[i] = b; key[ixj] = a; idx[i] = ib; idx[ixj] = ia; }
+                }
+            }
+        }
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) { // sequential cumulative sum (numpy.cumsum order): first position that is NOT kept
+        const double thresh = rmul(total, rsub(1.0, p.eps));
+        double cs = 0.0;
+        int s = 0;
+        for (; s < cnt; s++) {
+            if (s > 0 && !(cs < thresh)) break;
+            cs = radd(cs, key[s]);
+        }
+        s_end = s;
+    }
+    __syncthreads();
+    unsigned char *fl = p.flags + (long long)w * p.M;
+    for (int s = threadIdx.x; s < s_end; s += SEL_THREADS) {
+        const int i = idx[s];
+        fl[i < p.M ? i : p.neg_src[i - p.M]] = 1; // benign race: every writer stores 1
+    }
+}
+
+// Spin-weight -2 spherical harmonics for a batch of viewing angles (few.utils.ylm.GetYlms(assume_positive_m=True)
+// followed by the per-mode expansion of FastSchwarzschildEccentricFlux.__call__): out[w][i] = Y_{l_i, m_i}(theta_w, phi_w)
+// for i < M and Y_{l, -m} of mode neg_src[i - M] for the Mneg copies.  -2Y_lm = sqrt((2l+1)/4pi) d^l_{m,2}(theta) e^{i m phi}
+// with the explicit finite Wigner sum (exact at theta = 0, pi).  One CTA per walker: the <= 2 (lmax+1)^2 distinct
+// (l, +-m) values are computed once into shared memory, then gathered per mode.
+#define YLM_LMAX 12
+__global__ void __launch_bounds__(256) ylm_kernel(const int *__restrict__ l_arr, const int *__restrict__ m_arr, int M,
+                                                  const int *__restrict__ neg_src, int Mneg, const double *__restrict__ theta,
+                                                  const double *__restrict__ phi, double2 *__restrict__ out) {
+    __shared__ double2 tab[(YLM_LMAX + 1) * (2 * YLM_LMAX + 1)];
+    __shared__ double fact[2 * YLM_LMAX + 3];
+    const int w = blockIdx.x;
+    if (threadIdx.x == 0) { double f = 1.0; fact[0] = 1.0; for (int i = 1; i < 2 * YLM_LMAX + 3; i++) { f *= (double)i; fact[i] = f; } }
+    __syncthreads();
+    const double th = theta[w], ph = phi[w];
+    double sb, cb;
+    sincos(0.5 * th, &sb, &cb);
+    for (int q = threadIdx.x; q < (YLM_LMAX + 1) * (2 * YLM_LMAX + 1); q += blockDim.x) {
+        const int l = q / (2 * YLM_LMAX + 1), mp = q % (2 * YLM_LMAX + 1) - YLM_LMAX;
+        double2 v = make_double2(0.0, 0.0);
+        if (l >= 2 && mp >= -l && mp <= l) {
+            const int m = 2; // second index of d^l_{mp, m}: m = -s = 2
+            const double pref = sqrt(fact[l + mp] * fact[l - mp] * fact[l + m] * fact[l - m]);
+            const int k0 = max(0, m - mp), k1 = min(l + m, l - mp);
+            double tot = 0.0;
+            for (int k = k0; k <= k1; k++) {
+                const double den = fact[l + m - k] * fact[k] * fact[l - k - mp] * fact[k - m + mp];
+                double term = ((k - m + mp) & 1) ? -1.0 / den : 1.0 / den;
+                const int ec = 2 * l - 2 * k + m - mp, es = 2 * k - m + mp;
+                for (int a = 0; a < ec; a++) term *= cb;
+                for (int a = 0; a < es; a++) term *= sb;
+                tot += term;
+            }
+            const double d = sqrt((2.0 * l + 1.0) / (4.0 * 3.14159265358979323846)) * pref * tot;
+            double sn, cs;
+            sincos((double)mp * ph, &sn, &cs);
+            v = make_double2(d * cs, d * sn);
+        }
+        tab[q] = v;
+    }
+    __syncthreads();
+    double2 *o = out + (long long)w * (M + Mneg);
+    for (int i = threadIdx.x; i < M + Mneg; i += blockDim.x) {
+        const int src = i < M ? i : neg_src[i - M];
+        const int l = l_arr[src], m = i < M ? m_arr[src] : -m_arr[src];
+        o[i] = tab[l * (2 * YLM_LMAX + 1) + m + YLM_LMAX];
+    }
+}
+
+// Compaction step 1: per walker, the ascending list of kept mode indices and its length (block-wide scan of the flags).
+__global__ void __launch_bounds__(256) compact_count_kernel(const unsigned char *__restrict__ flags, int M, int *__restrict__ keep_idx,
+                                                            int *__restrict__ K_out) {
+    __shared__ int s_warp[8];
+    __shared__ int s_base;
+    const int w = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const unsigned char *fl = flags + (long long)w * M;
+    int *ki = keep_idx + (long long)w * M;
+    if (threadIdx.x == 0) s_base = 0;
+    __syncthreads();
+    for (int i0 = 0; i0 < M; i0 += 256) {
+        const int i = i0 + threadIdx.x;
+        const int f = i < M && fl[i] != 0;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int off = s_base;
+        for (int q = 0; q < wid; q++) off += s_warp[q];
+        if (f) ki[off + __popc(bal & ((1u << lane) - 1u))] = i;
+        __syncthreads();
+        if (threadIdx.x == 0) { int t = 0; for (int q = 0; q < 8; q++) t += s_warp[q]; s_base += t; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) K_out[w] = s_base;
+}
+
+// Compaction step 2: gather the kept modes of every walker into the packed layout the mode-sum pipeline consumes
+// (teuk [L][K], m/n [K], ylm [2K] = +m block then -m block; m = 0 modes reuse their +m value in the -m block).
+// grid (Lmax + 1, B): block row j < L gathers knot j of teuk; block row Lmax gathers m, n, ylm.
+__global__ void __launch_bounds__(256) compact_gather_kernel(const emrifd_walker_t *__restrict__ wk, int Lmax, int M, int Mneg,
+                                                             const double2 *__restrict__ teuk_full, const int *__restrict__ keep_idx,
+                                                             const int *__restrict__ m_basis, const int *__restrict__ n_basis,
+                                                             const int *__restrict__ neg_pos, const double2 *__restrict__ ylm_full,
+                                                             double2 *__restrict__ teuk_out, int *__restrict__ m_out,
+                                                             int *__restrict__ n_out, double2 *__restrict__ ylm_out) {
+    const int w = blockIdx.y, j = blockIdx.x;
+    const emrifd_walker_t W = wk[w];
+    const int *ki = keep_idx + (long long)w * M;
+    if (j < Lmax) {
+        if (j >= W.L) return;
+        const double2 *src = teuk_full + (W.knot_off + j) * (long long)M;
+        double2 *dst = teuk_out + W.teuk_off + (long long)j * W.K;
+        for (int k = threadIdx.x; k < W.K; k += blockDim.x) dst[k] = src[ki[k]];
+    } else {
+        const double2 *Y = ylm_full + (long long)w * (M + Mneg);
+        for (int k = threadIdx.x; k < W.K; k += blockDim.x) {
+            const int i = ki[k];
+            m_out[W.mode_off + k] = m_basis[i];
+            n_out[W.mode_off + k] = n_basis[i];
+            ylm_out[2 * W.mode_off + k] = Y[i];
+            ylm_out[2 * W.mode_off + W.K + k] = Y[neg_pos[i] >= 0 ? M + neg_pos[i] : i];
+        }
+    }
+}
+
 // FP64 FMA peak micro-benchmark: 8 independent chains per thread
 __global__ void __launch_bounds__(256) fma_bench_kernel(double *out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -1309,6 +1512,7 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaFuncSetAttribute(spline_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(spline_build_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(mode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_CAP * 10);
     cudaFuncSetAttribute(mode_sum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -1634,6 +1838,65 @@ int emrifd_loglike_batch_host(emrifd_handle_t *h, const emrifd_walker_t *walkers
         return set_err(h, st, st == EMRIFD_ERR_BRANCHES ? "a mode has more monotone branches than EMRIFD_MAX_BRANCHES"
                                                          : "trajectory knots are not strictly increasing");
     }
+    return 0;
+}
+
+int emrifd_mode_select(emrifd_handle_t *h, const double *teuk, int64_t nsamp, int64_t M, const int32_t *samp_walker,
+                       const double *ylm, const int32_t *neg_src, int64_t Mneg, int64_t B, double eps, uint8_t *flags) {
+    if (!h || !teuk || !samp_walker || !ylm || !flags || nsamp <= 0 || M <= 0 || Mneg < 0 || B <= 0 || (Mneg > 0 && !neg_src))
+        return set_err(h, EMRIFD_ERR_INVALID, "mode_select: bad argument");
+    if (M + Mneg > SEL_CAP) return set_err(h, EMRIFD_ERR_INVALID, "mode_select: more than 8192 modes (incl. -m copies)");
+    if (!(eps >= 0.0 && eps < 1.0)) return set_err(h, EMRIFD_ERR_INVALID, "mode_select: eps must be in [0, 1)");
+    cudaSetDevice(h->device);
+    SelParams p;
+    p.teuk = (const double2 *)teuk; p.samp_walker = samp_walker; p.ylm = (const double2 *)ylm; p.neg_src = neg_src;
+    p.M = (int)M; p.Mneg = (int)Mneg; p.eps = eps; p.flags = flags;
+    CUDA_TRY(h, cudaMemsetAsync(flags, 0, (size_t)(B * M), h->stream));
+    const size_t smem = SEL_CAP * (sizeof(double) + sizeof(unsigned short));
+    mode_select_kernel<<<(unsigned)nsamp, SEL_THREADS, smem, h->stream>>>(p);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int emrifd_ylm_batch(emrifd_handle_t *h, const int32_t *l_arr, const int32_t *m_arr, int64_t M, const int32_t *neg_src,
+                     int64_t Mneg, const double *theta, const double *phi, int64_t B, int lmax, double *ylm_out) {
+    if (!h || !l_arr || !m_arr || !theta || !phi || !ylm_out || M <= 0 || Mneg < 0 || B <= 0 || (Mneg > 0 && !neg_src))
+        return set_err(h, EMRIFD_ERR_INVALID, "ylm_batch: bad argument");
+    if (lmax < 2 || lmax > YLM_LMAX) return set_err(h, EMRIFD_ERR_INVALID, "ylm_batch: lmax must be in [2, 12]");
+    cudaSetDevice(h->device);
+    ylm_kernel<<<(unsigned)B, 256, 0, h->stream>>>(l_arr, m_arr, (int)M, neg_src, (int)Mneg, theta, phi, (double2 *)ylm_out);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int emrifd_mode_compact_count(emrifd_handle_t *h, const uint8_t *flags, int64_t B, int64_t M, int32_t *keep_idx, int32_t *K_out) {
+    if (!h || !flags || !keep_idx || !K_out || B <= 0 || M <= 0) return set_err(h, EMRIFD_ERR_INVALID, "mode_compact_count: bad argument");
+    cudaSetDevice(h->device);
+    compact_count_kernel<<<(unsigned)B, 256, 0, h->stream>>>(flags, (int)M, keep_idx, K_out);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int emrifd_mode_compact_gather(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B, const double *teuk_full, int64_t M,
+                               int64_t Mneg, const int32_t *keep_idx, const int32_t *m_basis, const int32_t *n_basis,
+                               const int32_t *neg_pos, const double *ylm_full, double *teuk_out, int32_t *m_out, int32_t *n_out,
+                               double *ylm_out) {
+    if (!h || !teuk_full || !keep_idx || !m_basis || !n_basis || !neg_pos || !ylm_full || !teuk_out || !m_out || !n_out || !ylm_out ||
+        M <= 0 || Mneg < 0)
+        return set_err(h, EMRIFD_ERR_INVALID, "mode_compact_gather: bad argument");
+    int Lmax, Kmax, rc;
+    if ((rc = validate_walkers(h, walkers, B, &Lmax, &Kmax))) return rc;
+    if (Kmax > M) return set_err(h, EMRIFD_ERR_INVALID, "mode_compact_gather: walker K exceeds the mode basis");
+    cudaSetDevice(h->device);
+    if ((rc = upload_walkers(h, walkers, B))) return rc;
+    compact_gather_kernel<<<dim3((unsigned)(Lmax + 1), (unsigned)B), 256, 0, h->stream>>>(
+        h->d_walkers, Lmax, (int)M, (int)Mneg, (const double2 *)teuk_full, keep_idx, m_basis, n_basis, neg_pos,
+        (const double2 *)ylm_full, (double2 *)teuk_out, m_out, n_out, (double2 *)ylm_out);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
 

@@ -266,6 +266,48 @@ void emrihost_trajectory_batch(int64_t nb, const double *M, const double *mu, co
     }
 }
 
+/* multi-threaded batch: plain pthreads created per call (no resident spinning team), walkers handed out through an atomic
+   counter because their cost varies (0.3-1 ms each) */
+#include <pthread.h>
+typedef struct {
+    int64_t nb;
+    const double *M, *mu, *p0, *e0, *Pp0, *Pr0;
+    double T, rtol, atol;
+    int max_len;
+    double *t, *p, *e, *Pp, *Pr, *fphi, *fr;
+    int32_t *lens;
+    int64_t next;
+} traj_job_t;
+
+static void *traj_worker(void *arg) {
+    traj_job_t *j = (traj_job_t *)arg;
+    for (;;) {
+        int64_t i = __atomic_fetch_add(&j->next, 1, __ATOMIC_RELAXED);
+        if (i >= j->nb) break;
+        size_t o = (size_t)i * j->max_len;
+        j->lens[i] = emrihost_trajectory(j->M[i], j->mu[i], j->p0[i], j->e0[i], j->Pp0[i], j->Pr0[i], j->T, j->rtol, j->atol,
+                                         j->max_len, j->t + o, j->p + o, j->e + o, j->Pp + o, j->Pr + o, j->fphi + o, j->fr + o);
+    }
+    return NULL;
+}
+
+void emrihost_trajectory_batch_mt(int64_t nb, const double *M, const double *mu, const double *p0, const double *e0,
+                                  const double *Phi_phi0, const double *Phi_r0, double T_years, double rtol, double atol,
+                                  int max_len, double *t, double *p, double *e, double *Pp, double *Pr, double *fphi,
+                                  double *fr, int32_t *lens, int nthreads) {
+    traj_job_t job = {nb, M, mu, p0, e0, Phi_phi0, Phi_r0, T_years, rtol, atol, max_len, t, p, e, Pp, Pr, fphi, fr, lens, 0};
+    if (nthreads > nb) nthreads = (int)nb;
+    if (nthreads > 64) nthreads = 64;
+    if (nthreads <= 1) { traj_worker(&job); return; }
+    pthread_t th[64];
+    int started = 0;
+    for (int k = 0; k < nthreads - 1; k++) {
+        if (pthread_create(&th[started], NULL, traj_worker, &job) == 0) started++;
+    }
+    traj_worker(&job);
+    for (int k = 0; k < started; k++) pthread_join(th[k], NULL);
+}
+
 int emrihost_num_threads(void) {
 #ifdef _OPENMP
     return omp_get_max_threads();

@@ -66,6 +66,29 @@ class DeviceBatch:
         self.coeff = torch.empty(pb.n_coeff, dtype=torch.float64, device=dev)
         self.branches = torch.zeros(pb.n_modes * MAX_BRANCHES * BRANCH_DTYPE.itemsize, dtype=torch.uint8, device=dev)
 
+    @classmethod
+    def from_device_parts(cls, handle, walkers, tracks, teuk, m, n, ylm):
+        """Batch whose packed arrays were produced on the device (device Ylm / mode selection / compaction,
+        waveform.FastSchwarzschildEccentricFlux.prepare_batch_device).  ``walkers``: host WALKER_DTYPE records;
+        ``tracks``: dict of device float64 tensors t, f_phi, f_r, Phi_phi, Phi_r [sum L]."""
+        import torch
+        self = cls.__new__(cls)
+        pb = PackedBatch.__new__(PackedBatch)
+        pb.B, pb.walkers = len(walkers), walkers
+        pb.n_knots = int(walkers["L"].sum())
+        pb.n_teuk = int((walkers["L"].astype(np.int64) * walkers["K"]).sum())
+        pb.n_modes = int(walkers["K"].sum())
+        pb.n_coeff = int((walkers["L"].astype(np.int64) * (2 * walkers["K"].astype(np.int64) + 4) * 4).sum())
+        pb.Lmax, pb.Kmax = int(walkers["L"].max()), int(walkers["K"].max())
+        self.pb, self.handle = pb, handle
+        self.t, self.f_phi, self.f_r = tracks["t"], tracks["f_phi"], tracks["f_r"]
+        self.Phi_phi, self.Phi_r = tracks["Phi_phi"], tracks["Phi_r"]
+        self.teuk, self.m, self.n, self.ylm = teuk, m, n, ylm
+        dev = handle.torch_device
+        self.coeff = torch.empty(pb.n_coeff, dtype=torch.float64, device=dev)
+        self.branches = torch.zeros(pb.n_modes * MAX_BRANCHES * BRANCH_DTYPE.itemsize, dtype=torch.uint8, device=dev)
+        return self
+
     def branches_host(self):
         """Work-list (A4 output) as a structured numpy array [n_modes, MAX_BRANCHES]."""
         return self.branches.cpu().numpy().view(BRANCH_DTYPE).reshape(self.pb.n_modes, MAX_BRANCHES)

@@ -19,7 +19,7 @@ from .. import _lib, engine
 class FDTemplateModel:
     """Batched FD template + likelihood plugin around a ``GenerateEMRIWaveform``-shaped generator."""
 
-    def __init__(self, waveform_generator, f_arr=None, device=None):
+    def __init__(self, waveform_generator, f_arr=None, device=None, producers="auto"):
         self.gen = waveform_generator
         self.base = waveform_generator.waveform_generator       # FastSchwarzschildEccentricFlux
         self._device = device
@@ -27,6 +27,12 @@ class FDTemplateModel:
         self._data = None
         self.f_arr = f_arr
         self.last_h2d_bytes = 0
+        if producers == "auto":
+            from .. import _hostlib
+            amp, ig = self.base.amplitude_generator, self.base.inspiral_generator
+            producers = ("device" if hasattr(amp, "device_call") and getattr(ig, "use_native", False)
+                         and _hostlib.load() is not None else "host")
+        self.producers = producers          # "device": Ylm / mode selection / compaction on the GPU; "host": NumPy producers
 
     @property
     def handle(self):
@@ -98,6 +104,22 @@ class FDTemplateModel:
             fpos_dev, val = None, 1.0 / (Ngrid * dt)
         if (Ngrid + 1) // 2 != self.n_data:
             raise ValueError("frequency grid and injected data have different lengths")
+        producers = kwargs.pop("producers", self.producers)
+        if producers == "device" and mode_selection is None:
+            # Ylm, mode selection and compaction on the device; only the sparse tracks cross PCIe
+            P = np.atleast_2d(params)
+            ang = np.array([self.gen._transform(*row[7:11]) for row in P])      # theta, phi, cos2psi, sin2psi
+            db, ok = self.base.prepare_batch_device(P[:, 0], P[:, 1], P[:, 3], P[:, 4], ang[:, 0], ang[:, 1], dist=P[:, 6],
+                                                    Phi_phi0=P[:, 11], Phi_r0=P[:, 13], T=T, dt=dt, eps=eps,
+                                                    cos2psi=ang[:, 2], sin2psi=ang[:, 3], handle=h)
+            ll = np.full(len(ok), np.nan)
+            if db is not None:
+                self.last_h2d_bytes = db.h2d_bytes
+                out = engine.run_loglike(db, Ngrid, val, fpos_dev, include_minus_m=include_minus_m).cpu().numpy()
+                h.status()
+                ll[ok] = out[:, 0]
+                self.last_dh_hh = out[:, 1:]
+            return ll
         items, ok = self.prepare_batch(params, T=T, dt=dt, eps=eps, mode_selection=mode_selection)
         ll = np.full(len(ok), np.nan)
         if items:

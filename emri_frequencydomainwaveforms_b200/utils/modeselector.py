@@ -20,7 +20,10 @@ class ModeSelector:
         modeinds = [l_arr, m_arr, n_arr].  Returns (teuk_modes_kept, ylms_kept [2K], ls, ms, ns)."""
         zero_up = self.num_m_zero_up
         full = np.concatenate([teuk_modes, np.conj(teuk_modes[:, self.m0mask])], axis=1)
-        power = np.abs(full * ylms[None, :]) ** 2
+        # |A Y|^2 with every operation individually rounded (the device kernel does exactly the same arithmetic)
+        ar, ai, yr, yi = full.real, full.imag, ylms.real[None, :], ylms.imag[None, :]
+        re, im = ar * yr - ai * yi, ar * yi + ai * yr
+        power = re * re + im * im
         picked = None
         ntot = power.shape[1]
         ktop = 768
@@ -54,3 +57,25 @@ class ModeSelector:
         ylms_kept = np.concatenate([ylms[keep_modes], ylms[neg_idx]])
         l_arr, m_arr, n_arr = modeinds
         return (teuk_modes[:, keep_modes], ylms_kept, l_arr[keep_modes], m_arr[keep_modes], n_arr[keep_modes])
+
+    # ---- device version (emrifd_mode_select) -----------------------------------------
+    def select_device(self, teuk_dev, samp_walker, ylm_full, eps=1e-5, handle=None):
+        """teuk_dev: torch complex128 [nsamp, M] (all walkers' time samples back to back) on the GPU;
+        samp_walker: int32 [nsamp]; ylm_full: complex128 [B, M + M_{m>0}].  Returns a torch uint8 [B, M] keep mask
+        (union over each walker's samples, -m picks folded onto their +m partner)."""
+        import torch
+        from .. import _lib
+        h = handle or _lib.get_handle()
+        dev = h.torch_device
+        if not hasattr(self, "_neg_src_dev") or self._neg_src_dev.device != dev:
+            self._neg_src_dev = torch.as_tensor(np.where(self.m0mask)[0].astype(np.int32)).to(dev)
+        teuk_dev = teuk_dev.to(device=dev, dtype=torch.complex128).contiguous()
+        sw = torch.as_tensor(np.asarray(samp_walker, dtype=np.int32)).to(dev)
+        yl = torch.as_tensor(np.ascontiguousarray(ylm_full, dtype=np.complex128)).to(dev)
+        B, nsamp, M = yl.shape[0], teuk_dev.shape[0], teuk_dev.shape[1]
+        if M != self.num_m_zero_up or yl.shape[1] != M + self.num_m_1_up:
+            raise ValueError("teuk_modes / ylms do not match the mode basis of this selector")
+        flags = torch.empty((B, M), dtype=torch.uint8, device=dev)
+        h.check(h.lib.emrifd_mode_select(h.h, teuk_dev.data_ptr(), nsamp, M, sw.data_ptr(), yl.data_ptr(),
+                                         self._neg_src_dev.data_ptr(), self.num_m_1_up, B, float(eps), flags.data_ptr()))
+        return flags

@@ -43,3 +43,18 @@ class GetYlms:
             l, m = l_in, m_in
         return np.array([spin_weighted_ylm(-2, int(a), int(b), theta, phi) for a, b in zip(l, m)],
                         dtype=np.complex128)
+
+
+def ylm_batch_device(l_arr, m_arr, neg_src, theta, phi, handle, lmax=10, cache=None):
+    """Device version for a batch of viewing angles (emrifd_ylm_batch):
+    returns torch complex128 [B, M + Mneg] = [Y_{l_i m_i}] ++ [Y_{l,-m} of the m > 0 modes] per walker, i.e.
+    ``GetYlms(assume_positive_m=True)`` already expanded to the mode basis.  l_arr, m_arr, neg_src: device int32."""
+    import torch
+    dev = handle.torch_device
+    th = torch.as_tensor(np.atleast_1d(np.asarray(theta, dtype=np.float64))).to(dev)
+    ph = torch.as_tensor(np.atleast_1d(np.asarray(phi, dtype=np.float64))).to(dev)
+    B, M, Mneg = th.shape[0], l_arr.shape[0], neg_src.shape[0]
+    out = torch.empty((B, M + Mneg), dtype=torch.complex128, device=dev)
+    handle.check(handle.lib.emrifd_ylm_batch(handle.h, l_arr.data_ptr(), m_arr.data_ptr(), M, neg_src.data_ptr(), Mneg,
+                                             th.data_ptr(), ph.data_ptr(), B, int(lmax), out.data_ptr()))
+    return out

@@ -120,6 +120,99 @@ class FastSchwarzschildEccentricFlux:
                     f_phi=om_phi / (2 * np.pi * M * MTSUN_SI), f_r=om_r / (2 * np.pi * M * MTSUN_SI),
                     scale=scale, M=M, mu=mu)
 
+    # ---- batched producers with Ylm, mode selection and compaction on the device ----
+    def _device_basis(self, handle):
+        import torch
+        dev = handle.torch_device
+        if getattr(self, "_basis_dev", None) is None or self._basis_dev["l"].device != dev:
+            up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+            neg_src = np.where(self.m0mask)[0]
+            neg_pos = np.where(self.m0mask, np.cumsum(self.m0mask) - 1, -1)
+            self._basis_dev = dict(l=up(self.l_arr), m=up(self.m_arr), n=up(self.n_arr), neg_src=up(neg_src), neg_pos=up(neg_pos))
+        return self._basis_dev
+
+    def prepare_batch_device(self, M, mu, p0, e0, theta, phi, dist=None, Phi_phi0=0.0, Phi_r0=0.0, T=1.0, dt=10.0,
+                             eps=1e-5, cos2psi=1.0, sin2psi=0.0, handle=None, nthreads=None, keep_full=False):
+        """Producers of a whole walker batch: trajectories on the host (native, threaded; north_star keeps the ODE
+        there), amplitudes / Ylm / mode selection / compaction on the device.  Arguments are arrays [nb] (scalars
+        broadcast).  Returns ``(DeviceBatch or None, ok[nb])``; walkers whose parameters are outside the domain of
+        validity or whose trajectory fails have ok = False (the single-walker path raises ValueError for those)."""
+        import os
+        import torch
+        from . import _hostlib, _lib, engine
+        from .utils.ylm import ylm_batch_device
+        h = handle or _lib.get_handle()
+        dev = h.torch_device
+        amp = self.amplitude_generator
+        if not hasattr(amp, "device_call"):
+            raise ValueError("prepare_batch_device needs an amplitude generator with device_call(p, e, device)")
+        if _hostlib.load() is None or not getattr(self.inspiral_generator, "use_native", False):
+            raise ValueError("prepare_batch_device needs the native trajectory library (csrc/libemrihost.so)")
+        bc = lambda x: np.ascontiguousarray(np.broadcast_to(np.asarray(x, dtype=np.float64), np.shape(M)).ravel())
+        M = np.atleast_1d(np.asarray(M, dtype=np.float64))
+        mu, p0, e0, theta, phi, Phi_phi0, Phi_r0, cos2psi, sin2psi = map(bc, (mu, p0, e0, theta, phi, Phi_phi0, Phi_r0, cos2psi, sin2psi))
+        nb = len(M)
+        ok = np.ones(nb, dtype=bool)
+        for i in range(nb):
+            try:
+                self.sanity_check_init(M[i], mu[i], p0[i], e0[i])
+                self.sanity_check_viewing_angles(theta[i], phi[i])
+            except ValueError:
+                ok[i] = False
+        ig = self.inspiral_generator
+        nthreads = nthreads or min(len(os.sched_getaffinity(0)), 16)
+        sel = np.where(ok)[0]
+        if len(sel) == 0:
+            return None, ok
+        out, lens = _hostlib.trajectory_batch(M[sel], mu[sel], p0[sel], e0[sel], Phi_phi0[sel], Phi_r0[sel], T, ig.rtol, ig.atol,
+                                              ig.max_init_len, nthreads=nthreads)
+        good = lens >= 4
+        ok[sel[~good]] = False
+        sel, out, lens = sel[good], [o[good] for o in out], lens[good].astype(np.int64)
+        B = len(sel)
+        if B == 0:
+            return None, ok
+        # ragged pack of the tracks: row mask of the [B, max_len] arrays
+        mask = np.arange(out[0].shape[1])[None, :] < lens[:, None]
+        tr = np.stack([o[mask] for o in out])             # [7, sum L]: t, p, e, Phi_phi, Phi_r, f_phi, f_r
+        nk = tr.shape[1]
+        tr_dev = torch.from_numpy(tr).to(dev)
+        samp_walker = torch.from_numpy(np.repeat(np.arange(B, dtype=np.int32), lens)).to(dev)
+        basis = self._device_basis(h)
+        Mb, Mneg = self.num_teuk_modes, int(self.m0mask.sum())
+        teuk_full = amp.device_call(tr_dev[1], tr_dev[2], dev).contiguous()          # [sum L, Mb] complex128
+        ylm_full = ylm_batch_device(basis["l"], basis["m"], basis["neg_src"], theta[sel], phi[sel], h, lmax=int(self.l_arr.max()))
+        flags = torch.empty((B, Mb), dtype=torch.uint8, device=dev)
+        h.check(h.lib.emrifd_mode_select(h.h, teuk_full.data_ptr(), nk, Mb, samp_walker.data_ptr(), ylm_full.data_ptr(),
+                                         basis["neg_src"].data_ptr(), Mneg, B, float(eps), flags.data_ptr()))
+        keep_idx = torch.empty((B, Mb), dtype=torch.int32, device=dev)
+        K_dev = torch.empty(B, dtype=torch.int32, device=dev)
+        h.check(h.lib.emrifd_mode_compact_count(h.h, flags.data_ptr(), B, Mb, keep_idx.data_ptr(), K_dev.data_ptr()))
+        K = K_dev.cpu().numpy().astype(np.int64)          # the one D2H of the producer stage: B ints
+        w = np.zeros(B, dtype=_lib.WALKER_DTYPE)
+        w["L"], w["K"] = lens, K
+        w["knot_off"] = np.concatenate([[0], np.cumsum(lens)[:-1]])
+        w["teuk_off"] = np.concatenate([[0], np.cumsum(lens * K)[:-1]])
+        w["mode_off"] = np.concatenate([[0], np.cumsum(K)[:-1]])
+        w["coeff_off"] = np.concatenate([[0], np.cumsum(lens * (2 * K + 4) * 4)[:-1]])
+        w["scale"] = 1.0 if dist is None else (mu[sel] * MRSUN_SI) / (bc(dist)[sel] * Gpc)
+        w["cos2psi"], w["sin2psi"] = cos2psi[sel], sin2psi[sel]
+        teuk = torch.empty(int((lens * K).sum()), dtype=torch.complex128, device=dev)
+        m_out = torch.empty(int(K.sum()), dtype=torch.int32, device=dev)
+        n_out = torch.empty_like(m_out)
+        ylm = torch.empty(2 * int(K.sum()), dtype=torch.complex128, device=dev)
+        h.check(h.lib.emrifd_mode_compact_gather(h.h, w.ctypes.data, B, teuk_full.data_ptr(), Mb, Mneg, keep_idx.data_ptr(),
+                                                 basis["m"].data_ptr(), basis["n"].data_ptr(), basis["neg_pos"].data_ptr(),
+                                                 ylm_full.data_ptr(), teuk.data_ptr(), m_out.data_ptr(), n_out.data_ptr(),
+                                                 ylm.data_ptr()))
+        tracks = dict(t=tr_dev[0], Phi_phi=tr_dev[3], Phi_r=tr_dev[4], f_phi=tr_dev[5], f_r=tr_dev[6])
+        db = engine.DeviceBatch.from_device_parts(h, w, tracks, teuk, m_out, n_out, ylm)
+        db.keep_idx, db.h2d_bytes = keep_idx, int(tr.nbytes + samp_walker.numel() * 4 + 2 * 8 * B + w.nbytes)
+        db.p_e_host = (tr[1], tr[2])
+        if keep_full:   # tests compare the selection against the numpy restatement on the very same inputs
+            db.teuk_full, db.ylm_full, db.flags = teuk_full, ylm_full, flags
+        return db, ok
+
     def __call__(self, M, mu, p0, e0, theta, phi, *args, dist=None, Phi_phi0=0.0, Phi_r0=0.0, dt=10.0, T=1.0,
                  eps=1e-5, show_progress=False, batch_size=-1, mode_selection=None, include_minus_m=True,
                  f_arr=None, mask_positive=False, cos2psi=1.0, sin2psi=0.0, **kwargs):

@@ -156,6 +156,31 @@ int emrifd_loglike_batch_host(emrifd_handle_t *h, const emrifd_walker_t *walkers
                               double *hp_dev, double *hc_dev, /* optional DEVICE outputs [B][(N+1)/2] complex (walker out_off), or NULL */
                               double *like_out_host /* [B][3] */);
 
+/* ---- SURVEY section 8f rank 1 ("next"): Ylm, mode selection by power and mode compaction on the device -------
+ * The producers that sit immediately before the path in FastSchwarzschildEccentricFlux.__call__ (upstream few/waveform.py;
+ * in-repo call sites emri_pe.py:86-105,212): ylm_gen -> mode_selector -> teuk_modes[:, keep].  With them on the device the
+ * full-basis amplitudes never cross PCIe and a walker batch needs one small D2H (the kept-mode counts).
+ *
+ * emrifd_ylm_batch replaces few.utils.ylm.GetYlms(assume_positive_m=True)(l, m, theta, phi) plus the per-mode expansion
+ * (Tutorial_FD_construction_single_mode.ipynb:87,597-611): l_arr, m_arr [M] mode basis (m >= 0), neg_src [Mneg] = basis
+ * index of each m > 0 mode (the -m copies), theta, phi [B]; ylm_out [B][M + Mneg] complex = Y_{l,m} block then Y_{l,-m}. */
+int emrifd_ylm_batch(emrifd_handle_t *h, const int32_t *l_arr, const int32_t *m_arr, int64_t M, const int32_t *neg_src,
+                     int64_t Mneg, const double *theta, const double *phi, int64_t B, int lmax, double *ylm_out);
+/* emrifd_mode_select replaces few.utils.modeselector.ModeSelector.__call__ (semantics SURVEY.md A.4).  teuk [nsamp][M]
+ * complex (all walkers' time samples back to back), samp_walker [nsamp] walker of each sample, ylm [B][M + Mneg] as
+ * above, flags [B][M] bytes out (1 = keep; the union over the walker's samples, -m picks folded onto +m). */
+int emrifd_mode_select(emrifd_handle_t *h, const double *teuk, int64_t nsamp, int64_t M, const int32_t *samp_walker,
+                       const double *ylm, const int32_t *neg_src, int64_t Mneg, int64_t B, double eps, uint8_t *flags);
+/* Compaction (the `teuk_modes[:, keep]`, `ylms[keep ++ keep_neg]`, `ls/ms/ns[keep]` indexing of ModeSelector.__call__):
+ * step 1 writes each walker's ascending kept indices keep_idx [B][M] (first K valid) and K_out [B]; the caller reads K_out,
+ * fills the walker descriptors (K and offsets), then step 2 gathers into the packed layout of emrifd_fd_waveform_batch.
+ * teuk_full [sum L][M] complex (walker rows at knot_off), neg_pos [M] = position of a mode in the -m block or -1 (m = 0). */
+int emrifd_mode_compact_count(emrifd_handle_t *h, const uint8_t *flags, int64_t B, int64_t M, int32_t *keep_idx, int32_t *K_out);
+int emrifd_mode_compact_gather(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B, const double *teuk_full, int64_t M,
+                               int64_t Mneg, const int32_t *keep_idx, const int32_t *m_basis, const int32_t *n_basis,
+                               const int32_t *neg_pos, const double *ylm_full, double *teuk_out, int32_t *m_out, int32_t *n_out,
+                               double *ylm_out);
+
 /* ---- measurement helpers (bench.py roofline denominators) ----------------------------------- */
 /* FP64 FMA throughput micro-benchmark: returns achieved GFLOP/s in *gflops. sync. */
 int emrifd_bench_fp64_fma(emrifd_handle_t *h, int iters, double *gflops);

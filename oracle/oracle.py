@@ -149,3 +149,59 @@ class Oracle:
         br, nbr = self.segment_build(t, coeff, m_arr, n_arr, N, val, fpos)
         hp, hc = self.mode_sum(t, coeff, m_arr, n_arr, ylms, N, br, nbr, val, fpos, **kw)
         return hp, hc, coeff, br, nbr
+
+
+# ---- mode selection by power (numpy restatement; checker only) ----------------------------
+def mode_select_ref(teuk_modes, ylms, m0mask, eps):
+    """few.utils.modeselector.ModeSelector.__call__ semantics (call site
+    Tutorial_FrequencyDomain_Waveforms.ipynb:122-131 through ``eps=``), with the summation orders frozen so that a
+    device implementation can be compared index-for-index:
+    power = |[A, conj(A[:, m>0])] * ylms|^2 (each operation rounded); per time sample sort descending (ties: ascending
+    index), sequential cumsum, keep entry s iff s == 0 or cumsum[s-1] < total * (1 - eps); union over samples; -m picks
+    fold onto their +m partner.  ``total`` is summed as 256 strided sequential partials, a 32-lane shuffle-down tree
+    per group of 32 partials, then sequentially over the 8 groups.  Returns the sorted kept +m indices."""
+    teuk_modes = np.asarray(teuk_modes, dtype=np.complex128)
+    m0mask = np.asarray(m0mask, dtype=bool)
+    M = teuk_modes.shape[1]
+    full = np.concatenate([teuk_modes, np.conj(teuk_modes[:, m0mask])], axis=1)
+    ar, ai, yr, yi = full.real, full.imag, ylms.real[None, :], ylms.imag[None, :]
+    re, im = ar * yr - ai * yi, ar * yi + ai * yr
+    power = re * re + im * im
+    ntot = power.shape[1]
+    src = np.concatenate([np.arange(M), np.where(m0mask)[0]])
+    keep = np.zeros(M, dtype=bool)
+    for row in power:
+        pad = np.zeros(((ntot + 255) // 256) * 256)
+        pad[:ntot] = row
+        part = np.zeros(256)
+        for chunk in pad.reshape(-1, 256):        # sequential strided partials (adding the zero padding is exact)
+            part = part + chunk
+        v = part.reshape(8, 32).copy()
+        for o in (16, 8, 4, 2, 1):                # shuffle-down tree: lane l += lane l+o (lanes >= 32-o add junk, unused)
+            v[:, :o] = v[:, :o] + v[:, o:2 * o]
+        total = 0.0
+        for q in range(8):
+            total = total + v[q, 0]
+        thresh = total * (1.0 - eps)
+        order = np.lexsort((np.arange(ntot), -row))
+        cs = 0.0
+        for s, i in enumerate(order):
+            if s > 0 and not (cs < thresh):
+                break
+            keep[src[i]] = True
+            cs = cs + row[i]
+    return np.where(keep)[0]
+
+
+def ylm_ref(l, m, theta, phi):
+    """-2Y_lm(theta, phi) by the explicit Wigner-d sum with exact integer factorials (few.utils.ylm.GetYlms values;
+    Tutorial_FD_construction_single_mode.ipynb:87).  Scalar, checker only."""
+    from math import factorial, sqrt, pi, cos, sin
+    mp, mm = m, 2
+    cb, sb = cos(theta / 2.0), sin(theta / 2.0)
+    tot = 0.0
+    for k in range(max(0, mm - mp), min(l + mm, l - mp) + 1):
+        den = factorial(l + mm - k) * factorial(k) * factorial(l - k - mp) * factorial(k - mm + mp)
+        tot += (-1.0) ** (k - mm + mp) / den * cb ** (2 * l - 2 * k + mm - mp) * sb ** (2 * k - mm + mp)
+    d = sqrt(factorial(l + mp) * factorial(l - mp) * factorial(l + mm) * factorial(l - mm)) * tot
+    return sqrt((2 * l + 1) / (4.0 * pi)) * d * complex(cos(m * phi), sin(m * phi))

@@ -159,3 +159,32 @@ def test_segmentation_properties(generator, oracle_quad):
     sub = f[zero: zero + 2001]
     hp2, hc2, *_ = oracle_waveform(oracle_quad, it, N=4001, fpos=sub)
     assert np.array_equal(hp2[2000:], hp[zero: zero + 2001])
+
+
+def test_mode_select_restatement_matches_host_selector(generator):
+    """oracle.mode_select_ref (frozen summation orders, checker of the device kernel) picks the same modes as the
+    product's host ModeSelector (few semantics) and obeys its defining properties."""
+    from oracle.oracle import mode_select_ref, ylm_ref
+    t, p, e, *_ = generator.inspiral_generator(1e6, 10.0, 0.0, 12.0, 0.35, 1.0, T=0.2, dt=10.0)
+    teuk = generator.amplitude_generator(p, e)
+    nl = len(generator.unique_l)
+    y = generator.ylm_gen(generator.unique_l, generator.unique_m, 1.0, -np.pi / 2)
+    ylms = np.concatenate([y[:nl][generator.inverse_lm], y[nl:][generator.inverse_lm][generator.m0mask]])
+    prev = None
+    for eps in (0.3, 1e-2, 1e-5):
+        keep = mode_select_ref(teuk, ylms, generator.m0mask, eps)
+        _, _, ls, ms, ns = generator.mode_selector(teuk, ylms, [generator.l_arr, generator.m_arr, generator.n_arr], eps=eps)
+        assert np.array_equal(generator.l_arr[keep], ls) and np.array_equal(generator.m_arr[keep], ms) and np.array_equal(generator.n_arr[keep], ns)
+        # kept power fraction >= 1 - eps at every time sample; smaller eps keeps a superset
+        full = np.concatenate([teuk, np.conj(teuk[:, generator.m0mask])], axis=1) * ylms[None, :]
+        pw = np.abs(full) ** 2
+        pos = np.cumsum(generator.m0mask) - 1
+        sel = np.concatenate([keep, generator.num_teuk_modes + pos[keep][generator.m0mask[keep]]])
+        assert np.all(pw[:, sel].sum(axis=1) >= (1 - eps) * pw.sum(axis=1) * (1 - 1e-12))
+        if prev is not None:
+            assert set(prev) <= set(keep)
+        prev = keep
+    # Ylm restatement against the product's host GetYlms
+    for (l, m) in [(2, 2), (2, -2), (5, 3), (10, -7), (10, 0)]:
+        from emri_frequencydomainwaveforms_b200.utils.ylm import spin_weighted_ylm
+        assert abs(ylm_ref(l, m, 0.9, 2.2) - spin_weighted_ylm(-2, l, m, 0.9, 2.2)) < 1e-15
