@@ -98,3 +98,49 @@ class get_fd_waveform_fromFD:
             ch1 = torch.where(nz, ch1, torch.zeros_like(ch1))
             ch2 = torch.where(nz, ch2, torch.zeros_like(ch2))
         return [ch1, ch2]
+
+
+# ---- TD <-> FD comparison utilities (FDutils.py:49-64,142-178) -----------------------
+def get_fft_td_windowed(signal, window, dt):
+    """``fftshift(fft(signal[i] * window)) * dt`` for the two polarisations (FDutils.py:49-64), as cuFFT calls."""
+    import torch
+    w = _as_dev(window, torch.float64)
+    out = []
+    for s in signal[:2]:
+        s = _as_dev(s, torch.complex128)
+        if s.ndim != 1 or s.shape != w.shape:
+            raise ValueError("signal channels and window must be 1D arrays of equal length.")
+        out.append(torch.fft.fftshift(torch.fft.fft(s * w)) * dt)
+    return out
+
+
+class get_fd_waveform_fromTD:
+    """Frequency-domain channels from a TIME-domain generator (FDutils.py:142-178): FFT of the windowed channels, f >= 0
+    kept, zero outside ``non_zero_mask``.  The TD generator itself (few's TD summation) is outside this package; any
+    callable returning ``[h+, hx]`` (or ``h+ - i hx``) on a uniform grid works."""
+
+    def __init__(self, waveform_generator, positive_frequency_mask, dt, non_zero_mask=None, window=None):
+        self.waveform_generator = waveform_generator
+        self.positive_frequency_mask = positive_frequency_mask
+        self.dt = dt
+        self.non_zero_mask = non_zero_mask
+        pm = positive_frequency_mask
+        pm = np.asarray(pm.cpu() if hasattr(pm, "cpu") else pm)
+        self.window = np.ones(len(pm)) if window is None else window
+
+    def __call__(self, *args, **kwargs):
+        import torch
+        data = self.waveform_generator(*args, **kwargs)
+        if not isinstance(data, (list, tuple)):       # complex h+ - i hx (check_mode_by_mode.py:247)
+            data = _as_dev(data, torch.complex128)
+            data = [data.real, -data.imag]
+        chans = get_fft_td_windowed(data, self.window, self.dt)
+        pm = self.positive_frequency_mask
+        mask = torch.as_tensor(np.asarray(pm.cpu() if hasattr(pm, "cpu") else pm), device=chans[0].device)
+        ch1, ch2 = chans[0][mask], chans[1][mask]
+        if self.non_zero_mask is not None:
+            nz = self.non_zero_mask
+            nz = torch.as_tensor(np.asarray(nz.cpu() if hasattr(nz, "cpu") else nz), device=ch1.device)
+            ch1 = torch.where(nz, ch1, torch.zeros_like(ch1))
+            ch2 = torch.where(nz, ch2, torch.zeros_like(ch2))
+        return [ch1, ch2]

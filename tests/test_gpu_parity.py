@@ -369,6 +369,28 @@ def test_fd_window_convolution(torch_cuda):
     assert ch[0].shape[0] == (n + 1) // 2 and np.max(np.abs(ch[0].cpu().numpy() - ref0[freq >= 0.0])) <= 1e-12 * np.max(np.abs(ref0))
 
 
+def test_td_to_fd_utilities(torch_cuda):
+    """FDutils.get_fft_td_windowed / get_fd_waveform_fromTD (FDutils.py:49-64,142-178) against numpy's FFT."""
+    from emri_frequencydomainwaveforms_b200.fdutils import get_fft_td_windowed, get_fd_waveform_fromTD
+    rng = np.random.default_rng(3)
+    n, dt = 1001, 10.0
+    hp, hc = rng.normal(size=n), rng.normal(size=n)
+    window = np.hanning(n)
+    got = get_fft_td_windowed([hp, hc], window, dt)
+    ref = [np.fft.fftshift(np.fft.fft(x * window)) * dt for x in (hp, hc)]            # FDutils.py:62-63 verbatim
+    for g, r in zip(got, ref):
+        assert np.max(np.abs(g.cpu().numpy() - r)) <= 1e-12 * np.max(np.abs(r))
+    freq = np.fft.fftshift(np.fft.fftfreq(n, dt))
+    pos = freq >= 0.0
+    nz = np.zeros(int(pos.sum()), dtype=bool)
+    nz[5:200] = True
+    ad = get_fd_waveform_fromTD(lambda *a, **k: hp - 1j * hc, pos, dt, non_zero_mask=nz, window=window)
+    ch = ad()
+    exp0 = np.where(nz, ref[0][pos], 0.0)
+    assert ch[0].shape[0] == (n + 1) // 2 and np.max(np.abs(ch[0].cpu().numpy() - exp0)) <= 1e-12 * np.max(np.abs(exp0))
+    assert np.all(ch[1].cpu().numpy()[~nz] == 0)
+
+
 def test_long_trajectory_paths(generator, oracle_quad, torch_cuda):
     """L = 700 knots: the spline kernel's non-tiled variant (forward-sweep intermediates parked in the output), fewer
     modes per CTA in the segmentation kernel and a 118 KB track staging area in the mode-sum kernel."""
