@@ -33,6 +33,12 @@
 #ifndef SUM_MINB
 #define SUM_MINB 2 /* resident CTAs per SM the register allocation is tuned for */
 #endif
+#ifndef SUM_ENT_CAP
+#define SUM_ENT_CAP 96 /* entry-cache capacity: work-list entries evaluated per pass (a chunk's overlap list is walked in groups) */
+#endif
+#ifndef SUM_SF
+#define SUM_SF 1 /* 1: exact bin frequencies staged in smem; 0: recomputed per use (8 B/bin less smem) */
+#endif
 #define SUM_TILE (SUM_THREADS * SUM_BPT)
 #define ACC_STRIDE (SUM_THREADS + 4) /* row stride of the smem accumulators: conflict-free own-slot and transposed access */
 #define SEG_THREADS 128
@@ -44,6 +50,9 @@ struct emrifd_handle {
     char err[512];
     int *d_status;              // device error word
     emrifd_walker_t *d_walkers; // device copy of the walker descriptors
+    void *d_queue;              // [2 x u64 control words][B * ntiles] non-empty tile queue of the mode sum
+    int64_t queue_cap;
+    int num_sms;
     int64_t walkers_cap;
     emrifd_walker_t *h_stage[4]; // pinned staging ring
     cudaEvent_t stage_ev[4];
@@ -495,6 +504,10 @@ struct SumParams {
     const long long *chunk_rng; // [B][cpw][2] hull of positive bins per record chunk
     int cpw;
     const double *tile_dd;      // [ceil(n_data/SUM_TILE)] sum |d~|^2 per tile of the injected data, or NULL
+    int no_empty;               // 1: treat every tile as non-empty (likelihood on a slice that is not tile-aligned)
+    int ntiles;                 // tiles per walker (= ceil(j_cnt / SUM_TILE))
+    unsigned long long *queue;  // [B * ntiles] non-empty tiles as (walker << 32 | tile), filled by empty_tile_kernel
+    unsigned int *qctl;         // [0] number of queued tiles, [1] next item handed to a persistent mode_sum CTA
 };
 
 
@@ -755,16 +768,64 @@ __global__ void __launch_bounds__(256) tile_dd_kernel(const double2 *__restrict_
     if (threadIdx.x == 0) { double t = 0; for (int q = 0; q < 8; q++) t += s[q]; out[blockIdx.x] = t; }
 }
 
+// Tiles no harmonic touches (most of the band of a non-plunging eps = 1e-2 system): h = 0 is stored and the tile's likelihood
+// term is the precomputed sum |d~|^2.  A kernel of its own because this work is a pure store stream: no shared memory and
+// 8 resident CTAs per SM keep enough stores in flight to approach the HBM write rate, which the two resident CTAs of
+// mode_sum_kernel (register- and smem-limited) cannot.  The walker descriptor and the chunk hulls are fetched together
+// (one memory round trip before the stores).
 template <bool WRITE_H, bool LIKE>
-__global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumParams p) {
-    extern __shared__ __align__(16) unsigned char smraw[];
+__global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p) {
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long *crng = p.chunk_rng + (long long)blockIdx.y * p.cpw * 2;
+    const long long c_lo = crng[0], c_hi = crng[1];          // first chunk's hull: independent of the descriptor
+    const emrifd_walker_t *wp = p.w + blockIdx.y;
+    const int K = wp->K;
+    const long long out_off = wp->out_off;
+    const long long jt0 = p.j_lo + (long long)blockIdx.x * SUM_TILE;
+    const long long jend = p.j_lo + p.j_cnt;
+    const long long jt1 = (jt0 + SUM_TILE < jend ? jt0 + SUM_TILE : jend) - 1;
+    bool any = !(c_lo > jt1 || c_hi < jt0);
+    const int nrec = K * MAXBR;
+    for (int ch = 1; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
+    if (any || p.no_empty) { // work for mode_sum_kernel's persistent CTAs (processing order does not affect any result)
+        if (tid == 0) p.queue[atomicAdd(&p.qctl[0], 1u)] = ((unsigned long long)blockIdx.y << 32) | blockIdx.x;
+        return;
+    }
+    const int ntile_ = (int)(jt1 - jt0 + 1);
+    if (WRITE_H) {
+        const double2 z = make_double2(0.0, 0.0);
+        const long long zero = p.g.zero;
+#pragma unroll
+        for (int i = 0; i < SUM_BPT; i++) {
+            const int lb = wid * (32 * SUM_BPT) + i * 32 + lane;
+            if (lb >= ntile_) continue;
+            const long long j = jt0 + lb;
+            if (p.mask_positive) {
+                const long long o = out_off + (j - p.j_lo);
+                p.hp[o] = z; p.hc[o] = z;
+            } else {
+                const long long o = out_off + zero;
+                p.hp[o + j] = z; p.hc[o + j] = z;
+                if (j > 0) { p.hp[o - j] = z; p.hc[o - j] = z; }
+            }
+        }
+    }
+    if (LIKE && lane == 0) {
+        double *o = p.partial + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * (SUM_THREADS / 32) + wid) * 3;
+        o[0] = (wid == 0) ? p.tile_dd[jt0 / SUM_TILE] : 0.0; o[1] = 0.0; o[2] = 0.0;
+    }
+}
+
+template <bool WRITE_H, bool LIKE>
+__device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile_x, const int walker_y, unsigned char *smraw,
+                                              int &staged_walker) {
     __shared__ int s_list[SUM_THREADS];
     __shared__ int s_wcount[SUM_THREADS / 32];
 
-    const emrifd_walker_t wd = p.w[blockIdx.y];
+    const emrifd_walker_t wd = p.w[walker_y];
     const int L = wd.L, K = wd.K, R = 2 * K + 4;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long jt0 = p.j_lo + (long long)blockIdx.x * SUM_TILE;
+    const long long jt0 = p.j_lo + (long long)tile_x * SUM_TILE;
     const long long jend = p.j_lo + p.j_cnt;                                   // exclusive
     const long long jt1 = (jt0 + SUM_TILE < jend ? jt0 + SUM_TILE : jend) - 1; // inclusive
     const long long j0 = jt0 + (long long)tid * SUM_BPT;                       // this thread's first bin
@@ -782,18 +843,18 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
     // dynamic smem: accumulators [4][SUM_BPT][SUM_THREADS] | entry cache | T[L] | Q[L][16] | U[L][4]
     double *acc = reinterpret_cast<double *>(smraw);
     Entry *ent = reinterpret_cast<Entry *>(acc + 4 * SUM_BPT * ACC_STRIDE);
-    double *sF = reinterpret_cast<double *>(ent + SUM_THREADS); // exact bin frequencies        [SUM_BPT][SUM_THREADS]
-    double *sX = sF + SUM_BPT * SUM_THREADS;                    // roots of the current entry  [SUM_BPT][SUM_THREADS]
-    int *sJ = reinterpret_cast<int *>(sX + SUM_BPT * SUM_THREADS);  // their segment indices   [SUM_BPT][SUM_THREADS]
-    double *sT = reinterpret_cast<double *>(sJ + SUM_BPT * SUM_THREADS);
+    double *sF = reinterpret_cast<double *>(ent + SUM_ENT_CAP); // exact bin frequencies        [SUM_BPT][SUM_THREADS]
+    double *sX = sF + SUM_SF * SUM_BPT * SUM_THREADS;           // roots of the current entry  [SUM_BPT][SUM_THREADS]
+    double *sT = sX + SUM_BPT * SUM_THREADS;
+    unsigned short *sJ = reinterpret_cast<unsigned short *>(sT + SMEM_PER_KNOT * L); // segment indices [SUM_BPT][SUM_THREADS]
     double *sQ = sT + L, *sU = sT + 17 * L;
 #define ACC(c, b) acc[((c) * SUM_BPT + (b)) * ACC_STRIDE + tid]
     // ---- does any work-list chunk touch this tile? ----
     const int nrec = K * MAXBR;
-    const long long *crng = p.chunk_rng + (long long)blockIdx.y * p.cpw * 2;
+    const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
     bool any = false;
     for (int ch = 0; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
-    if (!any && (!LIKE || p.tile_dd)) {
+    if (!any && (!LIKE || p.tile_dd)) { // (not reached through the queue: empty_tile_kernel has dealt with these tiles)
         // Empty tile fast path (most tiles of a non-plunging eps = 1e-2 system): h = 0 is stored straight away,
         // the likelihood term of the tile is the precomputed sum |d~|^2 -- no shared memory, no barrier, no data read.
         const int ntile_ = (int)(jt1 - jt0 + 1);
@@ -815,25 +876,33 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
             }
         }
         if (LIKE && lane == 0) {
-            double *o = p.partial + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * (SUM_THREADS / 32) + wid) * 3;
+            double *o = p.partial + (((long long)walker_y * p.ntiles + tile_x) * (SUM_THREADS / 32) + wid) * 3;
             o[0] = (wid == 0) ? p.tile_dd[jt0 / SUM_TILE] : 0.0; o[1] = 0.0; o[2] = 0.0;
         }
         return;
     }
 #pragma unroll
     for (int i = 0; i < 4 * SUM_BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
+#if SUM_SF
 #pragma unroll
     for (int b = 0; b < SUM_BPT; b++) {
         const long long jj = j0 + b;
         sF[b * SUM_THREADS + tid] = (b < nb) ? (p.g.fpos ? p.g.fpos[jj] : rmul((double)(int)jj, p.g.val)) : 0.0;
     }
+#define BINF(pF_, b_) ((pF_)[0])
+#define BINF2(pF_, b_) ((pF_)[SUM_THREADS])
+#else
+#define BINF(pF_, b_) (p.g.fpos ? p.g.fpos[j0 + (b_)] : rmul((double)(int)(j0 + (b_)), p.g.val))
+#define BINF2(pF_, b_) BINF(pF_, (b_) + 1)
+#endif
 
     const double val = p.g.val;
     const double *fpos = p.g.fpos;
 
     // ---- if some chunk touches the tile stage the shared tracks right away (knots, the four track quads, reduced
     //      knot phases) so that the loads overlap the first record scan ----
-    if (any) {
+    if (any && staged_walker != walker_y) { // (a persistent CTA often gets consecutive tiles of one walker: tracks stay staged)
+        staged_walker = walker_y;
         const double *t = p.t + wd.knot_off;
         for (int i = tid; i < L; i += SUM_THREADS) sT[i] = t[i];
         for (int i = tid; i < L * 4; i += SUM_THREADS) {
@@ -875,8 +944,11 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
         if (pred) s_list[off + __popc(bal & ((1u << lane) - 1))] = r;
         __syncthreads();
         if (count == 0) continue; // block-uniform
-        if (tid < count) { // fill the entry cache (ordered: deterministic summation order)
-            const emrifd_branch_t b = br[s_list[tid]];
+        for (int g0 = 0; g0 < count; g0 += SUM_ENT_CAP) { // the overlap list is evaluated in groups of SUM_ENT_CAP entries
+        const int gcount = count - g0 < SUM_ENT_CAP ? count - g0 : SUM_ENT_CAP;
+        if (g0 > 0) __syncthreads(); // every warp is done with the previous group's entries
+        if (tid < gcount) { // fill the entry cache (ordered: deterministic summation order)
+            const emrifd_branch_t b = br[s_list[g0 + tid]];
             const int k = b.mode;
             const int mi = marr[k], ni = narr[k];
             const double2 yp = ylm[k], ym = ylm[K + k];
@@ -928,7 +1000,7 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
         // ---- evaluate: every thread walks its SUM_BPT consecutive bins along each listed branch ----
         if (nb > 0) {
             const int tb0 = tid * SUM_BPT;
-            for (int li = 0; li < count; li++) {
+            for (int li = 0; li < gcount; li++) {
                 const Entry &E = ent[li];
 #pragma unroll 1
                 for (int side = 0; side < 2; side++) {
@@ -953,9 +1025,9 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                         double xprev = 0.0, fprev = 0.0, rprev = 0.0;
                         const double *pF = sF + tid + bl * SUM_THREADS;
                         double *pX = sX + tid + bl * SUM_THREADS;
-                        int *pJ = sJ + tid + bl * SUM_THREADS;
+                        unsigned short *pJ = sJ + tid + bl * SUM_THREADS;
                         for (int b = bl; b <= bh; b++, pF += SUM_THREADS, pX += SUM_THREADS, pJ += SUM_THREADS) {
-                            const double f = sgn * pF[0];
+                            const double f = sgn * BINF(pF, b);
                             const bool inside = (j >= 0) && (dir > 0 ? (f >= segA && f < segB) : (f <= segA && f > segB));
                             double x, rr;
                             bool ok = false;
@@ -1005,14 +1077,14 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                             }
                             xprev = x; fprev = f; rprev = rr;
                             pX[0] = x;
-                            pJ[0] = j;
+                            pJ[0] = (unsigned short)j;
                         }
                     }
                     // ---- stage 2: evaluate the bins two at a time (same segment) in straight-line code ----
                     {
                         const double *pF = sF + tid + bl * SUM_THREADS;
                         const double *pX = sX + tid + bl * SUM_THREADS;
-                        const int *pJ = sJ + tid + bl * SUM_THREADS;
+                        const unsigned short *pJ = sJ + tid + bl * SUM_THREADS;
                         int id0 = offd + bl * ACC_STRIDE, im0 = offm + bl * ACC_STRIDE;
                         for (int b = bl; b <= bh;) {
                             const int j = pJ[0];
@@ -1026,13 +1098,13 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                             const double tj = sT[j];
                             if (two) {
                                 const double x2[2] = {pX[0], pX[SUM_THREADS]};
-                                const double f2[2] = {sgn * pF[0], sgn * pF[SUM_THREADS]};
+                                const double f2[2] = {sgn * BINF(pF, b), sgn * BINF2(pF, b)};
                                 eval_bins<2>(x2, f2, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
                                 b += 2; pF += 2 * SUM_THREADS; pX += 2 * SUM_THREADS; pJ += 2 * SUM_THREADS;
                                 id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
                             } else {
                                 const double x1[1] = {pX[0]};
-                                const double f1[1] = {sgn * pF[0]};
+                                const double f1[1] = {sgn * BINF(pF, b)};
                                 eval_bins<1>(x1, f1, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
                                 b += 1; pF += SUM_THREADS; pX += SUM_THREADS; pJ += SUM_THREADS;
                                 id0 += ACC_STRIDE; im0 += ACC_STRIDE;
@@ -1042,6 +1114,7 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
                 }
             }
         }
+        } // entry groups
     }
 
     // ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
@@ -1099,9 +1172,38 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumPara
             a2 += __shfl_down_sync(0xffffffffu, a2, o);
         }
         if (lane == 0) {
-            double *o = p.partial + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * (SUM_THREADS / 32) + wid) * 3;
+            double *o = p.partial + (((long long)walker_y * p.ntiles + tile_x) * (SUM_THREADS / 32) + wid) * 3;
             o[0] = a0; o[1] = a1; o[2] = a2;
         }
+    }
+}
+
+// Persistent CTAs (one grid of #SM x resident-CTAs) pull the non-empty tiles queued by empty_tile_kernel: the heavy kernel
+// is never launched on the >90 % of the band that a sparse system leaves empty, and tiles of very different cost balance
+// dynamically.
+template <bool WRITE_H, bool LIKE>
+__global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    __shared__ unsigned long long s_q[2]; // double-buffered queue items: the next one is fetched while the current tile runs
+    const unsigned int nq = p.qctl[0];
+    const unsigned long long none = ~0ull;
+    if (threadIdx.x == 0) {
+        const unsigned int it = atomicAdd(&p.qctl[1], 1u);
+        s_q[0] = it < nq ? p.queue[it] : none;
+    }
+    __syncthreads();
+    int staged_walker = -1;
+    for (int cur = 0;; cur ^= 1) {
+        const unsigned long long q = s_q[cur];
+        if (q == none) return;
+        unsigned long long qn = none;
+        if (threadIdx.x == 0) { // in flight during the tile; consumed just before the barrier below
+            const unsigned int it = atomicAdd(&p.qctl[1], 1u);
+            if (it < nq) qn = p.queue[it];
+        }
+        mode_sum_tile<WRITE_H, LIKE>(p, (int)(q & 0xffffffffu), (int)(q >> 32), smraw, staged_walker);
+        if (threadIdx.x == 0) s_q[cur ^ 1] = qn;
+        __syncthreads(); // every warp has left the tile (shared memory is reused) and sees the next item
     }
 }
 
@@ -1421,7 +1523,8 @@ static size_t spline_smem_bytes(int L, bool tiled) {
 }
 
 static size_t sum_smem_bytes(int L) {
-    return sizeof(double) * 4 * SUM_BPT * ACC_STRIDE + 20 * SUM_BPT * SUM_THREADS + sizeof(Entry) * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
+    return sizeof(double) * 4 * SUM_BPT * ACC_STRIDE + (8 * SUM_SF + 8 + 2) * SUM_BPT * SUM_THREADS + sizeof(Entry) * SUM_ENT_CAP +
+           sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
 
 static int ensure_bytes(emrifd_handle *h, void **ptr, int64_t *cap, int64_t need, bool pinned_host = false) {
@@ -1507,6 +1610,7 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
     const int big = optin - 2048; // static smem of the kernel (< 2 KB) comes out of the same budget
     h->max_dyn_smem = big;
+    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
     cudaFuncSetAttribute(spline_build_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(spline_build_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(spline_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
@@ -1525,7 +1629,7 @@ int emrifd_destroy(emrifd_handle_t *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd);
+    cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_queue); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd);
     if (h->h_ws) cudaFreeHost(h->h_ws);
     for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); cudaEventDestroy(h->stage_ev[i]); }
     for (int i = 0; i < 64; i++) { cudaEventDestroy(h->ev_a[i]); cudaEventDestroy(h->ev_b[i]); }
@@ -1672,9 +1776,30 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     dim3 grid((unsigned)ntiles, (unsigned)B);
     int ev = -1;
     if (h->timing && h->ev_n < 64) { ev = h->ev_n++; cudaEventRecord(h->ev_a[ev], h->stream); }
-    if (write_h && like) mode_sum_kernel<true, true><<<grid, SUM_THREADS, smem, h->stream>>>(p);
-    else if (write_h) mode_sum_kernel<true, false><<<grid, SUM_THREADS, smem, h->stream>>>(p);
-    else mode_sum_kernel<false, true><<<grid, SUM_THREADS, smem, h->stream>>>(p);
+    // pass 1 (full grid, light): empty tiles are written here, the others are queued; pass 2: persistent CTAs drain the queue
+    p.no_empty = (like && !p.tile_dd) ? 1 : 0;
+    p.ntiles = (int)ntiles;
+    {
+        int rc = ensure_bytes(h, (void **)&h->d_queue, &h->queue_cap, (int64_t)sizeof(unsigned long long) * ntiles * B + 16);
+        if (rc) return rc;
+        p.qctl = (unsigned int *)h->d_queue;
+        p.queue = (unsigned long long *)h->d_queue + 2;
+        CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, 16, h->stream));
+    }
+    if (write_h && like) empty_tile_kernel<true, true><<<grid, SUM_THREADS, 0, h->stream>>>(p);
+    else if (write_h) empty_tile_kernel<true, false><<<grid, SUM_THREADS, 0, h->stream>>>(p);
+    else empty_tile_kernel<false, true><<<grid, SUM_THREADS, 0, h->stream>>>(p);
+    h->launches++;
+    int per_sm = 0;
+    if (write_h && like) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, true>, SUM_THREADS, smem);
+    else if (write_h) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, false>, SUM_THREADS, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<false, true>, SUM_THREADS, smem);
+    if (per_sm < 1) per_sm = 1;
+    int64_t pgrid = (int64_t)h->num_sms * per_sm;
+    if (pgrid > ntiles * B) pgrid = ntiles * B;
+    if (write_h && like) mode_sum_kernel<true, true><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
+    else if (write_h) mode_sum_kernel<true, false><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
+    else mode_sum_kernel<false, true><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
     if (ev >= 0) cudaEventRecord(h->ev_b[ev], h->stream);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
