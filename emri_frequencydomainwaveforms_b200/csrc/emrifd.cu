@@ -637,8 +637,10 @@ struct __align__(16) Entry {
 
 // ---- evaluation of W (1 or 2) bins of one segment in straight-line code: the W independent dependency chains
 //      (amplitude Horner, SPA factor, phase, sincos) interleave in the instruction stream (ILP without more warps) ----
-__device__ __forceinline__ void spa_fix(double fdot, double fddot, double s, double u, double &re, double &im) {
-    // rare path of the SPA factor: X = 1/u < 1024 (late inspiral, turnover neighbourhood); returns R/sqrt|fdot|
+__device__ __noinline__ double2 spa_fix(double fdot, double fddot, double s, double u) {
+    // rare path of the SPA factor: X = 1/u < 1024 (late inspiral, turnover neighbourhood); returns R/sqrt|fdot|.
+    // Out of line and returning by value: the hot loop keeps no address-taken locals and no code of this path.
+    double re, im;
     if (u <= 0.03125) {
         const double w = u * u;
         double pr = k13_asym_re[6], pi = k13_asym_im[6];
@@ -655,6 +657,7 @@ __device__ __forceinline__ void spa_fix(double fdot, double fddot, double s, dou
         const double sc = cbrt(1.4472025091165353 / fabs(fddot));
         re *= sc; im *= sc;
     }
+    return make_double2(re, im);
 }
 
 template <int W>
@@ -695,7 +698,7 @@ __device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f
     }
 #pragma unroll
     for (int i = 0; i < W; i++)
-        if (!(uu[i] <= 0.0009765625)) spa_fix(fd[i], fdd[i], s[i], uu[i], re[i], im[i]);
+        if (!(uu[i] <= 0.0009765625)) { const double2 g = spa_fix(fd[i], fdd[i], s[i], uu[i]); re[i] = g.x; im[i] = g.y; }
     const double ypr = E.ypr, ypi = E.ypi, sdir = (double)E.dir;
     const bool mirror = E.mirror;
 #pragma unroll
