@@ -50,6 +50,7 @@ def draw_walkers(n_distinct, n_total, seed, T=T_YR, dt=DT, eps=EPS, workload="pl
     tries = 0
     if workload == "cfg1":   # BASELINE.json configs[0]: M=1e6, mu=10, p0=12, e0=0.35 (does not plunge within 1 yr: sparse support)
         it = gen.prepare(1e6, 10.0, 12.0, 0.35, np.pi / 3, -np.pi / 2, dist=1.0, T=T, dt=dt, eps=eps)
+        it["raw"] = (1e6, 10.0, 12.0, 0.35, np.pi / 3)
         base.append(it)
     while len(base) < n_distinct and tries < 50 * n_distinct and workload != "cfg1":
         tries += 1
@@ -63,6 +64,7 @@ def draw_walkers(n_distinct, n_total, seed, T=T_YR, dt=DT, eps=EPS, workload="pl
             it = gen.prepare(M, mu, p0, e0, theta, -np.pi / 2, dist=1.0, T=T, dt=dt, eps=eps)
         except ValueError:
             continue
+        it["raw"] = (M, mu, p0, e0, theta)
         base.append(it)
     if not base:
         raise RuntimeError("no valid parameter draw")
@@ -71,8 +73,10 @@ def draw_walkers(n_distinct, n_total, seed, T=T_YR, dt=DT, eps=EPS, workload="pl
         b = base[i % len(base)]
         it = dict(b)
         # distinct initial phases: they shift Phi_phi(t), Phi_r(t) by constants, no new ODE solve needed
-        it["Phi_phi"] = b["Phi_phi"] + rng.uniform(0, 2 * np.pi)
-        it["Phi_r"] = b["Phi_r"] + rng.uniform(0, 2 * np.pi)
+        dphi, dr = rng.uniform(0, 2 * np.pi), rng.uniform(0, 2 * np.pi)
+        it["Phi_phi"] = b["Phi_phi"] + dphi
+        it["Phi_r"] = b["Phi_r"] + dr
+        it["raw"] = b["raw"] + (dphi, dr)      # (M, mu, p0, e0, theta, Phi_phi0, Phi_r0): the same walker as raw parameters
         items.append(it)
     return items
 
@@ -300,6 +304,47 @@ def main():
     clocks = sampler.finish()
     h.status()
 
+    # ---- e2e from RAW PARAMETERS through the generator's batched public call: host trajectories (threaded native ODE)
+    #      -> H2D of the sparse tracks -> device amplitudes / Ylm / mode selection / compaction -> the same spline /
+    #      segment / sum + likelihood launches -> D2H of ll.  Everything a user's get_ll(params) pays is inside.
+    e2e_par = None
+    try:
+        from emri_frequencydomainwaveforms_b200.waveform import FastSchwarzschildEccentricFlux
+        genp = FastSchwarzschildEccentricFlux(sum_kwargs=dict(pad_output=True, output_type="fd", odd_len=True))
+        raw = np.array([it["raw"] for it in items])
+
+        def step_params():
+            dbp, okp = genp.prepare_batch_device(raw[:, 0], raw[:, 1], raw[:, 2], raw[:, 3], raw[:, 4], -np.pi / 2, dist=1.0,
+                                                 Phi_phi0=raw[:, 5], Phi_r0=raw[:, 6], T=T_YR, dt=DT, eps=EPS, handle=h)
+            dbp.pb.walkers["out_off"] = np.arange(dbp.pb.B, dtype=np.int64) * n
+            h.check(h.lib.emrifd_fd_waveform_batch(
+                h.h, dbp.pb.walkers.ctypes.data, dbp.pb.B, dbp.t.data_ptr(), dbp.teuk.data_ptr(), dbp.f_phi.data_ptr(), dbp.f_r.data_ptr(),
+                dbp.Phi_phi.data_ptr(), dbp.Phi_r.data_ptr(), dbp.m.data_ptr(), dbp.n.data_ptr(), dbp.ylm.data_ptr(), N, val, None,
+                flags, dbp.coeff.data_ptr(), dbp.branches.data_ptr(), hp.data_ptr(), hc.data_ptr(), like.data_ptr()))
+            return like[:dbp.pb.B].cpu().numpy(), dbp
+
+        for _ in range(2):
+            llp, dbp = step_params()
+        psteps = max(3, args.steps // 2)
+        barrier()
+        t0 = time.perf_counter()
+        for _ in range(psteps):
+            llp, dbp = step_params()
+        torch.cuda.synchronize()
+        el = time.perf_counter() - t0
+        barrier()
+        tt = torch.tensor([el], dtype=torch.float64, device=dev)
+        if dist is not None:
+            dist.all_reduce(tt, op=dist.ReduceOp.MAX)
+        e2e_par = {"value": world * B * psteps / tt[0].item(), "unit": "walkers/s", "ms_per_step": 1e3 * tt[0].item() / psteps,
+                   "h2d_bytes_per_step": int(dbp.h2d_bytes), "d2h_bytes_per_step": int(llp.nbytes + 4 * B),
+                   "host_threads": len(os.sched_getaffinity(0)),
+                   "call": "FastSchwarzschildEccentricFlux.prepare_batch_device(raw parameters) + emrifd_fd_waveform_batch: host trajectory ODE "
+                           "(threaded) -> H2D tracks -> device amplitudes/Ylm/mode selection/compaction -> spline/segment/sum+likelihood -> D2H ll",
+                   "modes_per_walker": dbp.pb.n_modes / dbp.pb.B}
+    except Exception as exc:   # auxiliary figure: never let it break the bench line
+        e2e_par = {"value": None, "unit": "walkers/s", "error": str(exc)[:200]}
+
     # ---- dominant kernel (mode_sum) timed live with CUDA events on its own stream --------------
     h.check(h.lib.emrifd_sum_kernel_time(h.h, 1, None, None))
     ksteps = min(args.steps, 32)
@@ -356,7 +401,8 @@ def main():
                  "peak_source": "emrifd_bench_fp64_fma: CUDA-core DFMA micro-benchmark measured in this run (MEASURED_PEAKS.json has no FP64 entry; "
                                 "no tensor cores on this path)"}
     binding, other = (roof_fp64, roof_hbm) if roof_fp64["frac"] >= roof_hbm["frac"] else (roof_hbm, roof_fp64)
-    common = {"kernel": "mode_sum_kernel<true,true>", "kernel_ms": k_avg_ms, "kernel_share_of_step": k_avg_ms / (ms_dev / args.steps)}
+    common = {"kernel": "empty_tile_kernel<true,true> + mode_sum_kernel<true,true> (one event bracket: store stream for empty tiles, "
+                        "persistent CTAs for the others)", "kernel_ms": k_avg_ms, "kernel_share_of_step": k_avg_ms / (ms_dev / args.steps)}
     binding = dict(binding, **common)
 
     line = {
@@ -366,6 +412,7 @@ def main():
         "e2e": {"value": e2e_value, "unit": "walkers/s", "h2d_bytes_per_step": pb.h2d_bytes(), "d2h_bytes_per_step": int(like_host.nbytes),
                 "ms_per_step": ms_e2e_wall / args.steps,
                 "call": "emrifd_loglike_batch_host (host packed sparse inputs -> H2D -> spline/segment/sum+likelihood -> D2H ll)"},
+        "e2e_from_parameters": e2e_par,
         "gpu_launches": int(launches),
         "clocks": clocks,
         "roofline": binding,

@@ -39,6 +39,11 @@
 #ifndef SUM_SF
 #define SUM_SF 1 /* 1: exact bin frequencies staged in smem; 0: recomputed per use (8 B/bin less smem) */
 #endif
+#ifdef SUM_MAXNREG
+#define SUM_BOUNDS __maxnreg__(SUM_MAXNREG)
+#else
+#define SUM_BOUNDS __launch_bounds__(SUM_THREADS, SUM_MINB)
+#endif
 #define SUM_TILE (SUM_THREADS * SUM_BPT)
 #define ACC_STRIDE (SUM_THREADS + 4) /* row stride of the smem accumulators: conflict-free own-slot and transposed access */
 #define SEG_THREADS 128
@@ -1185,7 +1190,7 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
 // is never launched on the >90 % of the band that a sparse system leaves empty, and tiles of very different cost balance
 // dynamically.
 template <bool WRITE_H, bool LIKE>
-__global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_kernel(SumParams p) {
+__global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ unsigned long long s_q[2]; // double-buffered queue items: the next one is fetched while the current tile runs
     const unsigned int nq = p.qctl[0];
