@@ -76,6 +76,14 @@ def main():
     for _ in range(reps):
         like(start, **emri_kwargs)
     t_call = (time.perf_counter() - t0) / reps
+    # the same call with the NumPy host producers (amplitudes, Ylm, mode selection on the CPU)
+    model_h = FDTemplateModel(few_gen_list, f_arr=newfreq, producers="host")
+    like_h = Likelihood(model_h, 2, f_arr=f_arr_ds, parameter_transforms={"emri": tc}, fill_data_noise=True, subset=24)
+    like_h.inject_signal(data_stream=check, noise_fn=[get_sensitivity, get_sensitivity], noise_kwargs=[{}, {}])
+    ll_h = like_h(start, **emri_kwargs)
+    t0 = time.perf_counter()
+    like_h(start, **emri_kwargs)
+    t_call_host = time.perf_counter() - t0
     p14 = tc.both_transforms(start)
     t0 = time.perf_counter()
     items, ok = model.prepare_batch(p14, **emri_kwargs)
@@ -98,6 +106,9 @@ def main():
         "full_grid_waveform_s": t_full,
         "likelihood_call_s": t_call, "host_producers_s": t_host, "accelerated_path_s": t_gpu,
         "likelihoods_per_s_accelerated_path": nwalkers / t_gpu, "likelihoods_per_s_whole_call": nwalkers / t_call,
+        "producers": model.producers, "likelihood_call_s_host_producers": t_call_host,
+        "likelihoods_per_s_whole_call_host_producers": nwalkers / t_call_host,
+        "max_abs_ll_diff_device_vs_host_producers": float(np.nanmax(np.abs(ll - ll_h))),
         "h2d_bytes": pb.h2d_bytes(), "gpu_launches_per_call": 5}))
 
 
