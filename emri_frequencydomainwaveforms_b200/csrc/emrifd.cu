@@ -509,6 +509,7 @@ struct SumParams {
     const long long *chunk_rng; // [B][cpw][2] hull of positive bins per record chunk
     int cpw;
     const double *tile_dd;      // [ceil(n_data/SUM_TILE)] sum |d~|^2 per tile of the injected data, or NULL
+    long long tile_first, tile_stride; // this launch owns tiles tile_first + i * tile_stride of [j_lo, j_lo + j_cnt) (0, 1 = all)
     int no_empty;               // 1: treat every tile as non-empty (likelihood on a slice that is not tile-aligned)
     int ntiles;                 // tiles per walker (= ceil(j_cnt / SUM_TILE))
     unsigned long long *queue;  // [B * ntiles] non-empty tiles as (walker << 32 | tile), filled by empty_tile_kernel
@@ -789,7 +790,7 @@ __global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p)
     const emrifd_walker_t *wp = p.w + blockIdx.y;
     const int K = wp->K;
     const long long out_off = wp->out_off;
-    const long long jt0 = p.j_lo + (long long)blockIdx.x * SUM_TILE;
+    const long long jt0 = p.j_lo + (p.tile_first + (long long)blockIdx.x * p.tile_stride) * SUM_TILE;
     const long long jend = p.j_lo + p.j_cnt;
     const long long jt1 = (jt0 + SUM_TILE < jend ? jt0 + SUM_TILE : jend) - 1;
     bool any = !(c_lo > jt1 || c_hi < jt0);
@@ -833,7 +834,7 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     const emrifd_walker_t wd = p.w[walker_y];
     const int L = wd.L, K = wd.K, R = 2 * K + 4;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long jt0 = p.j_lo + (long long)tile_x * SUM_TILE;
+    const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * SUM_TILE;
     const long long jend = p.j_lo + p.j_cnt;                                   // exclusive
     const long long jt1 = (jt0 + SUM_TILE < jend ? jt0 + SUM_TILE : jend) - 1; // inclusive
     const long long j0 = jt0 + (long long)tid * SUM_BPT;                       // this thread's first bin
@@ -862,33 +863,7 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
     bool any = false;
     for (int ch = 0; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
-    if (!any && (!LIKE || p.tile_dd)) { // (not reached through the queue: empty_tile_kernel has dealt with these tiles)
-        // Empty tile fast path (most tiles of a non-plunging eps = 1e-2 system): h = 0 is stored straight away,
-        // the likelihood term of the tile is the precomputed sum |d~|^2 -- no shared memory, no barrier, no data read.
-        const int ntile_ = (int)(jt1 - jt0 + 1);
-        if (WRITE_H) {
-            const double2 z = make_double2(0.0, 0.0);
-#pragma unroll
-            for (int i = 0; i < SUM_BPT; i++) {
-                const int lb = wid * (32 * SUM_BPT) + i * 32 + lane;
-                if (lb >= ntile_) continue;
-                const long long j = jt0 + lb;
-                if (p.mask_positive) {
-                    const long long o = wd.out_off + (j - p.j_lo);
-                    p.hp[o] = z; p.hc[o] = z;
-                } else {
-                    const long long o = wd.out_off + zero;
-                    p.hp[o + j] = z; p.hc[o + j] = z;
-                    if (j > 0) { p.hp[o - j] = z; p.hc[o - j] = z; }
-                }
-            }
-        }
-        if (LIKE && lane == 0) {
-            double *o = p.partial + (((long long)walker_y * p.ntiles + tile_x) * (SUM_THREADS / 32) + wid) * 3;
-            o[0] = (wid == 0) ? p.tile_dd[jt0 / SUM_TILE] : 0.0; o[1] = 0.0; o[2] = 0.0;
-        }
-        return;
-    }
+    if (!any && (!LIKE || p.tile_dd)) return; // (direct-grid launches only: empty_tile_kernel has dealt with this tile)
 #pragma unroll
     for (int i = 0; i < 4 * SUM_BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
 #if SUM_SF
@@ -1213,6 +1188,16 @@ __global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
         if (threadIdx.x == 0) s_q[cur ^ 1] = qn;
         __syncthreads(); // every warp has left the tile (shared memory is reused) and sees the next item
     }
+}
+
+// Small launches (a few hundred tiles: one bin-sharded slice of a single long waveform, or a single short waveform) fit in
+// about one wave of CTAs; there the hardware's breadth-first placement of a plain (tile, walker) grid balances the SMs
+// better than queue order (measured on the 8-GPU bin-sharded configs[3] slices: 8.6 vs 13.1 ms), so they keep a direct grid.
+template <bool WRITE_H, bool LIKE>
+__global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_direct_kernel(SumParams p) {
+    extern __shared__ __align__(16) unsigned char smraw[];
+    int staged_walker = -1;
+    mode_sum_tile<WRITE_H, LIKE>(p, (int)blockIdx.x, (int)blockIdx.y, smraw, staged_walker);
 }
 
 // deterministic second stage: one CTA per walker
@@ -1628,6 +1613,9 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaFuncSetAttribute(mode_sum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(mode_sum_direct_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(mode_sum_direct_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    cudaFuncSetAttribute(mode_sum_direct_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     if (cudaGetLastError() != cudaSuccess) { delete h; return EMRIFD_ERR_CUDA; }
     *out = h;
     return 0;
@@ -1746,7 +1734,7 @@ int emrifd_batch_segment(emrifd_handle_t *h, const emrifd_walker_t *walkers, int
 static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const double *t, const double *coeff,
                          const int32_t *m_arr, const int32_t *n_arr, const double *ylm, const emrifd_branch_t *branches,
                          int64_t N, double val, const double *fpos, int flags, int64_t j_lo, int64_t j_cnt,
-                         double *hp, double *hc, double *like_out) {
+                         double *hp, double *hc, double *like_out, int64_t tile_first = 0, int64_t tile_stride = 1) {
     const bool write_h = hp && hc, like = like_out != nullptr;
     if (!write_h && !like) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum: nothing to compute (no output requested)");
     if (like && !h->d_data) return set_err(h, EMRIFD_ERR_NO_DATA, "likelihood requested before emrifd_set_data");
@@ -1763,7 +1751,14 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     p.include_minus_m = (flags & EMRIFD_INCLUDE_MINUS_M) != 0; p.mask_positive = mask_pos;
     p.hp = (double2 *)hp; p.hc = (double2 *)hc;
     p.dw = (const double2 *)h->d_data; p.wf = h->d_wfac; p.n_data = h->n_data;
-    const int64_t ntiles = (j_cnt + SUM_TILE - 1) / SUM_TILE;
+    const int64_t ntiles_all = (j_cnt + SUM_TILE - 1) / SUM_TILE;
+    if (tile_stride < 1 || tile_first < 0) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum: bad tile_first / tile_stride");
+    if (tile_first >= ntiles_all) { // this rank owns no tile: all sums are zero
+        if (like) CUDA_TRY(h, cudaMemsetAsync(like_out, 0, sizeof(double) * 3 * (size_t)B, h->stream));
+        return 0;
+    }
+    const int64_t ntiles = (ntiles_all - tile_first + tile_stride - 1) / tile_stride; // tiles of this launch
+    p.tile_first = tile_first; p.tile_stride = tile_stride;
     if (like) {
         int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * 3 * ntiles * (SUM_THREADS / 32) * B);
         if (rc) return rc;
@@ -1804,8 +1799,11 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<false, true>, SUM_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     int64_t pgrid = (int64_t)h->num_sms * per_sm;
-    if (pgrid > ntiles * B) pgrid = ntiles * B;
-    if (write_h && like) mode_sum_kernel<true, true><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
+    if (ntiles * B <= 4 * pgrid) { // about one wave: direct grid (see mode_sum_direct_kernel)
+        if (write_h && like) mode_sum_direct_kernel<true, true><<<grid, SUM_THREADS, smem, h->stream>>>(p);
+        else if (write_h) mode_sum_direct_kernel<true, false><<<grid, SUM_THREADS, smem, h->stream>>>(p);
+        else mode_sum_direct_kernel<false, true><<<grid, SUM_THREADS, smem, h->stream>>>(p);
+    } else if (write_h && like) mode_sum_kernel<true, true><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
     else if (write_h) mode_sum_kernel<true, false><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
     else mode_sum_kernel<false, true><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
     if (ev >= 0) cudaEventRecord(h->ev_b[ev], h->stream);
@@ -1831,6 +1829,25 @@ int emrifd_batch_sum(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t
     cudaSetDevice(h->device);
     if ((rc = upload_walkers(h, walkers, B))) return rc;
     return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, j_lo, j_cnt, hp, hc, like_out);
+}
+
+int emrifd_tile_bins(void) { return SUM_TILE; }
+
+int emrifd_batch_sum_cyclic(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,
+                            const double *t, const double *coeff, const int32_t *m_arr, const int32_t *n_arr,
+                            const double *ylm, const emrifd_branch_t *branches,
+                            int64_t N, double val, const double *fpos, int flags, int64_t tile_first, int64_t tile_stride,
+                            double *hp, double *hc, double *like_out) {
+    if (!h || !t || !coeff || !m_arr || !n_arr || !ylm || !branches) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum_cyclic: NULL argument");
+    if ((hp || hc) && !(flags & EMRIFD_MASK_POSITIVE))
+        return set_err(h, EMRIFD_ERR_INVALID, "batch_sum_cyclic: waveform output needs EMRIFD_MASK_POSITIVE");
+    int Lmax, Kmax, rc;
+    if ((rc = validate_walkers(h, walkers, B, &Lmax, &Kmax))) return rc;
+    if ((rc = check_grid(h, N, val, fpos))) return rc;
+    cudaSetDevice(h->device);
+    if ((rc = upload_walkers(h, walkers, B))) return rc;
+    return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, 0, (N + 1) / 2, hp, hc, like_out,
+                         tile_first, tile_stride);
 }
 
 int emrifd_fd_waveform_batch(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,

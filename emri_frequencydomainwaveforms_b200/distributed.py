@@ -106,6 +106,40 @@ def bin_sharded_sums(compute_partial, slices, group=None, device="cpu"):
 
 
 # ---- GPU conveniences ---------------------------------------------------------------------------
+def cyclic_tile_owner(world, rank):
+    """(tile_first, tile_stride) of ``rank`` in the cyclic tile sharding: rank r owns tiles r, r + world, ..."""
+    if not (0 <= rank < world):
+        raise ValueError("rank outside [0, world)")
+    return rank, world
+
+
+def gpu_bin_sharded_loglike_cyclic(db, N, val=0.0, fpos_dev=None, include_minus_m=True, group=None):
+    """Frequency-bin sharded likelihood with CYCLIC tile ownership (emrifd_batch_sum_cyclic): no work histogram, no
+    device->host copy of the work-list; every rank builds the (replicated, MB-sized) splines and work-list, sums its
+    interleaved tiles, and one NCCL all_reduce(SUM) of [B, 3] doubles finishes."""
+    import torch
+    import torch.distributed as dist
+    from . import _lib
+    from ._lib import INCLUDE_MINUS_M, MASK_POSITIVE
+    h, pb = db.handle, db.pb
+    world, rank = dist.get_world_size(group), dist.get_rank(group)
+    flags = (INCLUDE_MINUS_M if include_minus_m else 0) | MASK_POSITIVE
+    h.check(h.lib.emrifd_batch_spline(h.h, pb.walkers.ctypes.data, pb.B, db.t.data_ptr(), db.teuk.data_ptr(),
+                                      db.f_phi.data_ptr(), db.f_r.data_ptr(), db.Phi_phi.data_ptr(), db.Phi_r.data_ptr(),
+                                      db.coeff.data_ptr()))
+    h.check(h.lib.emrifd_batch_segment(h.h, pb.walkers.ctypes.data, pb.B, db.t.data_ptr(), db.coeff.data_ptr(),
+                                       db.m.data_ptr(), db.n.data_ptr(), int(N), float(val), _lib.ptr(fpos_dev),
+                                       db.branches.data_ptr(), None))
+    first, stride = cyclic_tile_owner(world, rank)
+    out = torch.zeros((pb.B, 3), dtype=torch.float64, device=h.torch_device)
+    h.check(h.lib.emrifd_batch_sum_cyclic(h.h, pb.walkers.ctypes.data, pb.B, db.t.data_ptr(), db.coeff.data_ptr(),
+                                          db.m.data_ptr(), db.n.data_ptr(), db.ylm.data_ptr(), db.branches.data_ptr(),
+                                          int(N), float(val), _lib.ptr(fpos_dev), flags, int(first), int(stride), None, None,
+                                          out.data_ptr()))
+    dist.all_reduce(out, op=dist.ReduceOp.SUM, group=group)
+    return out
+
+
 def gpu_bin_sharded_loglike(db, N, val=0.0, fpos_dev=None, include_minus_m=True, group=None, slices=None):
     """Frequency-bin sharded likelihood of a DeviceBatch replicated on every rank (NCCL all_reduce of [B,3]).
     ``slices``: reuse a previous work-balanced partition (e.g. across MCMC steps, where the work distribution

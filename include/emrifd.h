@@ -116,6 +116,17 @@ int emrifd_batch_sum(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t
                      int64_t j_lo, int64_t j_cnt, /* positive-bin slice [j_lo, j_lo+j_cnt); 0,(N+1)/2 = all */
                      double *hp, double *hc,      /* may both be NULL (likelihood only) */
                      double *like_out /* [B][3] device: ll, <d|h>, <h|h>; NULL = no likelihood */);
+/* Cyclic tile sharding of the mode sum (multi-GPU frequency-bin sharding of ONE long, high-mode-count waveform, SURVEY.md
+ * section 8e(2)): the f >= 0 bins are cut into tiles of emrifd_tile_bins() bins and this call evaluates tiles tile_first,
+ * tile_first + tile_stride, ... (rank r of W passes r, W).  Neighbouring tiles carry similar work, so the interleave balances
+ * the ranks without a work histogram, and every rank keeps several waves of tiles.  like_out [B][3] holds the partial sums
+ * over the owned tiles (all_reduce(SUM) them); hp/hc, if given, need EMRIFD_MASK_POSITIVE and receive the owned tiles only. */
+int emrifd_tile_bins(void);
+int emrifd_batch_sum_cyclic(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,
+                            const double *t, const double *coeff, const int32_t *m_arr, const int32_t *n_arr,
+                            const double *ylm, const emrifd_branch_t *branches,
+                            int64_t N, double val, const double *fpos, int flags, int64_t tile_first, int64_t tile_stride,
+                            double *hp, double *hc, double *like_out);
 int emrifd_fd_waveform_batch(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,
                              const double *t, const double *teuk, const double *f_phi, const double *f_r,
                              const double *Phi_phi, const double *Phi_r,

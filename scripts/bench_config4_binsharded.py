@@ -25,6 +25,8 @@ def main():
     ap.add_argument("--dt", type=float, default=10.0)
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=2)
+    ap.add_argument("--sharding", default="cyclic", choices=["cyclic", "contiguous"],
+                    help="cyclic: interleaved tile ownership (emrifd_batch_sum_cyclic); contiguous: work-balanced bin slices")
     args = ap.parse_args()
     import torch
     import torch.distributed as dist
@@ -67,7 +69,10 @@ def main():
         torch.cuda.synchronize(); dist.barrier(); torch.cuda.synchronize()
         e0_, e1_ = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
         e0_.record()
-        red, slices = D.gpu_bin_sharded_loglike(db, N, val, slices=slices)   # partition built in the first warm-up step, then reused
+        if args.sharding == "cyclic":
+            red = D.gpu_bin_sharded_loglike_cyclic(db, N, val)
+        else:
+            red, slices = D.gpu_bin_sharded_loglike(db, N, val, slices=slices)   # partition built in the first warm-up step, then reused
         e1_.record(); torch.cuda.synchronize()
         t = torch.tensor([e0_.elapsed_time(e1_)], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -75,14 +80,21 @@ def main():
             times.append(t.item())
     h.status()
     work = D.bin_work_histogram(db.branches_host(), it["m_arr"], N)
-    per_rank = [int(work[lo:lo + c].sum()) for lo, c in slices]
+    if args.sharding == "cyclic":
+        tile = h.lib.emrifd_tile_bins()
+        owner = (np.arange(len(work)) // tile) % world
+        per_rank = [int(work[owner == r].sum()) for r in range(world)]
+        slices = [(None, int((owner == r).sum())) for r in range(world)]
+    else:
+        per_rank = [int(work[lo:lo + c].sum()) for lo, c in slices]
     if rank == 0:
         r = red.cpu().numpy()[0]
         print(json.dumps({"config": "configs[3] high-mode stress, frequency-bin sharded", "n_gpus": world, "T_yr": args.T, "N": N,
                           "modes": int(len(it["m_arr"])), "knots": int(len(it["t"])), "evals": int(work.sum()),
                           "ms_per_likelihood": float(np.median(times)), "ms_all": times, "ll": float(r[0]), "hh": float(r[2]),
-                          "evals_per_rank": per_rank, "bins_per_rank": [c for _, c in slices],
-                          "includes": "spline build + segmentation + sliced mode sum + NCCL all_reduce (work-balanced partition built once in warm-up and reused)"}))
+                          "sharding": args.sharding, "evals_per_rank": per_rank, "bins_per_rank": [c for _, c in slices],
+                          "includes": "spline build + segmentation + sharded mode sum + NCCL all_reduce" + ("" if args.sharding == "cyclic" else
+                                      " (work-balanced partition built once in warm-up and reused)")}))
     dist.destroy_process_group()
 
 

@@ -112,3 +112,16 @@ def test_shard_helpers():
     sl = D.balanced_bin_slices(work, 8)                        # tile-aligned starts (mode-sum tiles of 1024 bins)
     assert sum(c for _, c in sl) == 100000 and all(lo % 1024 == 0 for lo, _ in sl)
     assert all(19000 <= lo <= 31000 for lo, _ in sl[1:])
+
+
+def test_cyclic_tile_ownership_covers_every_tile_once():
+    from emri_frequencydomainwaveforms_b200 import distributed as D
+    for world in (1, 2, 8):
+        ntiles = 1541
+        seen = np.zeros(ntiles, dtype=int)
+        for r in range(world):
+            first, stride = D.cyclic_tile_owner(world, r)
+            seen[first::stride] += 1
+        assert np.all(seen == 1)
+    with pytest.raises(ValueError):
+        D.cyclic_tile_owner(4, 4)

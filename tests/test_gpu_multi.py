@@ -44,12 +44,13 @@ def _worker(rank, world, port, q):
         h.check(h.lib.emrifd_set_data(h.h, dw.data_ptr(), w.data_ptr(), n))
         single = engine.run_loglike(db, N, val).cpu().numpy()
         red, slices = D.gpu_bin_sharded_loglike(db, N, val)
+        red_cyc = D.gpu_bin_sharded_loglike_cyclic(db, N, val)
         # walker sharding: each rank evaluates its block through the host-buffer call, results are gathered
         lo, hi = D.shard_range(len(items), world, rank)
         local = engine.run_loglike_host(engine.PackedBatch(items[lo:hi]), h, N, val)[:, 0]
         counts = [D.shard_range(len(items), world, r)[1] - D.shard_range(len(items), world, r)[0] for r in range(world)]
         gathered = D.gather_walker_results(torch.as_tensor(local, device=h.torch_device), counts).cpu().numpy()
-        q.put((rank, single, red.cpu().numpy(), slices, gathered))
+        q.put((rank, single, red.cpu().numpy(), slices, gathered, red_cyc.cpu().numpy()))
     finally:
         dist.destroy_process_group()
 
@@ -69,10 +70,11 @@ def test_bin_and_walker_sharding_nccl():
     for p in procs:
         p.join(timeout=60)
         assert p.exitcode == 0
-    (_, single0, red0, slices, g0), (_, single1, red1, _, g1) = res
+    (_, single0, red0, slices, g0, cyc0), (_, single1, red1, _, g1, cyc1) = res
     assert np.array_equal(single0, single1) and np.array_equal(red0, red1)
     scale = np.abs(single0[:, 2:3])
     assert np.all(np.abs(red0 - single0) <= 1e-12 * scale)                  # same sums, different partial order
+    assert np.array_equal(cyc0, cyc1) and np.all(np.abs(cyc0 - single0) <= 1e-12 * scale)   # cyclic tile ownership
     assert abs(single0[0, 0]) <= 1e-10 * scale[0, 0] and single0[1, 0] < 0
     assert slices[0][1] > 0 and slices[1][1] > 0 and slices[0][1] + slices[1][1] == (len(g0) and sum(c for _, c in slices))
     assert np.allclose(g0, single0[:, 0], rtol=1e-12, atol=1e-12 * scale.max()) and np.array_equal(g0, g1)

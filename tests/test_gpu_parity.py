@@ -369,6 +369,50 @@ def test_fd_window_convolution(torch_cuda):
     assert ch[0].shape[0] == (n + 1) // 2 and np.max(np.abs(ch[0].cpu().numpy() - ref0[freq >= 0.0])) <= 1e-12 * np.max(np.abs(ref0))
 
 
+def test_cyclic_tile_sharding_sums_to_full_likelihood(generator, torch_cuda):
+    """emrifd_batch_sum_cyclic (multi-GPU frequency-bin sharding): the partial sums over the tile sets
+    {r, r + W, ...}, r < W, add up to the full single-call likelihood; owned tiles of hp/hc equal the full waveform."""
+    torch = torch_cuda
+    from emri_frequencydomainwaveforms_b200 import _lib, engine
+    h = _lib.get_handle()
+    items = [make_item(generator, "plunge", dt=20.0), make_item(generator, "ecc_many", dt=20.0)]
+    N = max(it["N"] for it in items)
+    n = (N + 1) // 2
+    val = 1.0 / (N * 20.0)
+    db = engine.DeviceBatch(engine.PackedBatch(items), h)
+    hp, hc, _ = engine.run_waveform(db, N, val, mask_positive=True)
+    w = torch.full((2, n), 2.0e19, dtype=torch.float64, device=h.torch_device)
+    dw = (torch.stack([hp[0], hc[0]]) * w).contiguous()
+    h.check(h.lib.emrifd_set_data(h.h, dw.data_ptr(), w.data_ptr(), n))
+    full = engine.run_loglike(db, N, val).cpu().numpy()
+    tile = h.lib.emrifd_tile_bins()
+    pb = db.pb
+    flags = _lib.INCLUDE_MINUS_M | _lib.MASK_POSITIVE
+    for W in (1, 3, 8):
+        tot = np.zeros_like(full)
+        for r in range(W):
+            out = torch.zeros((pb.B, 3), dtype=torch.float64, device=h.torch_device)
+            hp2 = torch.full((pb.B, n), complex(7.0, 7.0), dtype=torch.complex128, device=h.torch_device)
+            hc2 = hp2.clone()
+            pb.walkers["out_off"] = np.arange(pb.B, dtype=np.int64) * n
+            h.check(h.lib.emrifd_batch_sum_cyclic(h.h, pb.walkers.ctypes.data, pb.B, db.t.data_ptr(), db.coeff.data_ptr(), db.m.data_ptr(),
+                                                  db.n.data_ptr(), db.ylm.data_ptr(), db.branches.data_ptr(), N, val, None, flags, r, W,
+                                                  hp2.data_ptr(), hc2.data_ptr(), out.data_ptr()))
+            tot += out.cpu().numpy()
+            owned = ((torch.arange(n, device=h.torch_device) // tile) % W) == r
+            assert torch.equal(hp2[:, owned], hp[:, owned]) and torch.equal(hc2[:, owned], hc[:, owned])
+            assert torch.all(hp2[:, ~owned] == complex(7.0, 7.0))          # tiles of other ranks are not touched
+        scale = np.abs(full[:, 2:3])
+        assert np.all(np.abs(tot - full) <= 1e-12 * scale), (W, tot, full)
+    # a rank beyond the number of tiles owns nothing
+    out = torch.ones((pb.B, 3), dtype=torch.float64, device=h.torch_device)
+    ntiles = (n + tile - 1) // tile
+    h.check(h.lib.emrifd_batch_sum_cyclic(h.h, pb.walkers.ctypes.data, pb.B, db.t.data_ptr(), db.coeff.data_ptr(), db.m.data_ptr(),
+                                          db.n.data_ptr(), db.ylm.data_ptr(), db.branches.data_ptr(), N, val, None, flags, ntiles + 2, ntiles + 5,
+                                          None, None, out.data_ptr()))
+    assert torch.all(out == 0)
+
+
 def test_td_to_fd_utilities(torch_cuda):
     """FDutils.get_fft_td_windowed / get_fd_waveform_fromTD (FDutils.py:49-64,142-178) against numpy's FFT."""
     from emri_frequencydomainwaveforms_b200.fdutils import get_fft_td_windowed, get_fd_waveform_fromTD
