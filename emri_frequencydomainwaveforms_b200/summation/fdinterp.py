@@ -9,7 +9,7 @@ import numpy as np
 
 from .. import _lib, engine
 from ..utils.constants import MTSUN_SI, YRSID_SI
-from ..utils.utility import schwarzschild_frequencies
+from ..utils.utility import fundamental_frequencies_hz
 
 
 def _np(x):
@@ -48,19 +48,50 @@ class FDInterpolatedModeSum:
         return d
 
     # -- few.utils.baseclasses.SummationBase.__call__ (output sizing) ------------
-    def __call__(self, t, *args, T=1.0, dt=10.0, **kwargs):
-        t_host = _np(t)
+    def _size_output(self, t_first, t_last, T, dt):
         n_pts = int(T * YRSID_SI / dt)
         T_s = n_pts * dt
-        if T_s < t_host[-1].item():
-            num_pts = int((T_s - t_host[0]) / dt) + 1
+        if T_s < t_last:
+            num_pts = int((T_s - t_first) / dt) + 1
             num_pts_pad = 0
         else:
-            num_pts = int((t_host[-1] - t_host[0]) / dt) + 1
-            num_pts_pad = int((T_s - t_host[0]) / dt) + 1 - num_pts if self.pad_output else 0
+            num_pts = int((t_last - t_first) / dt) + 1
+            num_pts_pad = int((T_s - t_first) / dt) + 1 - num_pts if self.pad_output else 0
         if self.odd_len and (num_pts + num_pts_pad) % 2 == 0:
             num_pts_pad += 1
         self.num_pts, self.num_pts_pad, self.dt = num_pts, num_pts_pad, dt
+
+    def _grid(self, f_arr, dt):
+        """A1: (N, val, fpos_dev) and ``self.frequency`` for an explicit two-sided f_arr or the implicit fftfreq grid."""
+        import torch
+        h = self.handle
+        if f_arr is not None:
+            f_host = _np(f_arr)
+            N, fpos = engine.grid_from_frequency(f_host)
+            self.frequency = torch.as_tensor(f_host, dtype=torch.float64).to(h.torch_device)
+            return N, 0.0, self.frequency[(N - 1) // 2:].contiguous()
+        N = self.num_pts + self.num_pts_pad
+        if N % 2 == 0 or N < 3:
+            raise ValueError("The frequency grid must have odd length: use sum_kwargs=dict(odd_len=True).")
+        val = 1.0 / (N * dt)
+        k = torch.arange(-(N - 1) // 2, (N - 1) // 2 + 1, dtype=torch.float64, device=h.torch_device)
+        self.frequency = k * val   # == fftshift(fftfreq(N, dt)) bit for bit (numpy multiplies k by 1/(N dt))
+        return N, val, None
+
+    def sum_device_batch(self, db, t_first, t_last, T=1.0, dt=10.0, include_minus_m=True, f_arr=None, mask_positive=False):
+        """Same as ``__call__`` for a batch whose packed inputs already live on the device
+        (``FastSchwarzschildEccentricFlux.prepare_batch_device``).  Returns ``[B, 2, n_out]`` (row w = vstack((h+, hx)))."""
+        self._size_output(float(t_first), float(t_last), T, dt)
+        N, val, fpos_dev = self._grid(f_arr, dt)
+        engine.run_waveform(db, N, val, fpos_dev, include_minus_m=include_minus_m, mask_positive=mask_positive)
+        self.handle.status()
+        self.last_batch = db
+        self.waveform = db.last_out[0]
+        return db.last_out
+
+    def __call__(self, t, *args, T=1.0, dt=10.0, **kwargs):
+        t_host = _np(t)
+        self._size_output(t_host[0].item(), t_host[-1].item(), T, dt)
         self.sum(t, *args, dt=dt, **kwargs)
         return self.waveform
 
@@ -74,28 +105,12 @@ class FDInterpolatedModeSum:
         h = self.handle
         t_h, p_h, e_h = _np(t).astype(np.float64), _np(p).astype(np.float64), _np(e).astype(np.float64)
         # A2: Schwarzschild fundamental frequencies at the sparse points (host, L values)
-        om_phi, om_r = schwarzschild_frequencies(p_h, e_h)
-        f_phi = om_phi / (2.0 * np.pi * M * MTSUN_SI)
-        f_r = om_r / (2.0 * np.pi * M * MTSUN_SI)
+        f_phi, f_r = fundamental_frequencies_hz(p_h, e_h, M)
         item = dict(t=t_h, teuk_modes=_np(teuk_modes), ylms=_np(ylms), Phi_phi=_np(Phi_phi), Phi_r=_np(Phi_r),
                     m_arr=_np(m_arr), n_arr=_np(n_arr), f_phi=f_phi, f_r=f_r, scale=scale, cos2psi=cos2psi,
                     sin2psi=sin2psi)
         pb = engine.PackedBatch([item])
-        # A1: frequency grid
-        if f_arr is not None:
-            f_host = _np(f_arr)
-            N, fpos = engine.grid_from_frequency(f_host)
-            self.frequency = torch.as_tensor(f_host, dtype=torch.float64).to(h.torch_device)
-            fpos_dev = self.frequency[(N - 1) // 2:].contiguous()
-            val = 0.0
-        else:
-            N = self.num_pts + self.num_pts_pad
-            if N % 2 == 0 or N < 3:
-                raise ValueError("The frequency grid must have odd length: use sum_kwargs=dict(odd_len=True).")
-            val = 1.0 / (N * dt)
-            k = torch.arange(-(N - 1) // 2, (N - 1) // 2 + 1, dtype=torch.float64, device=h.torch_device)
-            self.frequency = k * val   # == fftshift(fftfreq(N, dt)) bit for bit (numpy multiplies k by 1/(N dt))
-            fpos_dev = None
+        N, val, fpos_dev = self._grid(f_arr, dt)   # A1: frequency grid
         db = engine.DeviceBatch(pb, h)
         hp, hc, _ = engine.run_waveform(db, N, val, fpos_dev, include_minus_m=include_minus_m,
                                         mask_positive=mask_positive)

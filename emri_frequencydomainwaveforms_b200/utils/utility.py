@@ -18,6 +18,16 @@ def _ellip_pi(n, m):
     return elliprf(0.0, 1.0 - m, 1.0) + n / 3.0 * elliprj(0.0, 1.0 - m, 1.0, 1.0 - n)
 
 
+def fundamental_frequencies_hz(p, e, M, native=True):
+    """f_phi, f_r [Hz] at the sparse trajectory points: Omega / (2 pi M MTSUN_SI), evaluated as Omega / ((2 pi) * (M MTSUN_SI)) --
+    the association csrc/emrihost.c uses, so every producer path hands the kernels bit-identical tracks.  (It matters: the
+    waveform is ill-conditioned in the knot frequencies near turnovers of f_mn(t) -- a 1-ulp change moves individual bins
+    by ~3e-9 of max|h| -- so parity is only meaningful on identical inputs.)"""
+    om_phi, om_r = schwarzschild_frequencies(p, e, native=native)
+    Msec = M * MTSUN_SI
+    return om_phi / (2.0 * np.pi * Msec), om_r / (2.0 * np.pi * Msec)
+
+
 def schwarzschild_frequencies(p, e, native=True):
     """Omega_phi, Omega_r (dimensionless, units of 1/M) for a bound Schwarzschild geodesic.
 

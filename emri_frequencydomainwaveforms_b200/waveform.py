@@ -19,7 +19,7 @@ from .summation.fdinterp import FDInterpolatedModeSum
 from .trajectory.inspiral import EMRIInspiral
 from .utils.constants import MRSUN_SI, MTSUN_SI, Gpc, YRSID_SI
 from .utils.modeselector import ModeSelector
-from .utils.utility import schwarzschild_frequencies
+from .utils.utility import fundamental_frequencies_hz
 from .utils.ylm import GetYlms
 
 
@@ -47,6 +47,12 @@ class FastSchwarzschildEccentricFlux:
         self.ylm_gen = GetYlms(assume_positive_m=True)
         self.mode_selector = ModeSelector(self.m0mask)
         self.create_waveform = FDInterpolatedModeSum(**sk)
+        producers = kwargs.pop("producers", "auto")
+        if producers == "auto":
+            from . import _hostlib
+            producers = ("device" if hasattr(amp, "device_call") and getattr(self.inspiral_generator, "use_native", False)
+                         and _hostlib.load() is not None else "host")
+        self.producers = producers   # "device": batched CUDA producers for Ylm / mode selection; "host": NumPy
         self.inspiral_kwargs = dict(inspiral_kwargs)
         for k in ("DENSE_STEPPING", "max_init_len", "use_rk4"):
             self.inspiral_kwargs.pop(k, None)
@@ -111,13 +117,13 @@ class FastSchwarzschildEccentricFlux:
             neg = np.where(self.m0mask[keep], self.num_teuk_modes + pos[keep], keep)
             tm, yk = teuk[:, keep], np.concatenate([ylms[keep], ylms[neg]])
             ls, ms, ns = self.l_arr[keep], self.m_arr[keep], self.n_arr[keep]
-        om_phi, om_r = schwarzschild_frequencies(p, e)
+        f_phi, f_r = fundamental_frequencies_hz(p, e, M)
         scale = 1.0 if dist is None else (mu * MRSUN_SI) / (dist * Gpc)
         self.ls, self.ms, self.ns = ls, ms, ns
         self.num_modes_kept = len(ls)
         return dict(t=t, p=p, e=e, teuk_modes=np.ascontiguousarray(tm), ylms=yk, Phi_phi=Phi_phi, Phi_r=Phi_r,
                     m_arr=ms.astype(np.int32), n_arr=ns.astype(np.int32), l_arr=ls.astype(np.int32),
-                    f_phi=om_phi / (2 * np.pi * M * MTSUN_SI), f_r=om_r / (2 * np.pi * M * MTSUN_SI),
+                    f_phi=f_phi, f_r=f_r,
                     scale=scale, M=M, mu=mu)
 
     # ---- batched producers with Ylm, mode selection and compaction on the device ----
@@ -209,6 +215,8 @@ class FastSchwarzschildEccentricFlux:
         db = engine.DeviceBatch.from_device_parts(h, w, tracks, teuk, m_out, n_out, ylm)
         db.keep_idx, db.h2d_bytes = keep_idx, int(tr.nbytes + samp_walker.numel() * 4 + 2 * 8 * B + w.nbytes)
         db.p_e_host = (tr[1], tr[2])
+        ends = np.cumsum(lens) - 1
+        db.t_first, db.t_last = tr[0][ends - lens + 1], tr[0][ends]      # per walker: output sizing (few SummationBase)
         if keep_full:   # tests compare the selection against the numpy restatement on the very same inputs
             db.teuk_full, db.ylm_full, db.flags = teuk_full, ylm_full, flags
         return db, ok
@@ -217,6 +225,17 @@ class FastSchwarzschildEccentricFlux:
                  eps=1e-5, show_progress=False, batch_size=-1, mode_selection=None, include_minus_m=True,
                  f_arr=None, mask_positive=False, cos2psi=1.0, sin2psi=0.0, **kwargs):
         theta, phi = self.sanity_check_viewing_angles(theta, phi)
+        if mode_selection is None and self.producers == "device":
+            # Ylm / mode selection / compaction on the device (the NumPy producers cost ~30 ms per waveform)
+            db, ok = self.prepare_batch_device(M, mu, p0, e0, theta, phi, dist=dist, Phi_phi0=Phi_phi0, Phi_r0=Phi_r0, T=T, dt=dt,
+                                               eps=eps, cos2psi=cos2psi, sin2psi=sin2psi, handle=self.create_waveform.handle)
+            if db is not None:
+                out = self.create_waveform.sum_device_batch(db, db.t_first[0], db.t_last[0], T=T, dt=dt, include_minus_m=include_minus_m,
+                                                            f_arr=f_arr, mask_positive=mask_positive)
+                self.num_modes_kept = int(db.pb.walkers["K"][0])
+                self._last_device_batch = db
+                return out[0]
+            # invalid parameters: fall through so that the host producers raise FEW's ValueError
         it = self.prepare(M, mu, p0, e0, theta, phi, dist=dist, Phi_phi0=Phi_phi0, Phi_r0=Phi_r0, T=T, dt=dt,
                           eps=eps, mode_selection=mode_selection)
         return self.create_waveform(

@@ -439,8 +439,7 @@ def test_long_trajectory_paths(generator, oracle_quad, torch_cuda):
     """L = 700 knots: the spline kernel's non-tiled variant (forward-sweep intermediates parked in the output), fewer
     modes per CTA in the segmentation kernel and a 118 KB track staging area in the mode-sum kernel."""
     from scipy.interpolate import CubicSpline
-    from emri_frequencydomainwaveforms_b200.utils.utility import schwarzschild_frequencies
-    from emri_frequencydomainwaveforms_b200.utils.constants import MTSUN_SI
+    from emri_frequencydomainwaveforms_b200.utils.utility import fundamental_frequencies_hz
     it = make_item(generator, "plunge", dt=40.0)
     t0 = it["t"]
     # refine the knot vector (geometric mix keeps the clustering near the end), re-evaluate everything on it
@@ -450,9 +449,9 @@ def test_long_trajectory_paths(generator, oracle_quad, torch_cuda):
     K = len(it["m_arr"])
     amp = generator.amplitude_generator
     idx = [int(np.where((amp.l_arr == l) & (amp.m_arr == m) & (amp.n_arr == n))[0][0]) for l, m, n in zip(it["l_arr"], it["m_arr"], it["n_arr"])]
-    om_phi, om_r = schwarzschild_frequencies(p, e)
+    f_phi, f_r = fundamental_frequencies_hz(p, e, it["M"])
     long_it = dict(it, t=t, p=p, e=e, teuk_modes=np.ascontiguousarray(amp(p, e)[:, idx]), Phi_phi=CubicSpline(t0, it["Phi_phi"])(t),
-                   Phi_r=CubicSpline(t0, it["Phi_r"])(t), f_phi=om_phi / (2 * np.pi * it["M"] * MTSUN_SI), f_r=om_r / (2 * np.pi * it["M"] * MTSUN_SI))
+                   Phi_r=CubicSpline(t0, it["Phi_r"])(t), f_phi=f_phi, f_r=f_r)
     assert long_it["teuk_modes"].shape == (700, K)
     hp_o, hc_o, coeff_o, br_o, nbr_o = oracle_waveform(oracle_quad, long_it)
     s, out = _gpu_sum(long_it, torch_cuda)
