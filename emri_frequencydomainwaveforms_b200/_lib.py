@@ -34,7 +34,8 @@ SYMBOLS = [
     "emrifd_fd_waveform_batch", "emrifd_batch_status", "emrifd_set_data", "emrifd_inner_product",
     "emrifd_loglike", "emrifd_loglike_batch_host", "emrifd_bench_fp64_fma", "emrifd_launch_count",
     "emrifd_sum_kernel_time", "emrifd_mode_select", "emrifd_ylm_batch", "emrifd_mode_compact_count",
-    "emrifd_mode_compact_gather", "emrifd_tile_bins", "emrifd_batch_sum_cyclic"]
+    "emrifd_mode_compact_gather", "emrifd_tile_bins", "emrifd_batch_sum_cyclic",
+    "emrifd_synth_amplitude"]
 
 _lib = None
 
@@ -75,6 +76,7 @@ def load():
     lib.emrifd_loglike_batch_host.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, vp, i32, vp, vp, vp]
     lib.emrifd_mode_select.argtypes = [vp, vp, i64, i64, vp, vp, vp, i64, i64, dbl, vp]
     lib.emrifd_ylm_batch.argtypes = [vp, vp, vp, i64, vp, i64, vp, vp, i64, i32, vp]
+    lib.emrifd_synth_amplitude.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.emrifd_mode_compact_count.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.emrifd_mode_compact_gather.argtypes = [vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
     lib.emrifd_bench_fp64_fma.argtypes = [vp, i32, C.POINTER(dbl)]

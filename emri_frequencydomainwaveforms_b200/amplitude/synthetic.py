@@ -61,30 +61,28 @@ class SyntheticAmplitude:
         out = P[:, lidx] * ENV[:, midx, nidx] * (EPH[:, nidx] * cmode[None, :])
         return self._finish(out, specific_modes)
 
-    def device_call(self, p, e, device):
-        """Same amplitudes evaluated on the GPU (torch complex128 [L, num_modes]); values agree with the host version
-        to rounding (different exp/sin implementations)."""
+    def device_call(self, p, e, device, handle=None):
+        """Same amplitudes evaluated on the GPU by ``emrifd_synth_amplitude`` (torch complex128 [L, num_modes]); values agree
+        with the host version to rounding (different pow/exp/sincos implementations).  ``p``, ``e``: numpy or torch."""
         import torch
+        from .. import _lib
+        h = handle or _lib.get_handle(device.index if hasattr(device, "index") and device.index is not None else None)
+        dev = h.torch_device
         cmode, lidx, midx, nidx = self._tables()
-        if getattr(self, "_dev_tables", None) is None or self._dev_tables[0].device != device:
-            self._dev_tables = (torch.as_tensor(cmode).to(device), torch.as_tensor(lidx).to(device),
-                                torch.as_tensor(midx).to(device), torch.as_tensor(nidx).to(device))
-        cm, li, mi, ni = self._dev_tables
+        if getattr(self, "_dev_tables", None) is None or self._dev_tables[0].device != dev:
+            up = lambda a: torch.as_tensor(np.ascontiguousarray(a, dtype=np.int32)).to(dev)
+            self._dev_tables = (torch.as_tensor(np.ascontiguousarray(cmode)).to(dev), up(self.l_arr), up(self.m_arr), up(self.n_arr))
+        cm, la, ma, na = self._dev_tables
         if not torch.is_tensor(p):
             p = torch.as_tensor(np.asarray(p, dtype=np.float64))
         if not torch.is_tensor(e):
             e = torch.as_tensor(np.asarray(e, dtype=np.float64))
-        p, e = p.to(device=device, dtype=torch.float64), e.to(device=device, dtype=torch.float64)
-        lv = torch.arange(2, self.lmax + 1, dtype=torch.float64, device=device)
-        mv = torch.arange(0, self.lmax + 1, dtype=torch.float64, device=device)
-        nv = torch.arange(-self.nmax, self.nmax + 1, dtype=torch.float64, device=device)
-        P = p[:, None] ** (-lv[None, :] / 2.0)
-        n0 = (2.5 * e / torch.sqrt(1.0 - e))[:, None] * (1.0 + 0.2 * mv)[None, :]
-        sig = 0.35 + 3.5 * e
-        ENV = torch.exp(-((nv[None, None, :] - n0[:, :, None]) ** 2) / (2.0 * sig * sig)[:, None, None])
-        ang = (e / 6.0)[:, None] * nv[None, :] + (8.0 / p)[:, None]
-        EPH = torch.complex(torch.cos(ang), torch.sin(ang))
-        return P[:, li] * ENV[:, mi, ni] * (EPH[:, ni] * cm[None, :])
+        p = p.to(device=dev, dtype=torch.float64).contiguous()
+        e = e.to(device=dev, dtype=torch.float64).contiguous()
+        out = torch.empty((p.shape[0], self.num_teuk_modes), dtype=torch.complex128, device=dev)
+        h.check(h.lib.emrifd_synth_amplitude(h.h, p.data_ptr(), e.data_ptr(), p.shape[0], la.data_ptr(), ma.data_ptr(), na.data_ptr(),
+                                             cm.data_ptr(), self.num_teuk_modes, int(self.lmax), int(self.nmax), out.data_ptr()))
+        return out
 
     def _finish(self, out, specific_modes):
         if specific_modes is not None:

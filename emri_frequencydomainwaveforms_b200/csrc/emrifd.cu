@@ -1494,6 +1494,45 @@ __global__ void __launch_bounds__(256) compact_gather_kernel(const emrifd_walker
     }
 }
 
+// Stand-in amplitude producer on the device (amplitude/synthetic.py::SyntheticAmplitude, the offline substitute for few's
+// RomanAmplitude whose weights are a Zenodo download): A_lmn(p, e) = c_lmn p^{-l/2} exp(-(n - n0)^2 / (2 sigma^2))
+// exp(i (e n / 6 + 8 / p)), n0 = 2.5 e (1 + 0.2 m) / sqrt(1 - e), sigma = 0.35 + 3.5 e.  One CTA per trajectory point:
+// the separable factors go through small shared-memory tables ([l], [m][n], [n]); every mode is then three look-ups.
+#define AMP_LMAX 12
+#define AMP_NMAX 32
+__global__ void __launch_bounds__(256) synth_amplitude_kernel(const double *__restrict__ p_arr, const double *__restrict__ e_arr,
+                                                              const int *__restrict__ l_arr, const int *__restrict__ m_arr,
+                                                              const int *__restrict__ n_arr, const double2 *__restrict__ cmode,
+                                                              int M, int lmax, int nmax, double2 *__restrict__ out) {
+    __shared__ double sP[AMP_LMAX + 1];
+    __shared__ double sEnv[(AMP_LMAX + 1) * (2 * AMP_NMAX + 1)];
+    __shared__ double2 sPh[2 * AMP_NMAX + 1];
+    const long long row = blockIdx.x;
+    const double p = p_arr[row], e = e_arr[row];
+    const int nn = 2 * nmax + 1;
+    for (int l = 2 + threadIdx.x; l <= lmax; l += blockDim.x) sP[l] = pow(p, -0.5 * (double)l);
+    const double sig = 0.35 + 3.5 * e, n0b = 2.5 * e / sqrt(1.0 - e), inv2s2 = 1.0 / (2.0 * sig * sig);
+    for (int q = threadIdx.x; q < (lmax + 1) * nn; q += blockDim.x) {
+        const int m = q / nn, n = q % nn - nmax;
+        const double d = (double)n - n0b * (1.0 + 0.2 * (double)m);
+        sEnv[q] = exp(-(d * d) * inv2s2);
+    }
+    for (int q = threadIdx.x; q < nn; q += blockDim.x) {
+        double sn, cs;
+        sincos((e / 6.0) * (double)(q - nmax) + 8.0 / p, &sn, &cs);
+        sPh[q] = make_double2(cs, sn);
+    }
+    __syncthreads();
+    double2 *o = out + row * (long long)M;
+    for (int i = threadIdx.x; i < M; i += blockDim.x) {
+        const int l = l_arr[i], m = m_arr[i], n = n_arr[i] + nmax;
+        const double a = sP[l] * sEnv[m * nn + n];
+        const double2 ph = sPh[n], c = cmode[i];
+        const double pr = ph.x * c.x - ph.y * c.y, pi = ph.x * c.y + ph.y * c.x; // (EPH * cmode), then times the real envelope
+        o[i] = make_double2(a * pr, a * pi);
+    }
+}
+
 // FP64 FMA peak micro-benchmark: 8 independent chains per thread
 __global__ void __launch_bounds__(256) fma_bench_kernel(double *out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
@@ -2016,6 +2055,20 @@ int emrifd_ylm_batch(emrifd_handle_t *h, const int32_t *l_arr, const int32_t *m_
     if (lmax < 2 || lmax > YLM_LMAX) return set_err(h, EMRIFD_ERR_INVALID, "ylm_batch: lmax must be in [2, 12]");
     cudaSetDevice(h->device);
     ylm_kernel<<<(unsigned)B, 256, 0, h->stream>>>(l_arr, m_arr, (int)M, neg_src, (int)Mneg, theta, phi, (double2 *)ylm_out);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int emrifd_synth_amplitude(emrifd_handle_t *h, const double *p, const double *e, int64_t nsamp, const int32_t *l_arr,
+                           const int32_t *m_arr, const int32_t *n_arr, const double *cmode, int64_t M, int lmax, int nmax,
+                           double *teuk_out) {
+    if (!h || !p || !e || !l_arr || !m_arr || !n_arr || !cmode || !teuk_out || nsamp <= 0 || M <= 0)
+        return set_err(h, EMRIFD_ERR_INVALID, "synth_amplitude: bad argument");
+    if (lmax < 2 || lmax > AMP_LMAX || nmax < 0 || nmax > AMP_NMAX) return set_err(h, EMRIFD_ERR_INVALID, "synth_amplitude: lmax <= 12, nmax <= 32");
+    cudaSetDevice(h->device);
+    synth_amplitude_kernel<<<(unsigned)nsamp, 256, 0, h->stream>>>(p, e, l_arr, m_arr, n_arr, (const double2 *)cmode, (int)M, lmax, nmax,
+                                                                    (double2 *)teuk_out);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;

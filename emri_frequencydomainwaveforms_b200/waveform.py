@@ -186,7 +186,7 @@ class FastSchwarzschildEccentricFlux:
         samp_walker = torch.from_numpy(np.repeat(np.arange(B, dtype=np.int32), lens)).to(dev)
         basis = self._device_basis(h)
         Mb, Mneg = self.num_teuk_modes, int(self.m0mask.sum())
-        teuk_full = amp.device_call(tr_dev[1], tr_dev[2], dev).contiguous()          # [sum L, Mb] complex128
+        teuk_full = amp.device_call(tr_dev[1], tr_dev[2], dev, handle=h)             # [sum L, Mb] complex128
         ylm_full = ylm_batch_device(basis["l"], basis["m"], basis["neg_src"], theta[sel], phi[sel], h, lmax=int(self.l_arr.max()))
         flags = torch.empty((B, Mb), dtype=torch.uint8, device=dev)
         h.check(h.lib.emrifd_mode_select(h.h, teuk_full.data_ptr(), nk, Mb, samp_walker.data_ptr(), ylm_full.data_ptr(),

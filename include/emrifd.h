@@ -192,6 +192,13 @@ int emrifd_mode_compact_gather(emrifd_handle_t *h, const emrifd_walker_t *walker
                                const int32_t *neg_pos, const double *ylm_full, double *teuk_out, int32_t *m_out, int32_t *n_out,
                                double *ylm_out);
 
+/* Stand-in amplitude producer on the device (offline substitute for few.amplitude.romannet.RomanAmplitude, whose weights are
+ * a Zenodo download; formula in amplitude/synthetic.py): p, e [nsamp] trajectory points, mode basis l/m/n [M], cmode [M]
+ * complex per-mode constants; teuk_out [nsamp][M] complex -- the layout emrifd_mode_select / emrifd_mode_compact_gather read. */
+int emrifd_synth_amplitude(emrifd_handle_t *h, const double *p, const double *e, int64_t nsamp, const int32_t *l_arr,
+                           const int32_t *m_arr, const int32_t *n_arr, const double *cmode, int64_t M, int lmax, int nmax,
+                           double *teuk_out);
+
 /* ---- measurement helpers (bench.py roofline denominators) ----------------------------------- */
 /* FP64 FMA throughput micro-benchmark: returns achieved GFLOP/s in *gflops. sync. */
 int emrifd_bench_fp64_fma(emrifd_handle_t *h, int iters, double *gflops);

@@ -41,6 +41,22 @@ def test_ylm_device_matches_wigner_sum(generator, torch_cuda):
     assert np.all(out[0][m_all != 2] == 0) and np.all(np.abs(out[0][m_all == 2]) > 0)
 
 
+def test_device_amplitude_matches_host_standin(generator, torch_cuda):
+    """emrifd_synth_amplitude (device stand-in for the ROMAN amplitudes) against the NumPy version of the same formula:
+    floating point, 1e-13 of each mode's own magnitude (pow / exp / sincos implementations differ by rounding)."""
+    amp = generator.amplitude_generator
+    rng = np.random.default_rng(3)
+    p = rng.uniform(7.3, 17.0, 57)
+    e = rng.uniform(0.0, 0.74, 57)
+    e[:3] = [0.0, 0.74, 0.35]
+    host = amp(p, e)
+    dev = amp.device_call(p, e, torch_cuda.device("cuda", torch_cuda.cuda.current_device())).cpu().numpy()
+    assert dev.shape == host.shape == (57, amp.num_teuk_modes)
+    big = np.abs(host) > 1e-290
+    assert np.max(np.abs(dev - host)[big] / np.abs(host)[big]) <= 1e-12
+    assert np.max(np.abs(dev - host)[~big], initial=0.0) <= 1e-290
+
+
 @pytest.mark.parametrize("eps", [1e-2, 1e-5, 0.3])
 def test_mode_select_device_bit_exact(generator, torch_cuda, eps):
     from emri_frequencydomainwaveforms_b200 import _lib
