@@ -413,6 +413,83 @@ def test_cyclic_tile_sharding_sums_to_full_likelihood(generator, torch_cuda):
     assert torch.all(out == 0)
 
 
+def test_queue_and_direct_launch_modes_agree_bit_for_bit(generator, torch_cuda):
+    """The mode sum launches a direct (tile, walker) grid for small launches and persistent CTAs fed by a tile queue for
+    large ones (> 4 waves).  Results must not depend on which: a 24-walker batch (queue) equals its single-walker calls
+    (direct) bit for bit -- waveforms and likelihood sums -- and is reproducible run to run (queue order is not)."""
+    torch = torch_cuda
+    from emri_frequencydomainwaveforms_b200 import _lib, engine
+    h = _lib.get_handle()
+    base_items = [make_item(generator, "plunge", dt=20.0), make_item(generator, "ecc_many", dt=20.0), make_item(generator, "cfg1_like", dt=20.0)]
+    items = [dict(base_items[i % 3], Phi_phi=base_items[i % 3]["Phi_phi"] + 0.1 * i) for i in range(24)]
+    N = max(it["N"] for it in items)
+    n = (N + 1) // 2
+    val = 1.0 / (N * 20.0)
+    tile = h.lib.emrifd_tile_bins()
+    assert 24 * ((n + tile - 1) // tile) > 4 * 2 * torch.cuda.get_device_properties(0).multi_processor_count   # -> queue path
+    db0 = engine.DeviceBatch(engine.PackedBatch([items[0]]), h)
+    hp0, hc0, _ = engine.run_waveform(db0, N, val, mask_positive=True)
+    w = torch.full((2, n), 2.0e19, dtype=torch.float64, device=h.torch_device)
+    dw = (torch.stack([hp0[0], hc0[0]]) * w).contiguous()
+    h.check(h.lib.emrifd_set_data(h.h, dw.data_ptr(), w.data_ptr(), n))
+    dbB = engine.DeviceBatch(engine.PackedBatch(items), h)
+    hpB, hcB, likeB = engine.run_waveform(dbB, N, val, mask_positive=True, like=True)
+    hpB, hcB, likeB = hpB.clone(), hcB.clone(), likeB.clone()
+    hpB2, hcB2, likeB2 = engine.run_waveform(dbB, N, val, mask_positive=True, like=True)
+    assert torch.equal(hpB, hpB2) and torch.equal(hcB, hcB2) and torch.equal(likeB, likeB2)          # run-to-run
+    only = engine.run_loglike(dbB, N, val)                                                             # no h written
+    assert torch.equal(only, likeB)
+    for i in (0, 1, 2, 13, 23):
+        db1 = engine.DeviceBatch(engine.PackedBatch([items[i]]), h)
+        hp1, hc1, like1 = engine.run_waveform(db1, N, val, mask_positive=True, like=True)
+        assert torch.equal(hp1[0], hpB[i]) and torch.equal(hc1[0], hcB[i]) and torch.equal(like1[0], likeB[i]), i
+    h.status()
+
+
+def test_minimal_shapes_and_empty_support(generator, oracle_quad, torch_cuda):
+    """Edge cases: one mode and four knots (the not-a-knot minimum); a grid whose band misses the signal entirely
+    (h = 0 everywhere, ll = -2 sum|d~|^2 from the per-tile table); a non-uniform explicit f_arr."""
+    torch = torch_cuda
+    from emri_frequencydomainwaveforms_b200 import _lib, engine
+    h = _lib.get_handle()
+    it = make_item(generator, "cfg1_like")
+    K = len(it["m_arr"])
+    k = int(np.argmax(np.abs(it["teuk_modes"][0] * it["ylms"][:K])))
+    knots = np.array([0, len(it["t"]) // 3, 2 * len(it["t"]) // 3, len(it["t"]) - 1])
+    one = dict(it, t=it["t"][knots], p=it["p"][knots], e=it["e"][knots], Phi_phi=it["Phi_phi"][knots], Phi_r=it["Phi_r"][knots],
+               f_phi=it["f_phi"][knots], f_r=it["f_r"][knots], teuk_modes=np.ascontiguousarray(it["teuk_modes"][knots][:, [k]]),
+               m_arr=it["m_arr"][[k]], n_arr=it["n_arr"][[k]], ylms=it["ylms"][[k, K + k]])
+    hp_o, hc_o, coeff_o, br_o, _ = oracle_waveform(oracle_quad, one)
+    s, out = _gpu_sum(one, torch)
+    assert np.array_equal(s.last_batch.coeff_host(0), coeff_o)
+    assert rel_err(out[0], hp_o) <= TOL_BIN and rel_err(out[1], hc_o) <= TOL_BIN and np.array_equal(out[0] != 0, hp_o != 0)
+    # a band below the signal: f_max of the grid is under the lowest harmonic frequency of the kept modes
+    live = (it["m_arr"] != 0) | (it["n_arr"] != 0)                      # (l, 0, 0) modes have f_mn = 0 and no stationary point
+    f_lo = np.min(np.abs(np.outer(it["f_phi"], it["m_arr"][live]) + np.outer(it["f_r"], it["n_arr"][live])))
+    assert f_lo > 0
+    n = 5001
+    fpos = np.linspace(0.0, 0.5 * f_lo, n)
+    newf = np.hstack((-fpos[::-1][:-1], fpos))
+    s2, out2 = _gpu_sum(it, torch, f_arr=newf)
+    assert out2.shape == (2, 2 * n - 1) and not out2.any()
+    rng = np.random.default_rng(1)
+    d = rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n))
+    w = np.full((2, n), 3.0)
+    d_dev, w_dev = torch.from_numpy((d * w).view(np.float64)).cuda(), torch.from_numpy(w).cuda()
+    h.check(h.lib.emrifd_set_data(h.h, d_dev.data_ptr(), w_dev.data_ptr(), n))
+    fpos_dev = torch.from_numpy(fpos).cuda()
+    like = engine.run_loglike(engine.DeviceBatch(engine.PackedBatch([it]), h), 2 * n - 1, 0.0, fpos_dev).cpu().numpy()
+    ref = -2.0 * np.sum(np.abs(d * w) ** 2)
+    assert abs(like[0, 0] - ref) <= 1e-12 * abs(ref) and like[0, 1] == 0 and like[0, 2] == 0
+    # non-uniform (geometric) positive grid, as a user-supplied f_arr may be
+    hi = 1.02 * np.max(np.abs(np.outer(it["f_phi"], it["m_arr"]) + np.outer(it["f_r"], it["n_arr"])))
+    fpos3 = np.concatenate([[0.0], np.geomspace(0.2 * f_lo, hi, 4000)])
+    newf3 = np.hstack((-fpos3[::-1][:-1], fpos3))
+    s3, out3 = _gpu_sum(it, torch, f_arr=newf3)
+    hp3, hc3, *_ = oracle_waveform(oracle_quad, it, N=len(newf3), fpos=fpos3)
+    assert rel_err(out3[0], hp3) <= TOL_BIN and rel_err(out3[1], hc3) <= TOL_BIN and np.array_equal(out3[0] != 0, hp3 != 0)
+
+
 def test_td_to_fd_utilities(torch_cuda):
     """FDutils.get_fft_td_windowed / get_fd_waveform_fromTD (FDutils.py:49-64,142-178) against numpy's FFT."""
     from emri_frequencydomainwaveforms_b200.fdutils import get_fft_td_windowed, get_fd_waveform_fromTD
