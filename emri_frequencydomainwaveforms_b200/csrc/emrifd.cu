@@ -535,16 +535,48 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
     double y;
     asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(a));
     const double ha = 0.5 * a;
+#if OPT_HALLEY
+    const double e = fma(-ha * y, y, 0.5);           // e = (1 - a y^2)/2;  1/sqrt(a) = y (1 + e + 1.5 e^2 + O(e^3))
+    return fma(y * e, fma(1.5, e, 1.0), y);
+#else
     double e = fma(-ha * y, y, 0.5);
     y = fma(y, e, y);
     e = fma(-ha * y, y, 0.5);
     return fma(y, e, y);
+#endif
+}
+#ifndef OPT_RINT
+#define OPT_RINT 0   /* round-to-nearest-integer by adding 1.5 * 2^52 (two DADDs) instead of FRND / F2I (conversion pipe, quarter rate) */
+#endif
+#ifndef OPT_SIGN
+#define OPT_SIGN 1   /* multiplications by +-1 as a sign-bit XOR (integer pipe) */
+#endif
+#ifndef OPT_HALLEY
+#define OPT_HALLEY 1 /* rsqrt: one cubic (Halley) step instead of two Newton steps */
+#endif
+#define RINT_MAGIC 6755399441055744.0 /* 1.5 * 2^52: (x + M) - M = rint(x) for |x| < 2^51, and the low word of x + M is (int)rint(x) */
+__device__ __forceinline__ double rint_fast(double x) {
+#if OPT_RINT
+    return __dadd_rn(__dadd_rn(x, RINT_MAGIC), -RINT_MAGIC);
+#else
+    return rint(x);
+#endif
+}
+// x * s for s = +-1 given as its sign mask (0 or 0x80000000 for the high word)
+__device__ __forceinline__ double flip_sign(double x, unsigned int mask_hi) {
+    return __hiloint2double(__double2hiint(x) ^ (int)mask_hi, __double2loint(x));
 }
 // sin and cos of 2*pi*c for |c| <~ 2^20: quarter-turn reduction (exact) + degree-15/16 polynomials in r = c - q/4
 __device__ __forceinline__ void sincos_cycles(double c, double &sn, double &cs) {
+#if OPT_RINT
+    const double tq = fma(4.0, c, RINT_MAGIC);
+    const int qi = __double2loint(tq);
+    const double q = __dadd_rn(tq, -RINT_MAGIC);
+#else
     const double q = rint(4.0 * c);
-    const double r = fma(-0.25, q, c);
     const int qi = (int)q;
+#endif
+    const double r = fma(-0.25, q, c);
     const double r2 = r * r;
     double ps = c_sin[7], pc = c_cos[8];
 #pragma unroll
@@ -695,7 +727,7 @@ __device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f
         const double pr = xi * fma(xi, fma(xi, q15, q14), q13);
         double p0 = fi * tj;
         const double e0 = fma(fi, tj, -p0);
-        p0 -= rint(p0);
+        p0 -= rint_fast(p0);
         // |p0 - mu_hi| <~ 20 and |poly| <~ 1e4 cycles: summing them costs <= 1e-12 cycles of rounding, and the
         // quarter-turn reduction inside sincos_cycles is exact for |c| < 2^20
         const double poly = fma(fi, xi, -EMRIFD_INV2PI_HI * fma(dm, pp, dn * pr));
@@ -705,12 +737,19 @@ __device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f
 #pragma unroll
     for (int i = 0; i < W; i++)
         if (!(uu[i] <= 0.0009765625)) { const double2 g = spa_fix(fd[i], fdd[i], s[i], uu[i]); re[i] = g.x; im[i] = g.y; }
-    const double ypr = E.ypr, ypi = E.ypi, sdir = (double)E.dir;
+    const double ypr = E.ypr, ypi = E.ypi;
+#if !OPT_SIGN
+    const double sdir = (double)E.dir;
+#endif
     const bool mirror = E.mirror;
 #pragma unroll
     for (int i = 0; i < W; i++) {
         // A * R (conjugated on falling branches); the e^{+-i 3pi/4} of G lives in the entry's harmonics
+#if OPT_SIGN
+        const double gre = re[i], gim = flip_sign(im[i], E.dir < 0 ? 0x80000000u : 0u);
+#else
         const double gre = re[i], gim = sdir * im[i];
+#endif
         const double agr = ReA[i] * gre - ImA[i] * gim, agi = ReA[i] * gim + ImA[i] * gre;
         Cr[i] = agr * cs[i] - agi * sn[i];
         Ci[i] = agr * sn[i] + agi * cs[i];
@@ -992,6 +1031,7 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
                     const int bh = e_ - tb0 < nb - 1 ? e_ - tb0 : nb - 1;
                     if (bl > bh) continue;
                     const double sgn = side == 0 ? 1.0 : -1.0;
+                    const unsigned int smask = side == 0 ? 0u : 0x80000000u;
                     const int k = E.mode, dir = E.dir, ja = E.ja, jb = E.jb;
                     const double dm = E.dm, dn = E.dn, sdir = (double)dir;
                     const double *cmode = coeff + (long long)k * 4; // quads of Re A_k at knot 0; Im A_k is K*4 doubles further
@@ -1010,7 +1050,11 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
                         double *pX = sX + tid + bl * SUM_THREADS;
                         unsigned short *pJ = sJ + tid + bl * SUM_THREADS;
                         for (int b = bl; b <= bh; b++, pF += SUM_THREADS, pX += SUM_THREADS, pJ += SUM_THREADS) {
+#if OPT_SIGN
+                            const double f = flip_sign(BINF(pF, b), smask);
+#else
                             const double f = sgn * BINF(pF, b);
+#endif
                             const bool inside = (j >= 0) && (dir > 0 ? (f >= segA && f < segB) : (f <= segA && f > segB));
                             double x, rr;
                             bool ok = false;
@@ -1081,13 +1125,21 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
                             const double tj = sT[j];
                             if (two) {
                                 const double x2[2] = {pX[0], pX[SUM_THREADS]};
+#if OPT_SIGN
+                                const double f2[2] = {flip_sign(BINF(pF, b), smask), flip_sign(BINF2(pF, b), smask)};
+#else
                                 const double f2[2] = {sgn * BINF(pF, b), sgn * BINF2(pF, b)};
+#endif
                                 eval_bins<2>(x2, f2, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
                                 b += 2; pF += 2 * SUM_THREADS; pX += 2 * SUM_THREADS; pJ += 2 * SUM_THREADS;
                                 id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
                             } else {
                                 const double x1[1] = {pX[0]};
+#if OPT_SIGN
+                                const double f1[1] = {flip_sign(BINF(pF, b), smask)};
+#else
                                 const double f1[1] = {sgn * BINF(pF, b)};
+#endif
                                 eval_bins<1>(x1, f1, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
                                 b += 1; pF += SUM_THREADS; pX += SUM_THREADS; pJ += SUM_THREADS;
                                 id0 += ACC_STRIDE; im0 += ACC_STRIDE;
