@@ -126,6 +126,7 @@ class ClockSampler(threading.Thread):
 def cpu_oracle_rate(items, N, dt, data_w, wfac, max_seconds=20.0, min_walkers=2):
     from oracle.oracle import Oracle
     orc = Oracle("f64")
+    orc.lib.orc_set_num_threads(host_threads())
     cores = orc.lib.orc_num_threads()
     n = (N + 1) // 2
     val = 1.0 / (N * dt)
@@ -142,11 +143,17 @@ def cpu_oracle_rate(items, N, dt, data_w, wfac, max_seconds=20.0, min_walkers=2)
     return done / el, cores, done, el
 
 
-def run_reference(args):
+def host_threads():
+    return len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
+
+
+def run_reference(args, guard):
     """--impl reference: the reference algorithm's CPU implementation (oracle port, all host threads)."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return
+    # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is meant to use every host thread it can
+    os.environ["OMP_NUM_THREADS"] = str(host_threads())
     from oracle import oracle as orc_mod
     orc_mod.build()
     N = grid_len()
@@ -173,7 +180,7 @@ def run_reference(args):
                              "sample": f"{per_step} walkers/step x {args.steps} steps of the bench workload, oracle f64 build, OpenMP"},
             "e2e": {"value": value, "unit": "walkers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
             "gpu_launches": 0}
-    print(json.dumps(line))
+    guard.emit(json.dumps(line))
 
 
 def workload_config(batch, workload="plunge"):
@@ -189,7 +196,24 @@ def workload_config(batch, workload="plunge"):
 
 
 # ---------------------------------------------------------------------------------------------
+class StdoutGuard:
+    """Everything written to fd 1 while the bench runs (NCCL's version banner, library chatter) is sent to stderr, so that
+    stdout carries exactly ONE line: the JSON result."""
+
+    def __init__(self):
+        sys.stdout.flush()
+        self.saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def emit(self, line):
+        sys.stdout.flush()
+        os.dup2(self.saved, 1)
+        print(line, flush=True)
+        os.dup2(2, 1)
+
+
 def main():
+    guard = StdoutGuard()
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=20)
@@ -203,7 +227,7 @@ def main():
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3 if args.impl == "b200" else 0)
     if args.impl == "reference":
-        return run_reference(args)
+        return run_reference(args, guard)
 
     import torch
     import ctypes as C
@@ -420,7 +444,7 @@ def main():
         "work": {"evals_per_walker": evals / B, "mbe_per_walker": mbe / B, "modes_per_walker": pb.n_modes / B,
                  "knots_per_walker": pb.n_knots / B},
     }
-    if not args.no_cpu_baseline:
+    if not args.no_cpu_baseline and world == 1:   # the CPU baseline is an N = 1 figure (rank 0 would stall the other ranks' exit)
         try:
             from oracle import oracle as orc_mod
             orc_mod.build()
@@ -430,7 +454,7 @@ def main():
                                     "sample": f"first {done} walkers of the rank-0 batch, oracle f64 build (OpenMP over bins), {el:.1f} s"}
         except Exception as exc:   # the oracle is test infrastructure: never let it break the bench line
             line["cpu_baseline"] = {"value": None, "unit": "walkers/s", "cores": 0, "kind": "port", "sample": f"unavailable: {exc}"}
-    print(json.dumps(line))
+    guard.emit(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()
 

@@ -87,6 +87,15 @@ int orc_num_threads(void) {
 #endif
 }
 
+/* the timed CPU-baseline legs use every host thread even when the launcher (torchrun) exported OMP_NUM_THREADS=1 */
+void orc_set_num_threads(int n) {
+#ifdef _OPENMP
+    if (n > 0) omp_set_num_threads(n);
+#else
+    (void)n;
+#endif
+}
+
 /* ------------------------------------------------------------------ */
 /* A3: not-a-knot cubic spline, SciPy CubicSpline algebra              */
 /* y is [R][L] row-major; coeff out is [L][R][4] = (y, c1, c2, c3)      */
