@@ -554,6 +554,9 @@ __device__ __forceinline__ double fast_rsqrt(double a) {
 #ifndef OPT_HALLEY
 #define OPT_HALLEY 1 /* rsqrt: one cubic (Halley) step instead of two Newton steps */
 #endif
+#ifndef OPT_SPLIT
+#define OPT_SPLIT 1  /* stage 1: bins 1 and 2 both start from bin 0 (two independent Newton chains), bin 3 from bin 2 */
+#endif
 #define RINT_MAGIC 6755399441055744.0 /* 1.5 * 2^52: (x + M) - M = rint(x) for |x| < 2^51, and the low word of x + M is (int)rint(x) */
 __device__ __forceinline__ double rint_fast(double x) {
 #if OPT_RINT
@@ -1105,6 +1108,39 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
                             xprev = x; fprev = f; rprev = rr;
                             pX[0] = x;
                             pJ[0] = (unsigned short)j;
+#if OPT_SPLIT && SUM_BPT == 4 && SUM_SF
+                            if (b == 0 && bh == 3) {
+                                // All four bins of the thread lie on this branch (the common case).  Instead of the serial chain
+                                // 0 -> 1 -> 2 -> 3, bins 1 and 2 both extrapolate from bin 0 (steps df and 2 df): two independent
+                                // Newton chains interleave in the issue stream; bin 3 then follows bin 2.  Any bin that leaves the
+                                // segment or misses the tolerance sends the thread back to the serial loop.
+                                const double f1 = flip_sign(pF[SUM_THREADS], smask), f2 = flip_sign(pF[2 * SUM_THREADS], smask),
+                                             f3 = flip_sign(pF[3 * SUM_THREADS], smask);
+                                const bool in3 = dir > 0 ? (f1 >= segA && f1 < segB && f2 >= segA && f2 < segB && f3 >= segA && f3 < segB)
+                                                         : (f1 <= segA && f1 > segB && f2 <= segA && f2 > segB && f3 <= segA && f3 > segB);
+                                if (in3) {
+                                    const double kap = fma(2.0 * d3, x, d2) * rr;
+                                    const double dl1 = (f1 - f) * rr, dl2 = (f2 - f) * rr;
+                                    double x1 = fma(dl1, fma(-0.5 * kap, dl1, 1.0), x), x2 = fma(dl2, fma(-0.5 * kap, dl2, 1.0), x);
+                                    const double g1 = x1 * fma(x1, fma(x1, c3, c2), c1) - (f1 - c0);
+                                    const double g2 = x2 * fma(x2, fma(x2, c3, c2), c1) - (f2 - c0);
+                                    const double r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1)), r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
+                                    const double dx1 = g1 * r1, dx2 = g2 * r2;
+                                    x1 -= dx1; x2 -= dx2;
+                                    const double kap2 = fma(2.0 * d3, x2, d2) * r2, dl3 = (f3 - f2) * r2;
+                                    double x3 = fma(dl3, fma(-0.5 * kap2, dl3, 1.0), x2);
+                                    const double g3 = x3 * fma(x3, fma(x3, c3, c2), c1) - (f3 - c0);
+                                    const double dx3 = g3 * fast_rcp(fma(x3, fma(d3, x3, d2), c1));
+                                    x3 -= dx3;
+                                    const double xmin = fmin(fmin(x1, x2), x3), xmax = fmax(fmax(x1, x2), x3);
+                                    if (fmax(fmax(fabs(dx1), fabs(dx2)), fabs(dx3)) <= tol && xmin >= xlo_s && xmax <= xhi_s) {
+                                        pX[SUM_THREADS] = x1; pX[2 * SUM_THREADS] = x2; pX[3 * SUM_THREADS] = x3;
+                                        pJ[SUM_THREADS] = (unsigned short)j; pJ[2 * SUM_THREADS] = (unsigned short)j; pJ[3 * SUM_THREADS] = (unsigned short)j;
+                                        break;
+                                    }
+                                }
+                            }
+#endif
                         }
                     }
                     // ---- stage 2: evaluate the bins two at a time (same segment) in straight-line code ----
