@@ -28,13 +28,17 @@
 #define SUM_THREADS 256
 #endif
 #ifndef SUM_BPT
-#define SUM_BPT 4 /* consecutive bins per thread */
+#define SUM_BPT 4 /* consecutive bins per thread: the tile size every API-visible quantity refers to (emrifd_tile_bins) */
+#endif
+#ifndef SUM_BPT_WIDE
+#define SUM_BPT_WIDE 6 /* wider variant used when its shared memory still lets two CTAs share an SM (short trajectories):
+                          the cold root solve and the entry loop are amortised over 6 bins instead of 4 */
 #endif
 #ifndef SUM_MINB
 #define SUM_MINB 2 /* resident CTAs per SM the register allocation is tuned for */
 #endif
 #ifndef SUM_ENT_CAP
-#define SUM_ENT_CAP 96 /* entry-cache capacity: work-list entries evaluated per pass (a chunk's overlap list is walked in groups) */
+#define SUM_ENT_CAP 64 /* entry-cache capacity: work-list entries evaluated per pass (a chunk's overlap list is walked in groups) */
 #endif
 #ifndef SUM_SF
 #define SUM_SF 1 /* 1: exact bin frequencies staged in smem; 0: recomputed per use (8 B/bin less smem) */
@@ -67,8 +71,11 @@ struct emrifd_handle {
     int64_t partial_cap;
     long long *d_chunk; // per-chunk bin hulls
     int64_t chunk_cap;
-    double *d_tiledd;   // per-tile sum |d~|^2 of the injected data
+    double *d_tiledd;   // per-tile sum |d~|^2 of the injected data (tiles of SUM_THREADS * SUM_BPT bins)
     int64_t tiledd_cap;
+    double *d_tiledd_w; // same for the wide tiles (SUM_THREADS * SUM_BPT_WIDE bins)
+    int64_t tiledd_w_cap;
+    int force_bpt;      // 0 = choose per launch; else SUM_BPT or SUM_BPT_WIDE (EMRIFD_BPT environment variable, for A/B runs)
     const double *d_data; // whitened data [2][n]
     const double *d_wfac; // noise factor  [2][n]
     int64_t n_data;
@@ -701,7 +708,7 @@ __device__ __noinline__ double2 spa_fix(double fdot, double fddot, double s, dou
     return make_double2(re, im);
 }
 
-template <int W>
+template <int W, int BPT>
 __device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f)[W], const double c1, const double d2,
                                           const double d3, const double4 qa, const double4 qb, const double tj,
                                           const double *__restrict__ q, const double *__restrict__ u4, const double dm,
@@ -758,7 +765,7 @@ __device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f
         Ci[i] = agr * sn[i] + agi * cs[i];
         const int id = id0 + i * ACC_STRIDE;
         acc[id] = fma(ypr, Cr[i], fma(-ypi, Ci[i], acc[id]));
-        acc[id + SUM_BPT * ACC_STRIDE] = fma(ypr, Ci[i], fma(ypi, Cr[i], acc[id + SUM_BPT * ACC_STRIDE]));
+        acc[id + BPT * ACC_STRIDE] = fma(ypr, Ci[i], fma(ypi, Cr[i], acc[id + BPT * ACC_STRIDE]));
     }
     if (mirror) {
         const double ymr = E.ymr, ymi = E.ymi;
@@ -766,7 +773,7 @@ __device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f
         for (int i = 0; i < W; i++) {
             const int im_ = im0 + i * ACC_STRIDE;
             acc[im_] = fma(ymr, Cr[i], fma(ymi, Ci[i], acc[im_]));
-            acc[im_ + SUM_BPT * ACC_STRIDE] = fma(ymi, Cr[i], fma(-ymr, Ci[i], acc[im_ + SUM_BPT * ACC_STRIDE]));
+            acc[im_ + BPT * ACC_STRIDE] = fma(ymi, Cr[i], fma(-ymr, Ci[i], acc[im_ + BPT * ACC_STRIDE]));
         }
     }
 }
@@ -805,11 +812,11 @@ __global__ void __launch_bounds__(SUM_THREADS) chunk_range_kernel(const emrifd_w
 
 // sum over both channels of |d~|^2 for every tile of SUM_TILE bins of the injected data: a tile no harmonic touches
 // contributes exactly this to sum |d~ - h~|^2, so mode_sum_kernel does not have to read the data there
-__global__ void __launch_bounds__(256) tile_dd_kernel(const double2 *__restrict__ dw, long long n, double *__restrict__ out) {
+__global__ void __launch_bounds__(256) tile_dd_kernel(const double2 *__restrict__ dw, long long n, int tile, double *__restrict__ out) {
     __shared__ double s[8];
-    const long long j0 = (long long)blockIdx.x * SUM_TILE;
+    const long long j0 = (long long)blockIdx.x * tile;
     double a = 0.0;
-    for (int i = threadIdx.x; i < SUM_TILE; i += 256) {
+    for (int i = threadIdx.x; i < tile; i += 256) {
         const long long j = j0 + i;
         if (j < n) { const double2 d0 = dw[j], d1 = dw[n + j]; a += d0.x * d0.x + d0.y * d0.y + d1.x * d1.x + d1.y * d1.y; }
     }
@@ -824,7 +831,7 @@ __global__ void __launch_bounds__(256) tile_dd_kernel(const double2 *__restrict_
 // 8 resident CTAs per SM keep enough stores in flight to approach the HBM write rate, which the two resident CTAs of
 // mode_sum_kernel (register- and smem-limited) cannot.  The walker descriptor and the chunk hulls are fetched together
 // (one memory round trip before the stores).
-template <bool WRITE_H, bool LIKE>
+template <bool WRITE_H, bool LIKE, int BPT>
 __global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long *crng = p.chunk_rng + (long long)blockIdx.y * p.cpw * 2;
@@ -832,9 +839,9 @@ __global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p)
     const emrifd_walker_t *wp = p.w + blockIdx.y;
     const int K = wp->K;
     const long long out_off = wp->out_off;
-    const long long jt0 = p.j_lo + (p.tile_first + (long long)blockIdx.x * p.tile_stride) * SUM_TILE;
+    const long long jt0 = p.j_lo + (p.tile_first + (long long)blockIdx.x * p.tile_stride) * (SUM_THREADS * BPT);
     const long long jend = p.j_lo + p.j_cnt;
-    const long long jt1 = (jt0 + SUM_TILE < jend ? jt0 + SUM_TILE : jend) - 1;
+    const long long jt1 = (jt0 + (SUM_THREADS * BPT) < jend ? jt0 + (SUM_THREADS * BPT) : jend) - 1;
     bool any = !(c_lo > jt1 || c_hi < jt0);
     const int nrec = K * MAXBR;
     for (int ch = 1; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
@@ -847,8 +854,8 @@ __global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p)
         const double2 z = make_double2(0.0, 0.0);
         const long long zero = p.g.zero;
 #pragma unroll
-        for (int i = 0; i < SUM_BPT; i++) {
-            const int lb = wid * (32 * SUM_BPT) + i * 32 + lane;
+        for (int i = 0; i < BPT; i++) {
+            const int lb = wid * (32 * BPT) + i * 32 + lane;
             if (lb >= ntile_) continue;
             const long long j = jt0 + lb;
             if (p.mask_positive) {
@@ -863,11 +870,11 @@ __global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p)
     }
     if (LIKE && lane == 0) {
         double *o = p.partial + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * (SUM_THREADS / 32) + wid) * 3;
-        o[0] = (wid == 0) ? p.tile_dd[jt0 / SUM_TILE] : 0.0; o[1] = 0.0; o[2] = 0.0;
+        o[0] = (wid == 0) ? p.tile_dd[jt0 / (SUM_THREADS * BPT)] : 0.0; o[1] = 0.0; o[2] = 0.0;
     }
 }
 
-template <bool WRITE_H, bool LIKE>
+template <bool WRITE_H, bool LIKE, int BPT>
 __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile_x, const int walker_y, unsigned char *smraw,
                                               int &staged_walker) {
     __shared__ int s_list[SUM_THREADS];
@@ -876,12 +883,12 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     const emrifd_walker_t wd = p.w[walker_y];
     const int L = wd.L, K = wd.K, R = 2 * K + 4;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * SUM_TILE;
+    const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * (SUM_THREADS * BPT);
     const long long jend = p.j_lo + p.j_cnt;                                   // exclusive
-    const long long jt1 = (jt0 + SUM_TILE < jend ? jt0 + SUM_TILE : jend) - 1; // inclusive
-    const long long j0 = jt0 + (long long)tid * SUM_BPT;                       // this thread's first bin
+    const long long jt1 = (jt0 + (SUM_THREADS * BPT) < jend ? jt0 + (SUM_THREADS * BPT) : jend) - 1; // inclusive
+    const long long j0 = jt0 + (long long)tid * BPT;                       // this thread's first bin
     int nb = (int)(jt1 - j0 + 1);                                              // its number of valid bins
-    nb = nb < 0 ? 0 : (nb > SUM_BPT ? SUM_BPT : nb);
+    nb = nb < 0 ? 0 : (nb > BPT ? BPT : nb);
     const long long zero = p.g.zero;
     const long long pos_lo = zero + jt0, pos_hi = zero + jt1;
     const long long neg_lo = zero - jt1, neg_hi = zero - jt0;
@@ -891,15 +898,15 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     const int *marr = p.m + wd.mode_off, *narr = p.n + wd.mode_off;
     const double2 *ylm = p.ylm + 2 * wd.mode_off;
 
-    // dynamic smem: accumulators [4][SUM_BPT][SUM_THREADS] | entry cache | T[L] | Q[L][16] | U[L][4]
+    // dynamic smem: accumulators [4][BPT][SUM_THREADS] | entry cache | T[L] | Q[L][16] | U[L][4]
     double *acc = reinterpret_cast<double *>(smraw);
-    Entry *ent = reinterpret_cast<Entry *>(acc + 4 * SUM_BPT * ACC_STRIDE);
-    double *sF = reinterpret_cast<double *>(ent + SUM_ENT_CAP); // exact bin frequencies        [SUM_BPT][SUM_THREADS]
-    double *sX = sF + SUM_SF * SUM_BPT * SUM_THREADS;           // roots of the current entry  [SUM_BPT][SUM_THREADS]
-    double *sT = sX + SUM_BPT * SUM_THREADS;
-    unsigned short *sJ = reinterpret_cast<unsigned short *>(sT + SMEM_PER_KNOT * L); // segment indices [SUM_BPT][SUM_THREADS]
+    Entry *ent = reinterpret_cast<Entry *>(acc + 4 * BPT * ACC_STRIDE);
+    double *sF = reinterpret_cast<double *>(ent + SUM_ENT_CAP); // exact bin frequencies        [BPT][SUM_THREADS]
+    double *sX = sF + SUM_SF * BPT * SUM_THREADS;           // roots of the current entry  [BPT][SUM_THREADS]
+    double *sT = sX + BPT * SUM_THREADS;
+    unsigned short *sJ = reinterpret_cast<unsigned short *>(sT + SMEM_PER_KNOT * L); // segment indices [BPT][SUM_THREADS]
     double *sQ = sT + L, *sU = sT + 17 * L;
-#define ACC(c, b) acc[((c) * SUM_BPT + (b)) * ACC_STRIDE + tid]
+#define ACC(c, b) acc[((c) * BPT + (b)) * ACC_STRIDE + tid]
     // ---- does any work-list chunk touch this tile? ----
     const int nrec = K * MAXBR;
     const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
@@ -907,10 +914,10 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     for (int ch = 0; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
     if (!any && (!LIKE || p.tile_dd)) return; // (direct-grid launches only: empty_tile_kernel has dealt with this tile)
 #pragma unroll
-    for (int i = 0; i < 4 * SUM_BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
+    for (int i = 0; i < 4 * BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
 #if SUM_SF
 #pragma unroll
-    for (int b = 0; b < SUM_BPT; b++) {
+    for (int b = 0; b < BPT; b++) {
         const long long jj = j0 + b;
         sF[b * SUM_THREADS + tid] = (b < nb) ? (p.g.fpos ? p.g.fpos[jj] : rmul((double)(int)jj, p.g.val)) : 0.0;
     }
@@ -1022,9 +1029,9 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
         __syncthreads();
         used = true;
 
-        // ---- evaluate: every thread walks its SUM_BPT consecutive bins along each listed branch ----
+        // ---- evaluate: every thread walks its BPT consecutive bins along each listed branch ----
         if (nb > 0) {
-            const int tb0 = tid * SUM_BPT;
+            const int tb0 = tid * BPT;
             for (int li = 0; li < gcount; li++) {
                 const Entry &E = ent[li];
 #pragma unroll 1
@@ -1038,8 +1045,8 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
                     const int k = E.mode, dir = E.dir, ja = E.ja, jb = E.jb;
                     const double dm = E.dm, dn = E.dn, sdir = (double)dir;
                     const double *cmode = coeff + (long long)k * 4; // quads of Re A_k at knot 0; Im A_k is K*4 doubles further
-                    const int offd = side * 2 * SUM_BPT * ACC_STRIDE + tid;       // direct term -> this side
-                    const int offm = (1 - side) * 2 * SUM_BPT * ACC_STRIDE + tid; // mirrored -m term -> other side
+                    const int offd = side * 2 * BPT * ACC_STRIDE + tid;       // direct term -> this side
+                    const int offm = (1 - side) * 2 * BPT * ACC_STRIDE + tid; // mirrored -m term -> other side
                     // ---- stage 1: segment + root for each of this thread's bins.  Hot path = straight-line:
                     //      second-order extrapolation from the previous bin + ONE Newton step; everything else
                     //      (first bin, segment change, slow convergence) goes through the out-of-line slow path ----
@@ -1108,34 +1115,40 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
                             xprev = x; fprev = f; rprev = rr;
                             pX[0] = x;
                             pJ[0] = (unsigned short)j;
-#if OPT_SPLIT && SUM_BPT == 4 && SUM_SF
-                            if (b == 0 && bh == 3) {
-                                // All four bins of the thread lie on this branch (the common case).  Instead of the serial chain
-                                // 0 -> 1 -> 2 -> 3, bins 1 and 2 both extrapolate from bin 0 (steps df and 2 df): two independent
-                                // Newton chains interleave in the issue stream; bin 3 then follows bin 2.  Any bin that leaves the
-                                // segment or misses the tolerance sends the thread back to the serial loop.
-                                const double f1 = flip_sign(pF[SUM_THREADS], smask), f2 = flip_sign(pF[2 * SUM_THREADS], smask),
-                                             f3 = flip_sign(pF[3 * SUM_THREADS], smask);
-                                const bool in3 = dir > 0 ? (f1 >= segA && f1 < segB && f2 >= segA && f2 < segB && f3 >= segA && f3 < segB)
-                                                         : (f1 <= segA && f1 > segB && f2 <= segA && f2 > segB && f3 <= segA && f3 > segB);
-                                if (in3) {
-                                    const double kap = fma(2.0 * d3, x, d2) * rr;
-                                    const double dl1 = (f1 - f) * rr, dl2 = (f2 - f) * rr;
-                                    double x1 = fma(dl1, fma(-0.5 * kap, dl1, 1.0), x), x2 = fma(dl2, fma(-0.5 * kap, dl2, 1.0), x);
-                                    const double g1 = x1 * fma(x1, fma(x1, c3, c2), c1) - (f1 - c0);
-                                    const double g2 = x2 * fma(x2, fma(x2, c3, c2), c1) - (f2 - c0);
-                                    const double r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1)), r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
-                                    const double dx1 = g1 * r1, dx2 = g2 * r2;
-                                    x1 -= dx1; x2 -= dx2;
-                                    const double kap2 = fma(2.0 * d3, x2, d2) * r2, dl3 = (f3 - f2) * r2;
-                                    double x3 = fma(dl3, fma(-0.5 * kap2, dl3, 1.0), x2);
-                                    const double g3 = x3 * fma(x3, fma(x3, c3, c2), c1) - (f3 - c0);
-                                    const double dx3 = g3 * fast_rcp(fma(x3, fma(d3, x3, d2), c1));
-                                    x3 -= dx3;
-                                    const double xmin = fmin(fmin(x1, x2), x3), xmax = fmax(fmax(x1, x2), x3);
-                                    if (fmax(fmax(fabs(dx1), fabs(dx2)), fabs(dx3)) <= tol && xmin >= xlo_s && xmax <= xhi_s) {
-                                        pX[SUM_THREADS] = x1; pX[2 * SUM_THREADS] = x2; pX[3 * SUM_THREADS] = x3;
-                                        pJ[SUM_THREADS] = (unsigned short)j; pJ[2 * SUM_THREADS] = (unsigned short)j; pJ[3 * SUM_THREADS] = (unsigned short)j;
+#if OPT_SPLIT && SUM_SF
+                            if (BPT >= 3 && b == 0 && bh == BPT - 1) {
+                                // All bins of the thread lie on this branch (the common case).  Instead of the serial chain
+                                // 0 -> 1 -> 2 -> ..., bins b+1 and b+2 both extrapolate from bin b (steps df and 2 df): two independent
+                                // Newton chains interleave in the issue stream; an odd last bin follows its predecessor.  A bin that
+                                // leaves the segment or misses the tolerance sends the thread back to the serial loop.
+                                // (f is monotone in the bin index, so the first and the last bin decide "inside the segment".)
+                                const double fn1 = flip_sign(pF[SUM_THREADS], smask), fnl = flip_sign(pF[(BPT - 1) * SUM_THREADS], smask);
+                                const bool in_all = dir > 0 ? (fn1 >= segA && fn1 < segB && fnl >= segA && fnl < segB)
+                                                            : (fn1 <= segA && fn1 > segB && fnl <= segA && fnl > segB);
+                                if (in_all) {
+                                    double xs[BPT];
+                                    double xb = x, fb = f, rb = rr, worst = 0.0, xmin = x, xmax = x;
+#pragma unroll
+                                    for (int q = 0; q + 1 < BPT; q += 2) { // from bin q: bins q+1 and (if it exists) q+2
+                                        const bool two = q + 2 < BPT;
+                                        const double kap = fma(2.0 * d3, xb, d2) * rb;
+                                        const double f1 = flip_sign(pF[(q + 1) * SUM_THREADS], smask);
+                                        const double f2 = two ? flip_sign(pF[(q + 2) * SUM_THREADS], smask) : f1;
+                                        const double dl1 = (f1 - fb) * rb, dl2 = (f2 - fb) * rb;
+                                        double x1 = fma(dl1, fma(-0.5 * kap, dl1, 1.0), xb), x2 = fma(dl2, fma(-0.5 * kap, dl2, 1.0), xb);
+                                        const double g1 = x1 * fma(x1, fma(x1, c3, c2), c1) - (f1 - c0);
+                                        const double g2 = x2 * fma(x2, fma(x2, c3, c2), c1) - (f2 - c0);
+                                        const double r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1)), r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
+                                        const double dx1 = g1 * r1, dx2 = g2 * r2;
+                                        x1 -= dx1; x2 -= dx2;
+                                        xs[q + 1] = x1;
+                                        worst = fmax(worst, fmax(fabs(dx1), fabs(dx2)));
+                                        xmin = fmin(xmin, fmin(x1, x2)); xmax = fmax(xmax, fmax(x1, x2));
+                                        if (two) { xs[q + 2] = x2; xb = x2; fb = f2; rb = r2; }
+                                    }
+                                    if (worst <= tol && xmin >= xlo_s && xmax <= xhi_s) {
+#pragma unroll
+                                        for (int q = 1; q < BPT; q++) { pX[q * SUM_THREADS] = xs[q]; pJ[q * SUM_THREADS] = (unsigned short)j; }
                                         break;
                                     }
                                 }
@@ -1166,7 +1179,7 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
 #else
                                 const double f2[2] = {sgn * BINF(pF, b), sgn * BINF2(pF, b)};
 #endif
-                                eval_bins<2>(x2, f2, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
+                                eval_bins<2, BPT>(x2, f2, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
                                 b += 2; pF += 2 * SUM_THREADS; pX += 2 * SUM_THREADS; pJ += 2 * SUM_THREADS;
                                 id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
                             } else {
@@ -1176,7 +1189,7 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
 #else
                                 const double f1[1] = {sgn * BINF(pF, b)};
 #endif
-                                eval_bins<1>(x1, f1, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
+                                eval_bins<1, BPT>(x1, f1, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
                                 b += 1; pF += SUM_THREADS; pX += SUM_THREADS; pJ += SUM_THREADS;
                                 id0 += ACC_STRIDE; im0 += ACC_STRIDE;
                             }
@@ -1189,20 +1202,20 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     }
 
     // ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
-    // Warp-local transposed read-out: a warp owns 32*SUM_BPT consecutive bins (its lanes' bins); in iteration i lane l
+    // Warp-local transposed read-out: a warp owns 32*BPT consecutive bins (its lanes' bins); in iteration i lane l
     // finalises bin 32*i + l of them, so the warp stores 512 contiguous bytes per array and reads the data stream the
     // same way.  Only __syncwarp is needed: warps that finish early read out while the others still evaluate.
     __syncwarp();
     double a0 = 0, a1 = 0, a2 = 0;
     const int ntile = (int)(jt1 - jt0 + 1);
 #pragma unroll
-    for (int i = 0; i < SUM_BPT; i++) {
-        const int lb = wid * (32 * SUM_BPT) + i * 32 + lane;
+    for (int i = 0; i < BPT; i++) {
+        const int lb = wid * (32 * BPT) + i * 32 + lane;
         if (lb >= ntile) continue;
         const long long j = jt0 + lb;
-        const int own = lb / SUM_BPT, bb = lb % SUM_BPT;
+        const int own = lb / BPT, bb = lb % BPT;
         const double *ap = acc + bb * ACC_STRIDE + own;
-        double wpr = ap[0], wpi = ap[SUM_BPT * ACC_STRIDE], wmr = ap[2 * SUM_BPT * ACC_STRIDE], wmi = ap[3 * SUM_BPT * ACC_STRIDE];
+        double wpr = ap[0], wpi = ap[BPT * ACC_STRIDE], wmr = ap[2 * BPT * ACC_STRIDE], wmi = ap[3 * BPT * ACC_STRIDE];
         if (j == 0) { wpr += wmr; wpi += wmi; wmr = wpr; wmi = wpi; }
         const double pr_ = 0.5 * (-wmr - wpr), pi_ = 0.5 * (-wmi + wpi);
         const double xr_ = 0.5 * (wmi + wpi), xi_ = 0.5 * (-wmr + wpr);
@@ -1252,7 +1265,7 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
 // Persistent CTAs (one grid of #SM x resident-CTAs) pull the non-empty tiles queued by empty_tile_kernel: the heavy kernel
 // is never launched on the >90 % of the band that a sparse system leaves empty, and tiles of very different cost balance
 // dynamically.
-template <bool WRITE_H, bool LIKE>
+template <bool WRITE_H, bool LIKE, int BPT>
 __global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ unsigned long long s_q[2]; // double-buffered queue items: the next one is fetched while the current tile runs
@@ -1272,7 +1285,7 @@ __global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
             const unsigned int it = atomicAdd(&p.qctl[1], 1u);
             if (it < nq) qn = p.queue[it];
         }
-        mode_sum_tile<WRITE_H, LIKE>(p, (int)(q & 0xffffffffu), (int)(q >> 32), smraw, staged_walker);
+        mode_sum_tile<WRITE_H, LIKE, BPT>(p, (int)(q & 0xffffffffu), (int)(q >> 32), smraw, staged_walker);
         if (threadIdx.x == 0) s_q[cur ^ 1] = qn;
         __syncthreads(); // every warp has left the tile (shared memory is reused) and sees the next item
     }
@@ -1281,11 +1294,11 @@ __global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
 // Small launches (a few hundred tiles: one bin-sharded slice of a single long waveform, or a single short waveform) fit in
 // about one wave of CTAs; there the hardware's breadth-first placement of a plain (tile, walker) grid balances the SMs
 // better than queue order (measured on the 8-GPU bin-sharded configs[3] slices: 8.6 vs 13.1 ms), so they keep a direct grid.
-template <bool WRITE_H, bool LIKE>
+template <bool WRITE_H, bool LIKE, int BPT>
 __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_direct_kernel(SumParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
     int staged_walker = -1;
-    mode_sum_tile<WRITE_H, LIKE>(p, (int)blockIdx.x, (int)blockIdx.y, smraw, staged_walker);
+    mode_sum_tile<WRITE_H, LIKE, BPT>(p, (int)blockIdx.x, (int)blockIdx.y, smraw, staged_walker);
 }
 
 // deterministic second stage: one CTA per walker
@@ -1642,8 +1655,8 @@ static size_t spline_smem_bytes(int L, bool tiled) {
     return sizeof(double) * (size_t)L * (5 + (tiled ? 2 * SPL_ROWS : 0));
 }
 
-static size_t sum_smem_bytes(int L) {
-    return sizeof(double) * 4 * SUM_BPT * ACC_STRIDE + (8 * SUM_SF + 8 + 2) * SUM_BPT * SUM_THREADS + sizeof(Entry) * SUM_ENT_CAP +
+static size_t sum_smem_bytes(int L, int bpt = SUM_BPT) {
+    return sizeof(double) * 4 * bpt * ACC_STRIDE + (8 * SUM_SF + 8 + 2) * bpt * SUM_THREADS + sizeof(Entry) * SUM_ENT_CAP +
            sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
 
@@ -1737,12 +1750,18 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaFuncSetAttribute(spline_build_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
     cudaFuncSetAttribute(mode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_CAP * 10);
-    cudaFuncSetAttribute(mode_sum_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(mode_sum_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(mode_sum_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(mode_sum_direct_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(mode_sum_direct_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(mode_sum_direct_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+#define SET_SMEM(W_, L_) \
+    cudaFuncSetAttribute(mode_sum_kernel<W_, L_, SUM_BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(mode_sum_kernel<W_, L_, SUM_BPT_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(mode_sum_direct_kernel<W_, L_, SUM_BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
+    cudaFuncSetAttribute(mode_sum_direct_kernel<W_, L_, SUM_BPT_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    SET_SMEM(true, false) SET_SMEM(true, true) SET_SMEM(false, true)
+#undef SET_SMEM
+    {
+        const char *fb = getenv("EMRIFD_BPT");
+        h->force_bpt = fb ? atoi(fb) : 0;
+        if (h->force_bpt != SUM_BPT && h->force_bpt != SUM_BPT_WIDE) h->force_bpt = 0;
+    }
     if (cudaGetLastError() != cudaSuccess) { delete h; return EMRIFD_ERR_CUDA; }
     *out = h;
     return 0;
@@ -1752,7 +1771,7 @@ int emrifd_destroy(emrifd_handle_t *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_queue); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd);
+    cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_queue); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd); cudaFree(h->d_tiledd_w);
     if (h->h_ws) cudaFreeHost(h->h_ws);
     for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); cudaEventDestroy(h->stage_ev[i]); }
     for (int i = 0; i < 64; i++) { cudaEventDestroy(h->ev_a[i]); cudaEventDestroy(h->ev_b[i]); }
@@ -1861,7 +1880,8 @@ int emrifd_batch_segment(emrifd_handle_t *h, const emrifd_walker_t *walkers, int
 static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const double *t, const double *coeff,
                          const int32_t *m_arr, const int32_t *n_arr, const double *ylm, const emrifd_branch_t *branches,
                          int64_t N, double val, const double *fpos, int flags, int64_t j_lo, int64_t j_cnt,
-                         double *hp, double *hc, double *like_out, int64_t tile_first = 0, int64_t tile_stride = 1) {
+                         double *hp, double *hc, double *like_out, int64_t tile_first = 0, int64_t tile_stride = 1,
+                         int bpt_req = 0) {
     const bool write_h = hp && hc, like = like_out != nullptr;
     if (!write_h && !like) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum: nothing to compute (no output requested)");
     if (like && !h->d_data) return set_err(h, EMRIFD_ERR_NO_DATA, "likelihood requested before emrifd_set_data");
@@ -1878,7 +1898,15 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     p.include_minus_m = (flags & EMRIFD_INCLUDE_MINUS_M) != 0; p.mask_positive = mask_pos;
     p.hp = (double2 *)hp; p.hc = (double2 *)hc;
     p.dw = (const double2 *)h->d_data; p.wf = h->d_wfac; p.n_data = h->n_data;
-    const int64_t ntiles_all = (j_cnt + SUM_TILE - 1) / SUM_TILE;
+    // bins per thread: the wide variant when two of its CTAs still fit on an SM (short trajectories), else the base one
+    int bpt = bpt_req ? bpt_req : h->force_bpt;
+    if (!bpt) {
+        int fit = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, mode_sum_kernel<true, true, SUM_BPT_WIDE>, SUM_THREADS, sum_smem_bytes(Lmax, SUM_BPT_WIDE));
+        bpt = fit >= SUM_MINB ? SUM_BPT_WIDE : SUM_BPT;
+    }
+    const int64_t tile_bins = (int64_t)SUM_THREADS * bpt;
+    const int64_t ntiles_all = (j_cnt + tile_bins - 1) / tile_bins;
     if (tile_stride < 1 || tile_first < 0) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum: bad tile_first / tile_stride");
     if (tile_first >= ntiles_all) { // this rank owns no tile: all sums are zero
         if (like) CUDA_TRY(h, cudaMemsetAsync(like_out, 0, sizeof(double) * 3 * (size_t)B, h->stream));
@@ -1899,9 +1927,9 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
         chunk_range_kernel<<<cgrid, SUM_THREADS, 0, h->stream>>>(h->d_walkers, branches, (N - 1) / 2, h->d_chunk, cpw);
         h->launches++;
         p.chunk_rng = h->d_chunk; p.cpw = cpw;
-        p.tile_dd = (like && (j_lo % SUM_TILE) == 0) ? h->d_tiledd : nullptr;
+        p.tile_dd = (like && (j_lo % tile_bins) == 0) ? (bpt == SUM_BPT ? h->d_tiledd : h->d_tiledd_w) : nullptr;
     }
-    const size_t smem = sum_smem_bytes(Lmax);
+    const size_t smem = sum_smem_bytes(Lmax, bpt);
     if ((int64_t)smem > h->max_dyn_smem) return set_err(h, EMRIFD_ERR_TOO_MANY_KNOTS, "trajectory too long for the shared-memory staging of the mode-sum kernel");
     dim3 grid((unsigned)ntiles, (unsigned)B);
     int ev = -1;
@@ -1916,23 +1944,29 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
         p.queue = (unsigned long long *)h->d_queue + 2;
         CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, 16, h->stream));
     }
-    if (write_h && like) empty_tile_kernel<true, true><<<grid, SUM_THREADS, 0, h->stream>>>(p);
-    else if (write_h) empty_tile_kernel<true, false><<<grid, SUM_THREADS, 0, h->stream>>>(p);
-    else empty_tile_kernel<false, true><<<grid, SUM_THREADS, 0, h->stream>>>(p);
+    // dispatch on (WRITE_H, LIKE, bins per thread)
+#define SUM_DISPATCH(KERNEL, GRID, SMEM)                                                                              \
+    do {                                                                                                              \
+        if (bpt == SUM_BPT) {                                                                                         \
+            if (write_h && like) KERNEL<true, true, SUM_BPT><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);              \
+            else if (write_h) KERNEL<true, false, SUM_BPT><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);                \
+            else KERNEL<false, true, SUM_BPT><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);                             \
+        } else {                                                                                                      \
+            if (write_h && like) KERNEL<true, true, SUM_BPT_WIDE><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);         \
+            else if (write_h) KERNEL<true, false, SUM_BPT_WIDE><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);           \
+            else KERNEL<false, true, SUM_BPT_WIDE><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);                        \
+        }                                                                                                             \
+    } while (0)
+    SUM_DISPATCH(empty_tile_kernel, grid, 0);
     h->launches++;
     int per_sm = 0;
-    if (write_h && like) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, true>, SUM_THREADS, smem);
-    else if (write_h) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, false>, SUM_THREADS, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<false, true>, SUM_THREADS, smem);
+    if (bpt == SUM_BPT) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, true, SUM_BPT>, SUM_THREADS, smem);
+    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, true, SUM_BPT_WIDE>, SUM_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     int64_t pgrid = (int64_t)h->num_sms * per_sm;
-    if (ntiles * B <= 4 * pgrid) { // about one wave: direct grid (see mode_sum_direct_kernel)
-        if (write_h && like) mode_sum_direct_kernel<true, true><<<grid, SUM_THREADS, smem, h->stream>>>(p);
-        else if (write_h) mode_sum_direct_kernel<true, false><<<grid, SUM_THREADS, smem, h->stream>>>(p);
-        else mode_sum_direct_kernel<false, true><<<grid, SUM_THREADS, smem, h->stream>>>(p);
-    } else if (write_h && like) mode_sum_kernel<true, true><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
-    else if (write_h) mode_sum_kernel<true, false><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
-    else mode_sum_kernel<false, true><<<(unsigned)pgrid, SUM_THREADS, smem, h->stream>>>(p);
+    if (ntiles * B <= 4 * pgrid) SUM_DISPATCH(mode_sum_direct_kernel, grid, smem); // about one wave: direct grid
+    else SUM_DISPATCH(mode_sum_kernel, (unsigned)pgrid, smem);
+#undef SUM_DISPATCH
     if (ev >= 0) cudaEventRecord(h->ev_b[ev], h->stream);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -1955,7 +1989,10 @@ int emrifd_batch_sum(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t
     if ((rc = check_grid(h, N, val, fpos))) return rc;
     cudaSetDevice(h->device);
     if ((rc = upload_walkers(h, walkers, B))) return rc;
-    return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, j_lo, j_cnt, hp, hc, like_out);
+    // a slice that does not start on a wide-tile boundary keeps the base tiles (slice starts are aligned to emrifd_tile_bins())
+    const int bpt_req = (j_lo % ((int64_t)SUM_THREADS * SUM_BPT_WIDE) == 0) ? 0 : SUM_BPT;
+    return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, j_lo, j_cnt, hp, hc, like_out, 0, 1,
+                         bpt_req);
 }
 
 int emrifd_tile_bins(void) { return SUM_TILE; }
@@ -1974,7 +2011,7 @@ int emrifd_batch_sum_cyclic(emrifd_handle_t *h, const emrifd_walker_t *walkers, 
     cudaSetDevice(h->device);
     if ((rc = upload_walkers(h, walkers, B))) return rc;
     return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, 0, (N + 1) / 2, hp, hc, like_out,
-                         tile_first, tile_stride);
+                         tile_first, tile_stride, SUM_BPT); // ownership is defined on emrifd_tile_bins() = base tiles
 }
 
 int emrifd_fd_waveform_batch(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,
@@ -2014,11 +2051,14 @@ int emrifd_set_data(emrifd_handle_t *h, const double *d_whitened, const double *
     if (!h || !d_whitened || !noise_factor || n <= 0) return set_err(h, EMRIFD_ERR_INVALID, "set_data: bad argument");
     h->d_data = d_whitened; h->d_wfac = noise_factor; h->n_data = n;
     cudaSetDevice(h->device);
-    const int64_t nt = (n + SUM_TILE - 1) / SUM_TILE;
+    const int tile = SUM_THREADS * SUM_BPT, tile_w = SUM_THREADS * SUM_BPT_WIDE;
+    const int64_t nt = (n + tile - 1) / tile, nt_w = (n + tile_w - 1) / tile_w;
     int rc = ensure_bytes(h, (void **)&h->d_tiledd, &h->tiledd_cap, (int64_t)sizeof(double) * nt);
     if (rc) return rc;
-    tile_dd_kernel<<<(unsigned)nt, 256, 0, h->stream>>>((const double2 *)d_whitened, n, h->d_tiledd);
-    h->launches++;
+    if ((rc = ensure_bytes(h, (void **)&h->d_tiledd_w, &h->tiledd_w_cap, (int64_t)sizeof(double) * nt_w))) return rc;
+    tile_dd_kernel<<<(unsigned)nt, 256, 0, h->stream>>>((const double2 *)d_whitened, n, tile, h->d_tiledd);
+    tile_dd_kernel<<<(unsigned)nt_w, 256, 0, h->stream>>>((const double2 *)d_whitened, n, tile_w, h->d_tiledd_w);
+    h->launches += 2;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }

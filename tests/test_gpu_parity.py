@@ -400,7 +400,11 @@ def test_cyclic_tile_sharding_sums_to_full_likelihood(generator, torch_cuda):
                                                   hp2.data_ptr(), hc2.data_ptr(), out.data_ptr()))
             tot += out.cpu().numpy()
             owned = ((torch.arange(n, device=h.torch_device) // tile) % W) == r
-            assert torch.equal(hp2[:, owned], hp[:, owned]) and torch.equal(hc2[:, owned], hc[:, owned])
+            # (not bit-for-bit: the full call may run the wide 6-bins-per-thread variant, the cyclic call always the base one;
+            #  their Newton chains start from different bins, which moves results at the rounding level)
+            for full_ch, own_ch in ((hp, hp2), (hc, hc2)):
+                tol_ = 1e-12 * float(full_ch.abs().max())
+                assert float((own_ch[:, owned] - full_ch[:, owned]).abs().max()) <= tol_
             assert torch.all(hp2[:, ~owned] == complex(7.0, 7.0))          # tiles of other ranks are not touched
         scale = np.abs(full[:, 2:3])
         assert np.all(np.abs(tot - full) <= 1e-12 * scale), (W, tot, full)
@@ -415,18 +419,18 @@ def test_cyclic_tile_sharding_sums_to_full_likelihood(generator, torch_cuda):
 
 def test_queue_and_direct_launch_modes_agree_bit_for_bit(generator, torch_cuda):
     """The mode sum launches a direct (tile, walker) grid for small launches and persistent CTAs fed by a tile queue for
-    large ones (> 4 waves).  Results must not depend on which: a 24-walker batch (queue) equals its single-walker calls
+    large ones (> 4 waves).  Results must not depend on which: a 40-walker batch (queue) equals its single-walker calls
     (direct) bit for bit -- waveforms and likelihood sums -- and is reproducible run to run (queue order is not)."""
     torch = torch_cuda
     from emri_frequencydomainwaveforms_b200 import _lib, engine
     h = _lib.get_handle()
     base_items = [make_item(generator, "plunge", dt=20.0), make_item(generator, "ecc_many", dt=20.0), make_item(generator, "cfg1_like", dt=20.0)]
-    items = [dict(base_items[i % 3], Phi_phi=base_items[i % 3]["Phi_phi"] + 0.1 * i) for i in range(24)]
+    items = [dict(base_items[i % 3], Phi_phi=base_items[i % 3]["Phi_phi"] + 0.1 * i) for i in range(40)]
     N = max(it["N"] for it in items)
     n = (N + 1) // 2
     val = 1.0 / (N * 20.0)
     tile = h.lib.emrifd_tile_bins()
-    assert 24 * ((n + tile - 1) // tile) > 4 * 2 * torch.cuda.get_device_properties(0).multi_processor_count   # -> queue path
+    assert 40 * ((n + 2 * tile - 1) // (2 * tile)) > 4 * 2 * torch.cuda.get_device_properties(0).multi_processor_count   # -> queue path (any tile size)
     db0 = engine.DeviceBatch(engine.PackedBatch([items[0]]), h)
     hp0, hc0, _ = engine.run_waveform(db0, N, val, mask_positive=True)
     w = torch.full((2, n), 2.0e19, dtype=torch.float64, device=h.torch_device)
@@ -439,7 +443,7 @@ def test_queue_and_direct_launch_modes_agree_bit_for_bit(generator, torch_cuda):
     assert torch.equal(hpB, hpB2) and torch.equal(hcB, hcB2) and torch.equal(likeB, likeB2)          # run-to-run
     only = engine.run_loglike(dbB, N, val)                                                             # no h written
     assert torch.equal(only, likeB)
-    for i in (0, 1, 2, 13, 23):
+    for i in (0, 1, 2, 13, 39):
         db1 = engine.DeviceBatch(engine.PackedBatch([items[i]]), h)
         hp1, hc1, like1 = engine.run_waveform(db1, N, val, mask_positive=True, like=True)
         assert torch.equal(hp1[0], hpB[i]) and torch.equal(hc1[0], hcB[i]) and torch.equal(like1[0], likeB[i]), i
