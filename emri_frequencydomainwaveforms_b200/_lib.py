@@ -34,7 +34,7 @@ SYMBOLS = [
     "emrifd_fd_waveform_batch", "emrifd_batch_status", "emrifd_set_data", "emrifd_inner_product",
     "emrifd_loglike", "emrifd_loglike_batch_host", "emrifd_bench_fp64_fma", "emrifd_launch_count",
     "emrifd_sum_kernel_time", "emrifd_mode_select", "emrifd_ylm_batch", "emrifd_mode_compact_count",
-    "emrifd_mode_compact_gather", "emrifd_tile_bins", "emrifd_cyclic_tile_bins", "emrifd_batch_sum_cyclic",
+    "emrifd_mode_compact_gather", "emrifd_tile_bins", "emrifd_batch_sum_cyclic",
     "emrifd_synth_amplitude"]
 
 _lib = None
@@ -66,7 +66,6 @@ def load():
     lib.emrifd_batch_spline.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp]
     lib.emrifd_batch_segment.argtypes = [vp, vp, i64, vp, vp, vp, vp, i64, dbl, vp, vp, vp]
     lib.emrifd_batch_sum.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, dbl, vp, i32, i64, i64, vp, vp, vp]
-    lib.emrifd_cyclic_tile_bins.argtypes = [vp, i64]
     lib.emrifd_batch_sum_cyclic.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, i64, dbl, vp, i32, i64, i64, vp, vp, vp]
     lib.emrifd_fd_waveform_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, vp, i32,
                                              vp, vp, vp, vp, vp]

@@ -1877,17 +1877,6 @@ int emrifd_batch_segment(emrifd_handle_t *h, const emrifd_walker_t *walkers, int
     return batch_segment_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, N, val, fpos, branches, n_eval);
 }
 
-// bins per thread of the mode sum for trajectories of up to Lmax knots: the wide variant when two of its CTAs still fit on an SM
-static int choose_bpt(emrifd_handle *h, int Lmax, int req) {
-    int bpt = req ? req : h->force_bpt;
-    if (!bpt) {
-        int fit = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, mode_sum_kernel<true, true, SUM_BPT_WIDE>, SUM_THREADS, sum_smem_bytes(Lmax, SUM_BPT_WIDE));
-        bpt = fit >= SUM_MINB ? SUM_BPT_WIDE : SUM_BPT;
-    }
-    return bpt;
-}
-
 static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const double *t, const double *coeff,
                          const int32_t *m_arr, const int32_t *n_arr, const double *ylm, const emrifd_branch_t *branches,
                          int64_t N, double val, const double *fpos, int flags, int64_t j_lo, int64_t j_cnt,
@@ -1910,7 +1899,12 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     p.hp = (double2 *)hp; p.hc = (double2 *)hc;
     p.dw = (const double2 *)h->d_data; p.wf = h->d_wfac; p.n_data = h->n_data;
     // bins per thread: the wide variant when two of its CTAs still fit on an SM (short trajectories), else the base one
-    const int bpt = choose_bpt(h, Lmax, bpt_req);
+    int bpt = bpt_req ? bpt_req : h->force_bpt;
+    if (!bpt) {
+        int fit = 0;
+        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, mode_sum_kernel<true, true, SUM_BPT_WIDE>, SUM_THREADS, sum_smem_bytes(Lmax, SUM_BPT_WIDE));
+        bpt = fit >= SUM_MINB ? SUM_BPT_WIDE : SUM_BPT;
+    }
     const int64_t tile_bins = (int64_t)SUM_THREADS * bpt;
     const int64_t ntiles_all = (j_cnt + tile_bins - 1) / tile_bins;
     if (tile_stride < 1 || tile_first < 0) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum: bad tile_first / tile_stride");
@@ -2003,12 +1997,6 @@ int emrifd_batch_sum(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t
 
 int emrifd_tile_bins(void) { return SUM_TILE; }
 
-int emrifd_cyclic_tile_bins(emrifd_handle_t *h, int64_t Lmax) {
-    if (!h || Lmax < 4 || Lmax > EMRIFD_MAX_KNOTS) return EMRIFD_ERR_INVALID;
-    cudaSetDevice(h->device);
-    return SUM_THREADS * choose_bpt(h, (int)Lmax, 0);
-}
-
 int emrifd_batch_sum_cyclic(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,
                             const double *t, const double *coeff, const int32_t *m_arr, const int32_t *n_arr,
                             const double *ylm, const emrifd_branch_t *branches,
@@ -2023,7 +2011,7 @@ int emrifd_batch_sum_cyclic(emrifd_handle_t *h, const emrifd_walker_t *walkers, 
     cudaSetDevice(h->device);
     if ((rc = upload_walkers(h, walkers, B))) return rc;
     return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, 0, (N + 1) / 2, hp, hc, like_out,
-                         tile_first, tile_stride); // ownership is defined on tiles of emrifd_cyclic_tile_bins(h, Lmax) bins
+                         tile_first, tile_stride, SUM_BPT); // ownership is defined on emrifd_tile_bins() = base tiles
 }
 
 int emrifd_fd_waveform_batch(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,

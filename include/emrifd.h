@@ -117,14 +117,11 @@ int emrifd_batch_sum(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t
                      double *hp, double *hc,      /* may both be NULL (likelihood only) */
                      double *like_out /* [B][3] device: ll, <d|h>, <h|h>; NULL = no likelihood */);
 /* Cyclic tile sharding of the mode sum (multi-GPU frequency-bin sharding of ONE long, high-mode-count waveform, SURVEY.md
- * section 8e(2)): the f >= 0 bins are cut into tiles of emrifd_cyclic_tile_bins() bins and this call evaluates tiles tile_first,
+ * section 8e(2)): the f >= 0 bins are cut into tiles of emrifd_tile_bins() bins and this call evaluates tiles tile_first,
  * tile_first + tile_stride, ... (rank r of W passes r, W).  Neighbouring tiles carry similar work, so the interleave balances
  * the ranks without a work histogram, and every rank keeps several waves of tiles.  like_out [B][3] holds the partial sums
  * over the owned tiles (all_reduce(SUM) them); hp/hc, if given, need EMRIFD_MASK_POSITIVE and receive the owned tiles only. */
-int emrifd_tile_bins(void); /* base tile: alignment unit of the contiguous slices of emrifd_batch_sum */
-/* tile size emrifd_batch_sum_cyclic uses for a batch whose longest trajectory has Lmax knots (the kernel runs 1536-bin tiles
- * when its shared memory allows, else the 1024-bin base tiles; every rank holds the same replicated batch, so all agree) */
-int emrifd_cyclic_tile_bins(emrifd_handle_t *h, int64_t Lmax);
+int emrifd_tile_bins(void);
 int emrifd_batch_sum_cyclic(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,
                             const double *t, const double *coeff, const int32_t *m_arr, const int32_t *n_arr,
                             const double *ylm, const emrifd_branch_t *branches,

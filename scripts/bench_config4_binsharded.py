@@ -81,7 +81,7 @@ def main():
     h.status()
     work = D.bin_work_histogram(db.branches_host(), it["m_arr"], N)
     if args.sharding == "cyclic":
-        tile = h.lib.emrifd_cyclic_tile_bins(h.h, int(db.pb.Lmax))
+        tile = h.lib.emrifd_tile_bins()
         owner = (np.arange(len(work)) // tile) % world
         per_rank = [int(work[owner == r].sum()) for r in range(world)]
         slices = [(None, int((owner == r).sum())) for r in range(world)]

@@ -385,9 +385,8 @@ def test_cyclic_tile_sharding_sums_to_full_likelihood(generator, torch_cuda):
     dw = (torch.stack([hp[0], hc[0]]) * w).contiguous()
     h.check(h.lib.emrifd_set_data(h.h, dw.data_ptr(), w.data_ptr(), n))
     full = engine.run_loglike(db, N, val).cpu().numpy()
+    tile = h.lib.emrifd_tile_bins()
     pb = db.pb
-    tile = h.lib.emrifd_cyclic_tile_bins(h.h, int(pb.Lmax))
-    assert tile in (h.lib.emrifd_tile_bins(), h.lib.emrifd_tile_bins() * 3 // 2)
     flags = _lib.INCLUDE_MINUS_M | _lib.MASK_POSITIVE
     for W in (1, 3, 8):
         tot = np.zeros_like(full)
@@ -401,7 +400,11 @@ def test_cyclic_tile_sharding_sums_to_full_likelihood(generator, torch_cuda):
                                                   hp2.data_ptr(), hc2.data_ptr(), out.data_ptr()))
             tot += out.cpu().numpy()
             owned = ((torch.arange(n, device=h.torch_device) // tile) % W) == r
-            assert torch.equal(hp2[:, owned], hp[:, owned]) and torch.equal(hc2[:, owned], hc[:, owned])   # same kernel variant, same tiles
+            # (not bit-for-bit: the full call may run the wide 6-bins-per-thread variant, the cyclic call always the base one;
+            #  their Newton chains start from different bins, which moves results at the rounding level)
+            for full_ch, own_ch in ((hp, hp2), (hc, hc2)):
+                tol_ = 1e-12 * float(full_ch.abs().max())
+                assert float((own_ch[:, owned] - full_ch[:, owned]).abs().max()) <= tol_
             assert torch.all(hp2[:, ~owned] == complex(7.0, 7.0))          # tiles of other ranks are not touched
         scale = np.abs(full[:, 2:3])
         assert np.all(np.abs(tot - full) <= 1e-12 * scale), (W, tot, full)
