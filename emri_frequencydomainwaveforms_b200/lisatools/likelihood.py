@@ -108,7 +108,9 @@ class FDTemplateModel:
         if producers == "device" and mode_selection is None:
             # Ylm, mode selection and compaction on the device; only the sparse tracks cross PCIe
             P = np.atleast_2d(params)
-            ang = np.array([self.gen._transform(*row[7:11]) for row in P])      # theta, phi, cos2psi, sin2psi
+            from ..waveform import ssb_transform_batch
+            ang = np.stack(ssb_transform_batch(P[:, 7], P[:, 8], P[:, 9], P[:, 10],
+                                               detector_frame=getattr(self.gen, "frame", "detector") == "detector"), axis=1)
             db, ok = self.base.prepare_batch_device(P[:, 0], P[:, 1], P[:, 3], P[:, 4], ang[:, 0], ang[:, 1], dist=P[:, 6],
                                                     Phi_phi0=P[:, 11], Phi_r0=P[:, 13], T=T, dt=dt, eps=eps,
                                                     cos2psi=ang[:, 2], sin2psi=ang[:, 3], handle=h)

@@ -158,13 +158,10 @@ class FastSchwarzschildEccentricFlux:
         M = np.atleast_1d(np.asarray(M, dtype=np.float64))
         mu, p0, e0, theta, phi, Phi_phi0, Phi_r0, cos2psi, sin2psi = map(bc, (mu, p0, e0, theta, phi, Phi_phi0, Phi_r0, cos2psi, sin2psi))
         nb = len(M)
-        ok = np.ones(nb, dtype=bool)
-        for i in range(nb):
-            try:
-                self.sanity_check_init(M[i], mu[i], p0[i], e0[i])
-                self.sanity_check_viewing_angles(theta[i], phi[i])
-            except ValueError:
-                ok[i] = False
+        # the domain checks of sanity_check_init / sanity_check_viewing_angles, vectorised (same conditions)
+        ok = ~((e0 > 0.75) | (e0 < 0.0) | ((p0 < 10.0) & ~(p0 >= 7.2 + 2.0 * e0)) | (p0 > 16.0 + 2.0 * e0)
+               | (theta < 0.0) | (theta > np.pi) | ~(M > 0.0) | ~(mu > 0.0))
+        ok &= np.isfinite(M) & np.isfinite(mu) & np.isfinite(p0) & np.isfinite(e0) & np.isfinite(theta) & np.isfinite(phi)
         ig = self.inspiral_generator
         nthreads = nthreads or min(len(os.sched_getaffinity(0)), 16)
         sel = np.where(ok)[0]
@@ -249,7 +246,10 @@ def viewing_angles(qS, phiS, qK, phiK):
     GenerateEMRIWaveform._get_viewing_angles: theta = arccos(-R.S), phi = -pi/2."""
     R = np.array([np.sin(qS) * np.cos(phiS), np.sin(qS) * np.sin(phiS), np.cos(qS)])
     S = np.array([np.sin(qK) * np.cos(phiK), np.sin(qK) * np.sin(phiK), np.cos(qK)])
-    theta = np.arccos(np.clip(-np.dot(R, S), -1.0, 1.0))
+    # explicit sum (not np.dot): the batched twin ssb_transform_batch evaluates the same expression, bit for bit --
+    # near theta = pi (the scripts' geometry) arccos turns a 1-ulp difference of R.S into 1.5e-8 rad
+    dot = (R[0] * S[0] + R[1] * S[1]) + R[2] * S[2]
+    theta = np.arccos(np.clip(-dot, -1.0, 1.0))
     return theta, -np.pi / 2.0
 
 
@@ -258,6 +258,21 @@ def polarization_angle(qS, phiS, qK, phiK):
     up = np.cos(qS) * np.sin(qK) * np.cos(phiS - phiK) - np.cos(qK) * np.sin(qS)
     dw = np.sin(qK) * np.sin(phiS - phiK)
     return -np.arctan2(up, dw) if dw != 0.0 else 0.5 * np.pi
+
+
+def ssb_transform_batch(qS, phiS, qK, phiK, detector_frame=True):
+    """Vectorised ``GenerateEMRIWaveform._transform``: arrays [nb] -> (theta, phi, cos2psi, sin2psi) arrays."""
+    qS, phiS, qK, phiK = (np.asarray(a, dtype=np.float64) for a in (qS, phiS, qK, phiK))
+    dot = (((np.sin(qS) * np.cos(phiS)) * (np.sin(qK) * np.cos(phiK)) + (np.sin(qS) * np.sin(phiS)) * (np.sin(qK) * np.sin(phiK)))
+           + np.cos(qS) * np.cos(qK))
+    theta = np.arccos(np.clip(-dot, -1.0, 1.0))
+    phi = np.full_like(theta, -np.pi / 2.0)
+    if not detector_frame:
+        return theta, phi, np.ones_like(theta), np.zeros_like(theta)
+    up = np.cos(qS) * np.sin(qK) * np.cos(phiS - phiK) - np.cos(qK) * np.sin(qS)
+    dw = np.sin(qK) * np.sin(phiS - phiK)
+    psi = np.where(dw != 0.0, -np.arctan2(up, dw), 0.5 * np.pi)
+    return theta, phi, np.cos(2.0 * psi), np.sin(2.0 * psi)
 
 
 class GenerateEMRIWaveform:

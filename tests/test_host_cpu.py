@@ -182,3 +182,34 @@ def test_native_host_producers_match_python_twins():
         assert np.max(np.abs(CubicSpline(tn, pn)(tt) - CubicSpline(tp, pp)(tt))) < 1e-7      # different knots, same orbit
     with pytest.raises(ValueError):
         nat(1e6, 10.0, 0.0, 6.5, 0.3, 1.0)
+
+
+def test_batched_host_helpers_match_scalar_twins(generator):
+    """The vectorised domain checks and SSB transform used by the batched device-producer path make the same decisions /
+    return the same doubles as the per-walker versions the single-waveform call uses."""
+    import warnings
+    from emri_frequencydomainwaveforms_b200.waveform import GenerateEMRIWaveform, ssb_transform_batch
+    g = GenerateEMRIWaveform("FastSchwarzschildEccentricFlux", sum_kwargs=dict(pad_output=True, output_type="fd", odd_len=True))
+    rng = np.random.default_rng(0)
+    A = rng.uniform(0.0, np.pi, (500, 4))
+    A[:3] = np.pi / 3                                   # the scripts' geometry: theta = pi, sin(phiS - phiK) = 0
+    A[3] = [1.0, 2.0, np.pi - 1.0, 2.0 + np.pi]         # R = -S: theta = 0
+    ref = np.array([g._transform(*row) for row in A])
+    got = np.stack(ssb_transform_batch(A[:, 0], A[:, 1], A[:, 2], A[:, 3]), axis=1)
+    assert np.array_equal(ref, got)
+    src = np.stack(ssb_transform_batch(A[:, 0], A[:, 1], A[:, 2], A[:, 3], detector_frame=False), axis=1)
+    assert np.array_equal(src[:, 0], ref[:, 0]) and np.all(src[:, 2] == 1.0) and np.all(src[:, 3] == 0.0)
+    # trajectories: the threaded batch equals the single calls bit for bit
+    from emri_frequencydomainwaveforms_b200 import _hostlib
+    if _hostlib.load() is not None:
+        M, mu = np.array([1e6, 5e5, 2e6]), np.array([10.0, 20.0, 50.0])
+        p0, e0 = np.array([12.0, 10.5, 9.0]), np.array([0.35, 0.6, 0.3])
+        ig = generator.inspiral_generator
+        out1, l1 = _hostlib.trajectory_batch(M, mu, p0, e0, np.zeros(3), np.ones(3), 0.1, ig.rtol, ig.atol, ig.max_init_len, nthreads=1)
+        out4, l4 = _hostlib.trajectory_batch(M, mu, p0, e0, np.zeros(3), np.ones(3), 0.1, ig.rtol, ig.atol, ig.max_init_len, nthreads=4)
+        assert np.array_equal(l1, l4)
+        for a, b in zip(out1, out4):
+            for w in range(3):
+                assert np.array_equal(a[w, :l1[w]], b[w, :l4[w]])
+        t, p, e, x, Pp, Pt, Pr = ig(M[1], mu[1], 0.0, p0[1], e0[1], 1.0, Phi_phi0=0.0, Phi_r0=1.0, T=0.1, dt=10.0)
+        assert np.array_equal(t, out1[0][1, :l1[1]]) and np.array_equal(Pr, out1[4][1, :l1[1]])
