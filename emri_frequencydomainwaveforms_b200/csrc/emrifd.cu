@@ -4,10 +4,14 @@
 //   spline_build_kernel   A3  batched not-a-knot cubic spline (shared tridiagonal factorisation in smem,
 //                             one RHS per thread, coalesced quad stores)
 //   segment_kernel        A4  per-mode monotone-branch segmentation + bit-exact bin ranges
-//   mode_sum_kernel       A5-A7 (+A11 fused) bin-owner stationary-phase sum: one thread owns the (+f,-f)
-//                             bin pair, no atomics, h+/hx split + scale + rotation fused into the store,
-//                             optional fused |d - h|^2 / <d|h> / <h|h> block reduction
+//   empty_tile_kernel     A5-A7 pass 1: tiles no harmonic touches are zero-filled (a store stream at the HBM write rate),
+//                             the others are queued
+//   mode_sum_kernel       A5-A7 (+A11 fused) pass 2, persistent CTAs fed by the tile queue (mode_sum_direct_kernel: plain grid
+//                             for small launches): bin-owner stationary-phase sum, a thread owns 4 or 6 consecutive (+f,-f)
+//                             bin pairs, no atomics, h+/hx split + scale + rotation fused into the store, optional fused
+//                             |d - h|^2 / <d|h> / <h|h> reduction (like_finalize_kernel adds the partials in a fixed order)
 //   inner_product / loglike kernels  A10/A11 on materialised arrays
+//   ylm / synth_amplitude / mode_select / compact_* kernels  the producers right before the path
 //
 // The per-harmonic formula follows the reference's statement of it
 // (Tutorial_FD_construction_single_mode.ipynb:548-623, cell 26); see include/emrifd.h for the
