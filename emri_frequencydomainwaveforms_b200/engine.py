@@ -48,9 +48,6 @@ class PackedBatch:
         return int(self.walkers.nbytes + 5 * self.t.nbytes + self.teuk.nbytes + self.m.nbytes + self.n.nbytes
                    + self.ylm.nbytes)
 
-    def subset(self, idx):
-        raise NotImplementedError
-
 
 class DeviceBatch:
     """Device-resident copy of a PackedBatch plus its work buffers (coeff, branches)."""

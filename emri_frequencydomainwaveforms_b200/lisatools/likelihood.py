@@ -186,8 +186,8 @@ class Likelihood:
                 raise ValueError("Length of all injection channels must match.")
         if len(inj) != self.num_channels:
             raise ValueError("Number of channels from template_model does not match number of channels declare by user.")
-        if add_noise:
-            raise NotImplementedError
+        if add_noise and self.df is not None and not getattr(self, "noise_has_been_added", False):
+            raise NotImplementedError   # as the reference does (likelihood.py:183-184); with f_arr add_noise is ignored there too
         nf = noise_fn if isinstance(noise_fn, list) else [noise_fn] * self.num_channels
         if len(nf) == 1:
             nf = nf * self.num_channels
