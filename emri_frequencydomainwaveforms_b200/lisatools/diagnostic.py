@@ -21,8 +21,6 @@ def inner_product(sig1, sig2, dt=None, df=None, f_arr=None, PSD="lisasens", PSD_
     import torch
     if df is None and dt is None and f_arr is None:
         raise ValueError("Must provide either df, dt or f_arr keyword arguments.")
-    if dt is not None:
-        raise ValueError("Time-domain inputs (dt=) are outside the FD hot path; pass f_arr= or df=.")
     if not isinstance(sig1, list):
         sig1 = [sig1]
     if not isinstance(sig2, list):
@@ -31,12 +29,25 @@ def inner_product(sig1, sig2, dt=None, df=None, f_arr=None, PSD="lisasens", PSD_
         raise ValueError("Signal 1 has {} channels. Signal 2 has {} channels. Must be equal.".format(
             len(sig1), len(sig2)))
     h = _lib.get_handle(device)
+    if dt is not None:
+        # time-domain inputs (diagnostic.py:49-67): zero-pad the shorter signal, rfft * dt (cuFFT), drop the DC bin
+        import warnings
+        ta = [_dev(s, h, torch.float64) for s in sig1]
+        tb = [_dev(s, h, torch.float64) for s in sig2]
+        length = max(ta[0].shape[0], tb[0].shape[0])
+        if ta[0].shape[0] != tb[0].shape[0]:
+            warnings.warn("The two signals are two different lengths in the time domain. Zero padding smaller array.")
+            ta = [torch.nn.functional.pad(s, (0, length - s.shape[0])) for s in ta]
+            tb = [torch.nn.functional.pad(s, (0, length - s.shape[0])) for s in tb]
+        sig1 = [torch.fft.rfft(s)[1:] * dt for s in ta]
+        sig2 = [torch.fft.rfft(s)[1:] * dt for s in tb]
+        f_arr = torch.fft.rfftfreq(length, dt, dtype=torch.float64, device=h.torch_device)[1:]
     a = torch.stack([_dev(s, h, torch.complex128) for s in sig1])
     b = torch.stack([_dev(s, h, torch.complex128) for s in sig2])
     nch, n = a.shape
     if b.shape != a.shape:
         raise ValueError("Length of all channels must match.")
-    if df is not None:
+    if df is not None and dt is None:
         freqs = (torch.arange(n, dtype=torch.float64, device=h.torch_device) + 1) * df   # ignores DC (+1)
     else:
         freqs = _dev(f_arr, h, torch.float64)

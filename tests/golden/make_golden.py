@@ -29,6 +29,33 @@ sys.path.insert(0, os.path.join(ROOT, "tests"))
 REF = "/root/reference"
 
 
+def lisatools_td_golden():
+    """inner_product(..., dt=) branch of the reference (diagnostic.py:49-67): rfft of the time series, DC dropped, zero padding
+    of the shorter signal."""
+    import warnings
+    sys.path.insert(0, os.path.join(REF, "LISAanalysistools"))
+    from lisatools.diagnostic import inner_product, snr
+    from scipy.interpolate import CubicSpline
+    S = np.genfromtxt(os.path.join(REF, "LISA_Alloc_Sh.txt"))
+    Sh_X = CubicSpline(S[:, 0], S[:, 1])
+    rng = np.random.default_rng(77)
+    n, dt = 4096, 10.0
+    t = np.arange(n) * dt
+    x = [np.sin(2 * np.pi * 2e-3 * t + 0.3 * k) * 1e-20 + 1e-21 * rng.normal(size=n) for k in range(2)]
+    y = [x[k] + 2e-21 * rng.normal(size=n) for k in range(2)]
+    y_short = [c[:4000] for c in y]
+    psd = Sh_X(np.fft.rfftfreq(n, dt)[1:])
+    out = dict(x=np.asarray(x), y=np.asarray(y), dt=dt, psd=psd)
+    out["ip_xy"] = inner_product(x, y, dt=dt, PSD=psd)
+    out["ip_xy_norm"] = inner_product(x, y, dt=dt, PSD=psd, normalize=True)
+    out["snr_x"] = snr(x, dt=dt, PSD=psd)
+    with warnings.catch_warnings():
+        warnings.simplefilter("ignore")
+        out["ip_xy_short"] = inner_product(x, y_short, dt=dt, PSD=psd)
+    np.savez(os.path.join(HERE, "lisatools_td_golden.npz"), **out)
+    print("lisatools_td_golden.npz", out["ip_xy"], out["ip_xy_norm"], out["snr_x"], out["ip_xy_short"])
+
+
 def lisatools_golden():
     sys.path.insert(0, os.path.join(REF, "LISAanalysistools"))
     sys.path.insert(0, os.path.join(REF, "Eryn"))
@@ -124,6 +151,7 @@ def waveform_golden():
 
 
 if __name__ == "__main__":
+    lisatools_td_golden()
     lisatools_golden()
     spline_golden()
     k13_golden()

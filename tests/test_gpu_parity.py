@@ -135,6 +135,21 @@ def test_inner_product_matches_lisatools_golden(torch_cuda):
         inner_product(a, b[:1], f_arr=f, PSD=psd)
 
 
+def test_inner_product_time_domain_branch_matches_lisatools_golden(torch_cuda):
+    """inner_product(..., dt=) (diagnostic.py:49-67: rfft * dt, DC dropped, zero padding) against the reference's own output."""
+    import warnings
+    from emri_frequencydomainwaveforms_b200.lisatools.diagnostic import inner_product, snr
+    g = np.load(os.path.join(GOLD, "lisatools_td_golden.npz"))
+    x, y, dt, psd = [g["x"][0], g["x"][1]], [g["y"][0], g["y"][1]], float(g["dt"]), g["psd"]
+    assert np.isclose(inner_product(x, y, dt=dt, PSD=psd), g["ip_xy"], rtol=1e-11)
+    assert np.isclose(inner_product(x, y, dt=dt, PSD=psd, normalize=True), g["ip_xy_norm"], rtol=1e-11)
+    assert np.isclose(snr(x, dt=dt, PSD=psd), g["snr_x"], rtol=1e-11)
+    with warnings.catch_warnings(record=True) as wlist:
+        warnings.simplefilter("always")
+        v = inner_product(x, [c[:4000] for c in y], dt=dt, PSD=psd)
+    assert np.isclose(v, g["ip_xy_short"], rtol=1e-11) and any("Zero padding" in str(w.message) for w in wlist)
+
+
 def test_likelihood_mirror_matches_lisatools_golden(torch_cuda):
     from emri_frequencydomainwaveforms_b200.lisatools.likelihood import Likelihood
     from emri_frequencydomainwaveforms_b200.fdutils import get_sensitivity
