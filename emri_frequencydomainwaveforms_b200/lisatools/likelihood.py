@@ -73,6 +73,12 @@ class FDTemplateModel:
         w = np.ascontiguousarray(np.stack([to_np(c) for c in noise_factor]), dtype=np.float64)
         if d.shape[0] != 2 or w.shape != d.shape:
             raise ValueError("data and noise_factor must be [2, n] (plus, cross).")
+        if np.isnan(w[0, 0]):
+            # the reference skips the DC bin when the PSD is NaN there (start_ind = 1, likelihood.py:268): a zero weight and a
+            # zero datum drop the bin from every sum just the same
+            w, d = w.copy(), d.copy()
+            w[:, 0] = 0.0
+            d[:, 0] = 0.0
         dd = torch.from_numpy(d.view(np.float64)).to(h.torch_device)
         ww = torch.from_numpy(w).to(h.torch_device)
         h.check(h.lib.emrifd_set_data(h.h, dd.data_ptr(), ww.data_ptr(), d.shape[1]))
@@ -210,13 +216,20 @@ class Likelihood:
             self.injection_channels = whitened
         self.freqs, self.psd, self.data_length = freqs, psd, self.injection_length
         h = self.handle
-        self._d_dev = torch.from_numpy(np.ascontiguousarray(self.injection_channels).view(np.float64)).to(h.torch_device)
-        self._w_dev = torch.from_numpy(np.ascontiguousarray(self.noise_factor)).to(h.torch_device)
+        d_up, w_up = np.ascontiguousarray(self.injection_channels), np.ascontiguousarray(self.noise_factor)
+        if np.isnan(w_up[0, 0]):      # PSD undefined at f = 0: the reference starts its sums at bin 1 (likelihood.py:268)
+            d_up, w_up = d_up.copy(), w_up.copy()
+            d_up[:, 0] = 0.0
+            w_up[:, 0] = 0.0
+        self._d_dev = torch.from_numpy(d_up.view(np.float64)).to(h.torch_device)
+        self._w_dev = torch.from_numpy(w_up).to(h.torch_device)
 
     def get_ll(self, params, *args, **kwargs):
         import torch
         if not self.like_here:
             return self._plugin_ll(params, *args, **kwargs)
+        if self.separate_d_h:
+            raise NotImplementedError   # as the reference (likelihood.py:253-254)
         h = self.handle
         if self.vectorized:
             chans = self.template_model(*params, *args, **kwargs)

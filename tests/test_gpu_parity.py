@@ -180,6 +180,31 @@ def _emri_params(n, rng=None):
     return out
 
 
+def test_likelihood_skips_dc_bin_when_psd_is_nan_there(torch_cuda):
+    """likelihood.py:268: start_ind = 1 when noise_factor[0, 0] is NaN (a PSD that is undefined at f = 0)."""
+    from emri_frequencydomainwaveforms_b200.lisatools.likelihood import Likelihood
+    rng = np.random.default_rng(4)
+    n = 513
+    f = np.linspace(0.0, 1e-2, n)
+    data = [rng.normal(size=n) + 1j * rng.normal(size=n) for _ in range(2)]
+    tmpl = [[c * (1.0 + 0.1 * k) for c in data] for k in range(3)]
+
+    def psd_nan(freqs, **kw):
+        out = 1e-2 + np.asarray(freqs) ** 2
+        out = out.copy()
+        out[0] = np.nan
+        return out
+
+    like = Likelihood(lambda k, **kw: tmpl[int(k)], 2, f_arr=f)
+    like.inject_signal(data_stream=data, noise_fn=[psd_nan, psd_nan], noise_kwargs=[{}, {}])
+    ll = like(np.arange(3.0)[:, None])
+    nf = like.noise_factor
+    ref = [-2.0 * np.sum(np.abs((np.asarray(data) - np.asarray(tmpl[k])) * nf)[:, 1:] ** 2) for k in range(3)]
+    assert np.all(np.isfinite(ll)) and np.allclose(ll, ref, rtol=1e-12, atol=1e-18)
+    with pytest.raises(NotImplementedError):
+        Likelihood(lambda k, **kw: tmpl[int(k)], 2, f_arr=f, separate_d_h=True).get_ll(np.arange(3.0)[:, None])
+
+
 def test_generate_emri_waveform_surface(oracle_quad, torch_cuda):
     from emri_frequencydomainwaveforms_b200.waveform import GenerateEMRIWaveform
     kw = dict(T=0.1, dt=20.0, eps=1e-2)
