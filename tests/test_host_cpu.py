@@ -213,3 +213,22 @@ def test_batched_host_helpers_match_scalar_twins(generator):
                 assert np.array_equal(a[w, :l1[w]], b[w, :l4[w]])
         t, p, e, x, Pp, Pt, Pr = ig(M[1], mu[1], 0.0, p0[1], e0[1], 1.0, Phi_phi0=0.0, Phi_r0=1.0, T=0.1, dt=10.0)
         assert np.array_equal(t, out1[0][1, :l1[1]]) and np.array_equal(Pr, out1[4][1, :l1[1]])
+
+
+def test_bench_reference_arm_prints_one_json_line():
+    """Driver contract: `bench.py --impl reference` runs on the host cores alone and prints exactly ONE JSON line on stdout
+    with the keys the driver reads (library chatter is diverted to stderr by bench.StdoutGuard)."""
+    import json
+    import subprocess
+    import sys
+    out = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0"],
+                         capture_output=True, text=True, timeout=600, cwd=ROOT)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["metric"] == "fd_waveform_likelihoods_per_s" and d["unit"] == "walkers/s"
+    assert d["value"] > 0 and d["higher_is_better"] is True and d["steps"] == 1 and d["n_gpus"] == 1
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
+    assert d["e2e"] == {"value": d["value"], "unit": "walkers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in d["config"] and "model" not in d["config"]
