@@ -586,3 +586,25 @@ def test_long_trajectory_paths(generator, oracle_quad, torch_cuda):
                Phi_phi=np.linspace(0, 1e4, 1100), Phi_r=np.linspace(0, 7e3, 1100))
     with pytest.raises(ValueError):
         _gpu_sum(big, torch_cuda)
+
+
+def test_bench_line_contract(torch_cuda):
+    """`python bench.py` prints ONE JSON line with the keys the driver reads (metric, value, e2e, roofline, clocks, gpu_launches)."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3", "--batch", "8", "--distinct", "2",
+                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    lines = [l for l in out.stdout.splitlines() if l.strip()]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling", "vs_baseline", "dtype",
+                "data", "config", "e2e", "gpu_launches", "clocks", "roofline"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["value"] > 0 and d["dtype"] == "f64" and d["gpu_launches"] >= 2 * 5
+    assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["bound"] in ("hbm", "fp64") and 0 < r["frac"] < 1.5 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"]
+    assert d["e2e_from_parameters"]["value"] > 0
