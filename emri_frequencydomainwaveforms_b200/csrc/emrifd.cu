@@ -958,7 +958,8 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
             }
         }
     }
-    __syncthreads();
+    // (no barrier here: the staged tracks are first read in the entry fill, behind the two barriers of the record scan below,
+    //  so the scan's global loads are in flight together with the staging loads)
 
     bool used = false; // the entry cache holds a previous chunk that some warp may still be evaluating
     for (int base = 0, ch = 0; any && base < nrec; base += SUM_THREADS, ch++) {
@@ -984,8 +985,9 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
         const int gcount = count - g0 < SUM_ENT_CAP ? count - g0 : SUM_ENT_CAP;
         if (g0 > 0) __syncthreads(); // every warp is done with the previous group's entries
         if (tid < gcount) { // fill the entry cache (ordered: deterministic summation order)
-            const emrifd_branch_t b = br[s_list[g0 + tid]];
-            const int k = b.mode;
+            const int rec = s_list[g0 + tid];
+            const int k = rec / MAXBR;                    // record r belongs to mode r / MAXBR (== b.mode): no dependent load
+            const emrifd_branch_t b = br[rec];
             const int mi = marr[k], ni = narr[k];
             const double2 yp = ylm[k], ym = ylm[K + k];
             Entry e;
