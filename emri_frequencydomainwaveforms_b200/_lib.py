@@ -35,7 +35,7 @@ SYMBOLS = [
     "emrifd_loglike", "emrifd_loglike_batch_host", "emrifd_bench_fp64_fma", "emrifd_launch_count",
     "emrifd_sum_kernel_time", "emrifd_mode_select", "emrifd_ylm_batch", "emrifd_mode_compact_count",
     "emrifd_mode_compact_gather", "emrifd_tile_bins", "emrifd_batch_sum_cyclic",
-    "emrifd_synth_amplitude"]
+    "emrifd_synth_amplitude", "emrifd_walker_status", "emrifd_set_k13_mode"]
 
 _lib = None
 
@@ -70,6 +70,8 @@ def load():
     lib.emrifd_fd_waveform_batch.argtypes = [vp, vp, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp, i64, dbl, vp, i32,
                                              vp, vp, vp, vp, vp]
     lib.emrifd_batch_status.argtypes = [vp]
+    lib.emrifd_walker_status.argtypes = [vp, i64, vp]
+    lib.emrifd_set_k13_mode.argtypes = [vp, i32]
     lib.emrifd_set_data.argtypes = [vp, vp, vp, i64]
     lib.emrifd_inner_product.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
     lib.emrifd_loglike.argtypes = [vp, vp, i64, vp]
@@ -121,7 +123,23 @@ class Handle:
         raise EmrifdError(f"{name}: {msg}")
 
     def status(self):
+        """Raise ValueError if ANY walker of the last batch failed (the single-waveform behaviour of FEW's sanity checks)."""
         self.check(self.lib.emrifd_batch_status(self.h))
+
+    def walker_status(self, B):
+        """Per-walker status codes of the last batch (0 = ok).  Failed walkers have h = 0 and ll = NaN; the others are
+        unaffected -- the per-walker contract of the reference's samplers (Eryn/eryn/moves/red_blue.py:282-284)."""
+        out = np.zeros(int(B), dtype=np.int32)
+        self.check(self.lib.emrifd_walker_status(self.h, int(B), out.ctypes.data))
+        self.lib.emrifd_batch_status(self.h)   # clear the sticky batch word: the failures have been reported per walker
+        return out
+
+    def set_k13_mode(self, mode):
+        """"exact" (default, <= 3e-15) or "few" (FastEMRIWaveforms' 14-term / 9-term SPAFunc with its seam at |X| = 7)."""
+        codes = {"exact": 0, "few": 1}
+        if mode not in codes:
+            raise ValueError("k13_mode must be 'exact' or 'few'")
+        self.check(self.lib.emrifd_set_k13_mode(self.h, codes[mode]))
 
     def synchronize(self):
         self.check(self.lib.emrifd_synchronize(self.h))

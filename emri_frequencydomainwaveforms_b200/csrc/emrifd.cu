@@ -22,6 +22,7 @@
 #include <string.h>
 #include <stdlib.h>
 #include <math.h>
+#include <limits.h>
 #include <new>
 
 #include "../../include/emrifd.h"
@@ -55,7 +56,7 @@
 #define SUM_TILE (SUM_THREADS * SUM_BPT)
 #define ACC_STRIDE (SUM_THREADS + 4) /* row stride of the smem accumulators: conflict-free own-slot and transposed access */
 #define SEG_THREADS 128
-#define SMEM_PER_KNOT 21 /* doubles: t, 16 track coefficients, 4 reduced knot phases */
+#define SMEM_PER_KNOT 3 /* doubles staged per knot by the mode sum: t, f_phi, f_r */
 
 struct emrifd_handle {
     int device;
@@ -88,6 +89,13 @@ struct emrifd_handle {
     char *h_ws; int64_t h_ws_cap;
     int64_t launches;
     int max_dyn_smem;
+    // per-walker status words, (m, n) group index and combined amplitude quads (workspace of the mode sum)
+    int *d_wstatus; int64_t wstatus_cap;
+    int *d_leader; int64_t leader_cap;
+    int *d_gcount; int64_t gcount_cap;
+    double *d_gq; int64_t gq_cap;
+    int64_t tot_modes, tot_teuk; // packed sizes of the batch validated last (sum K, sum L*K)
+    int k13_few;
     // kernel timing
     int timing;
     cudaEvent_t ev_a[64], ev_b[64];
@@ -290,6 +298,7 @@ __device__ __forceinline__ double grid_f(const Grid &g, long long i) {
 }
 // smallest i in [0,N] with f_i >= F (strict=0) or f_i > F (strict=1)
 __device__ long long grid_lower(const Grid &g, double F, int strict) {
+    if (!(F == F)) return g.N; // NaN track: no bin (keeps the walks below finite)
     double df = g.fpos ? rdiv(g.fpos[g.zero], (double)g.zero) : g.val;
     double e = radd(rdiv(F, df), (double)g.zero);
     long long i;
@@ -308,6 +317,7 @@ struct SegParams {
     const int *m, *n;
     emrifd_branch_t *br;
     long long *n_eval; // [B][2] or NULL
+    int *wstatus;      // [B] per-walker status word (zeroed by the host before the launch)
     Grid g;
 };
 
@@ -338,6 +348,8 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *
     const double *coeff = p.coeff + wd.coeff_off;
     double *st = sm, *sq = sm + L, *sxr = sm + 9 * L, *sFx = sxr + 2 * mpc * L;
     int *snr = reinterpret_cast<int *>(sFx + 2 * mpc * L);
+    __shared__ int s_bad;
+    if (threadIdx.x == 0) s_bad = 0;
     for (int i = threadIdx.x; i < L; i += SEG_THREADS) st[i] = t[i];
     for (int i = threadIdx.x; i < 2 * L; i += SEG_THREADS) {
         const int jj = i >> 1, q = i & 1;
@@ -346,6 +358,20 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *
         d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
     }
     __syncthreads();
+    // knots that are not strictly increasing (or NaN): the spline kernel has refused this walker and its coefficients are
+    // undefined.  The walker gets an empty work-list and its status word; the other walkers of the batch are unaffected.
+    for (int i = threadIdx.x; i < L - 1; i += SEG_THREADS) if (!(st[i + 1] > st[i])) s_bad = 1;
+    __syncthreads();
+    if (s_bad) {
+        if ((int)threadIdx.x < nm) {
+            emrifd_branch_t b;
+            b.mode = k0 + threadIdx.x; b.dir = 0; b.ja = 0; b.jb = 0; b.closed_end = 0; b.pad = 0;
+            b.start = 0; b.end = -1; b.xa = 0; b.xb = 0; b.Fa = 0; b.Fb = 0;
+            for (int q = 0; q < MAXBR; q++) p.br[(wd.mode_off + k0 + threadIdx.x) * MAXBR + q] = b;
+        }
+        if (threadIdx.x == 0) { atomicMin(status, EMRIFD_ERR_KNOT_ORDER); atomicMin(&p.wstatus[blockIdx.y], EMRIFD_ERR_KNOT_ORDER); }
+        return;
+    }
     // ---- phase A ----
     for (int item = threadIdx.x; item < nm * (L - 1); item += SEG_THREADS) {
         const int kl = item / (L - 1), j = item - kl * (L - 1);
@@ -421,7 +447,7 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *
         if (b.end >= b.start) evals += b.end - b.start + 1;
     }
     for (int q = 0; q < MAXBR; q++) out[q] = br[q];
-    if (overflow) atomicMin(status, EMRIFD_ERR_BRANCHES);
+    if (overflow) { atomicMin(status, EMRIFD_ERR_BRANCHES); atomicMin(&p.wstatus[blockIdx.y], EMRIFD_ERR_BRANCHES); }
     if (p.n_eval && evals) {
         atomicAdd((unsigned long long *)&p.n_eval[2 * blockIdx.y], (unsigned long long)evals);
         atomicAdd((unsigned long long *)&p.n_eval[2 * blockIdx.y + 1], (unsigned long long)(evals * (mi > 0 ? 2 : 1)));
@@ -525,6 +551,12 @@ struct SumParams {
     int ntiles;                 // tiles per walker (= ceil(j_cnt / SUM_TILE))
     unsigned long long *queue;  // [B * ntiles] non-empty tiles as (walker << 32 | tile), filled by empty_tile_kernel
     unsigned int *qctl;         // [0] number of queued tiles, [1] next item handed to a persistent mode_sum CTA
+    // (m, n) groups (group_kernel): one stationary point per (group, bin)
+    const int *leader;          // [sum K] walker block at mode_off: first member (mode index) of each group
+    const int *gcount;          // [B] groups per walker
+    const double *gq;           // walker block at 16 * teuk_off: [L][G][16] combined amplitude quads
+    const int *wstatus;         // [B] per-walker status (0 = ok): failed walkers give zeros / a NaN likelihood, the rest of the batch is unaffected
+    int k13_few;                // 1: FastEMRIWaveforms-compatible K_1/3 evaluation (emrifd_set_k13_mode)
 };
 
 
@@ -677,22 +709,204 @@ __device__ __forceinline__ void spa_G2(double fdot, double fddot, double &gre, d
     if (fdot < 0.0) gim = -gim;
 }
 
-// compacted work-list entry cached in shared memory (one per overlapping branch of the current chunk)
-struct __align__(16) Entry {
-    double xa, xb;
-    double ypr, ypi, ymr, ymi;
-    double dm, dn;
-    int spos, epos, sneg, eneg; // tile-local bin ranges covered on the +f / -f side (empty if s > e)
-    int mode, dir, ja, jb;
-    int jlo, jhi, mirror, pad;  // segment range the +f bins of this tile can fall in
+// ==========================================================================================
+// (m, n) groups.  The stationary point t*, the SPA factor and the phase of a harmonic depend on (m, n) only
+// (Tutorial_FD_construction_single_mode.ipynb:558-616, cell 26): modes (l, m, n) that share (m, n) differ in A_lmn(t) Y_lm
+// alone, and the cubic-spline quads are linear in the knot values.  group_kernel finds each walker's distinct (m, n) pairs
+// ("groups", numbered in order of first occurrence) and combines the amplitude quads of a group's members into two complex
+// rows per (knot, group),
+//     Cp = e^{+i 3pi/4} sum_l Y_lm A_lmn,        Cm = e^{-i 3pi/4} sum_l Y_l-m conj(A_lmn),
+// so that mode_sum_kernel solves ONE stationary point per (group, bin) instead of one per (mode, bin): 30 modes -> 27 groups
+// at eps = 1e-2, 3843 -> 671 with all modes.  e^{+-i 3pi/4} is the constant phase of the SPA factor G on rising branches;
+// falling branches add a quarter turn to the phase instead (SubEntry::mu_hi).  The per-mode work-list of segment_kernel stays
+// the exported A4 result; a group uses the records of its first member.
+// ==========================================================================================
+#define GRP_THREADS 256
+#define GRP_TAB 8192 /* cells of the direct (m, n) -> first mode table; larger index ranges take the quadratic fallback */
+struct GroupParams {
+    const emrifd_walker_t *w;
+    const double *coeff;
+    const int *m, *n;
+    const double2 *ylm;
+    int *leader; // [sum K]: walker block at mode_off, its first G entries = mode index of each group's first member
+    int *gcount; // [B] number of groups G
+    double *gq;  // walker block at 16 * teuk_off doubles: [L][G][16] = quads of Re Cp, Im Cp, Re Cm, Im Cm
 };
 
-// ---- evaluation of W (1 or 2) bins of one segment in straight-line code: the W independent dependency chains
-//      (amplitude Horner, SPA factor, phase, sincos) interleave in the instruction stream (ILP without more warps) ----
-__device__ __noinline__ double2 spa_fix(double fdot, double fddot, double s, double u) {
+__global__ void __launch_bounds__(GRP_THREADS) group_kernel(GroupParams p) {
+    extern __shared__ int gsm[]; // tab [GRP_TAB] | grp [K] | mem [K] | lead [K] | off [K + 1]
+    __shared__ int s_mn[4], s_warp[GRP_THREADS / 32], s_base;
+    const emrifd_walker_t wd = p.w[blockIdx.y];
+    const int K = wd.K, L = wd.L, R = 2 * K + 4;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int *marr = p.m + wd.mode_off, *narr = p.n + wd.mode_off;
+    int *tab = gsm, *grp = gsm + GRP_TAB, *mem = grp + K, *lead = mem + K, *off = lead + K;
+    if (tid == 0) { s_mn[0] = INT_MAX; s_mn[1] = INT_MIN; s_mn[2] = INT_MAX; s_mn[3] = INT_MIN; s_base = 0; }
+    __syncthreads();
+    {
+        int mlo = INT_MAX, mhi = INT_MIN, nlo = INT_MAX, nhi = INT_MIN;
+        for (int k = tid; k < K; k += GRP_THREADS) {
+            const int mk = marr[k], nk = narr[k];
+            mlo = min(mlo, mk); mhi = max(mhi, mk); nlo = min(nlo, nk); nhi = max(nhi, nk);
+        }
+        mlo = __reduce_min_sync(0xffffffffu, mlo); mhi = __reduce_max_sync(0xffffffffu, mhi);
+        nlo = __reduce_min_sync(0xffffffffu, nlo); nhi = __reduce_max_sync(0xffffffffu, nhi);
+        if (lane == 0) { atomicMin(&s_mn[0], mlo); atomicMax(&s_mn[1], mhi); atomicMin(&s_mn[2], nlo); atomicMax(&s_mn[3], nhi); }
+    }
+    __syncthreads();
+    const int mmin = s_mn[0], nmin = s_mn[2];
+    const long long mspan = (long long)s_mn[1] - mmin + 1, nspan = (long long)s_mn[3] - nmin + 1;
+    // ---- first member of every mode's group -> mem[k] ----
+    if (mspan * nspan <= GRP_TAB) {
+        const int cells = (int)(mspan * nspan), ns = (int)nspan;
+        for (int i = tid; i < cells; i += GRP_THREADS) tab[i] = INT_MAX;
+        __syncthreads();
+        for (int k = tid; k < K; k += GRP_THREADS) atomicMin(&tab[(marr[k] - mmin) * ns + (narr[k] - nmin)], k);
+        __syncthreads();
+        for (int k = tid; k < K; k += GRP_THREADS) mem[k] = tab[(marr[k] - mmin) * ns + (narr[k] - nmin)];
+    } else {
+        for (int k = tid; k < K; k += GRP_THREADS) {
+            const int mk = marr[k], nk = narr[k];
+            int j = 0;
+            while (j < k && !(marr[j] == mk && narr[j] == nk)) j++;
+            mem[k] = j;
+        }
+    }
+    __syncthreads();
+    // ---- number the groups in order of first occurrence ----
+    for (int k0 = 0; k0 < K; k0 += GRP_THREADS) {
+        const int k = k0 + tid;
+        const bool f = k < K && mem[k] == k;
+        const unsigned bal = __ballot_sync(0xffffffffu, f);
+        if (lane == 0) s_warp[wid] = __popc(bal);
+        __syncthreads();
+        int o = s_base;
+        for (int q = 0; q < wid; q++) o += s_warp[q];
+        if (f) { const int g = o + __popc(bal & ((1u << lane) - 1u)); grp[k] = g; lead[g] = k; }
+        __syncthreads();
+        if (tid == 0) { int t = 0; for (int q = 0; q < GRP_THREADS / 32; q++) t += s_warp[q]; s_base += t; }
+        __syncthreads();
+    }
+    const int G = s_base;
+    for (int k = tid; k < K; k += GRP_THREADS) if (mem[k] != k) grp[k] = grp[mem[k]];
+    for (int g = tid; g <= G; g += GRP_THREADS) off[g] = 0;
+    __syncthreads();
+    // ---- member lists (CSR), ascending mode index inside a group: fixed summation order ----
+    for (int k = tid; k < K; k += GRP_THREADS) atomicAdd(&off[grp[k] + 1], 1);
+    __syncthreads();
+    if (wid == 0) {
+        int carry = 0;
+        for (int g0 = 0; g0 < G; g0 += 32) {
+            const int g = g0 + lane;
+            int v = g < G ? off[g + 1] : 0;
+            for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+            if (g < G) off[g + 1] = carry + v;
+            carry += __shfl_sync(0xffffffffu, v, 31);
+        }
+    }
+    __syncthreads();
+    for (int g = tid; g < G; g += GRP_THREADS) {
+        int o = off[g];
+        const int oe = off[g + 1];
+        for (int k = lead[g]; o < oe; k++) if (grp[k] == g) mem[o++] = k;
+    }
+    __syncthreads();
+    if (blockIdx.x == 0) {
+        for (int g = tid; g < G; g += GRP_THREADS) p.leader[wd.mode_off + g] = lead[g];
+        if (tid == 0) p.gcount[blockIdx.y] = G;
+    }
+    // ---- combined quads of this CTA's knots ----
+    const double2 *ylm = p.ylm + 2 * wd.mode_off;
+    const double *coeff = p.coeff + wd.coeff_off;
+    double *gq = p.gq + 16 * wd.teuk_off;
+    const double r2 = 0.7071067811865476;
+    for (int j = blockIdx.x; j < L; j += gridDim.x) {
+        for (int g = tid; g < G; g += GRP_THREADS) {
+            double pr[4] = {0, 0, 0, 0}, pi[4] = {0, 0, 0, 0}, mr[4] = {0, 0, 0, 0}, mi[4] = {0, 0, 0, 0};
+            for (int i = off[g]; i < off[g + 1]; i++) {
+                const int k = mem[i];
+                const double4 a4 = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + k) * 4);
+                const double4 b4 = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + K + k) * 4);
+                const double2 yp = ylm[k], ym = ylm[K + k];
+                // Y_lm e^{+i 3pi/4} and Y_l-m e^{-i 3pi/4}
+                const double ypr = -r2 * (yp.x + yp.y), ypi = r2 * (yp.x - yp.y);
+                const double ymr = r2 * (ym.y - ym.x), ymi = -r2 * (ym.x + ym.y);
+                const double a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+#pragma unroll
+                for (int c = 0; c < 4; c++) {
+                    pr[c] = fma(ypr, a[c], fma(-ypi, b[c], pr[c])); // Y (a + i b)
+                    pi[c] = fma(ypr, b[c], fma(ypi, a[c], pi[c]));
+                    mr[c] = fma(ymr, a[c], fma(ymi, b[c], mr[c]));  // Y_- (a - i b)
+                    mi[c] = fma(ymi, a[c], fma(-ymr, b[c], mi[c]));
+                }
+            }
+            double4 *o = reinterpret_cast<double4 *>(gq + ((long long)j * G + g) * 16);
+            o[0] = make_double4(pr[0], pr[1], pr[2], pr[3]);
+            o[1] = make_double4(pi[0], pi[1], pi[2], pi[3]);
+            o[2] = make_double4(mr[0], mr[1], mr[2], mr[3]);
+            o[3] = make_double4(mi[0], mi[1], mi[2], mi[3]);
+        }
+    }
+}
+
+// ==========================================================================================
+// mode-sum building blocks
+// ==========================================================================================
+// One monotone cubic piece of one group's f_mn(t) restricted to the current tile: a (branch, side, spline segment) triple with
+// every per-segment constant combined once per tile by the fill warp, so the evaluation loop neither searches segments nor
+// recombines (m, n) with the track quads.
+#define SE_SIDE 1   /* bins are at -f: the direct term lands in the -f accumulators, the mirrored -m term in the +f ones */
+#define SE_MIRROR 2 /* m > 0 and include_minus_m: add the mirrored term */
+#define SE_FALL 4   /* falling branch: G is conjugated (and mu_hi carries the extra quarter turn) */
+struct __align__(16) SubEntry {
+    double c0, c1, c2, c3;  // f_mn(t_j + x) = c0 + c1 x + c2 x^2 + c3 x^3
+    double xlo, xhi;        // slackened root bracket
+    double tol, tj;         // Newton tolerance, knot time
+    double mu_hi, mu_lo;    // (m Phi_phi + n Phi_r)(t_j) / 2pi mod 1 as a double-double; -1/4 on falling branches
+    double p1, p2, p3;      // -(1/2pi) x (m Phi_phi + n Phi_r) cubic remainder, in cycles
+    const double *amp;      // 16 doubles: quads of Re Cp, Im Cp, Re Cm, Im Cm of (segment, group)
+    int s, e;               // tile-local bin range (inclusive)
+    unsigned int fmask;     // 0 / 0x80000000: sign mask applied to the bin frequency
+    int flags;
+};
+// overlapping work-list record of the current fill round (written and read by the fill warp only)
+struct __align__(16) FillEntry {
+    double xa, xb, dm, dn;
+    int ja, jb, dir, g;
+    int s[2], e[2];     // tile-local bin range per side (+f, -f); empty if s > e
+    int jlo[2], jhi[2]; // spline segments those bins fall in
+    int mirror, off;    // off: index of its first sub-entry in the round's list
+    int nsub, pad;
+};
+#ifndef SUM_SUBCAP
+#define SUM_SUBCAP 64 /* sub-entries evaluated per pass */
+#endif
+#define SUM_ECAP 32   /* work-list records per fill round: one per lane of the fill warp */
+
+__device__ __noinline__ double2 spa_fix(double fdot, double fddot, double s, double u, int few) {
     // rare path of the SPA factor: X = 1/u < 1024 (late inspiral, turnover neighbourhood); returns R/sqrt|fdot|.
     // Out of line and returning by value: the hot loop keeps no address-taken locals and no code of this path.
+    // few != 0: FastEMRIWaveforms-compatible evaluation: 9-term asymptotic series for X > 7, 14-term
+    // ascending series below (2.5e-7 off at the seam); default: <= 3e-15 everywhere.
     double re, im;
+    if (few) {
+        if (u < 1.0 / 7.0) {
+            const double w = u * u;
+            double pr = k13_asym_re[4], pi = k13_asym_im[3];
+#pragma unroll
+            for (int k = 3; k >= 0; k--) pr = fma(pr, w, k13_asym_re[k]);
+#pragma unroll
+            for (int k = 2; k >= 0; k--) pi = fma(pi, w, k13_asym_im[k]);
+            re = pr * s; im = u * pi * s;
+        } else {
+            const double af = fabs(fdot);
+            const double X = 2.0943951023931953 * af * af * af / (fddot * fddot);
+            k13_small_S(X, re, im);
+            const double sc = cbrt(1.4472025091165353 / fabs(fddot));
+            re *= sc; im *= sc;
+        }
+        return make_double2(re, im);
+    }
     if (u <= 0.03125) {
         const double w = u * u;
         double pr = k13_asym_re[6], pi = k13_asym_im[6];
@@ -712,86 +926,87 @@ __device__ __noinline__ double2 spa_fix(double fdot, double fddot, double s, dou
     return make_double2(re, im);
 }
 
+// ---- evaluation of W (1 or 2) bins of one sub-entry in straight-line code: the W independent dependency chains
+//      (SPA factor, phase, sincos, amplitude Horner) interleave in the instruction stream (ILP without more warps) ----
 template <int W, int BPT>
-__device__ __forceinline__ void eval_bins(const double (&x)[W], const double (&f)[W], const double c1, const double d2,
-                                          const double d3, const double4 qa, const double4 qb, const double tj,
-                                          const double *__restrict__ q, const double *__restrict__ u4, const double dm,
-                                          const double dn, const Entry &E, double *__restrict__ acc, const int id0,
-                                          const int im0) {
-    double Cr[W], Ci[W], re[W], im[W], s[W], uu[W], fd[W], fdd[W], sn[W], cs[W], ReA[W], ImA[W];
-    const double q9 = q[9], q10 = q[10], q11 = q[11], q13 = q[13], q14 = q[14], q15 = q[15];
-    const double u0 = u4[0], u1 = u4[1], u2 = u4[2], u3 = u4[3];
-    const double mu_hi = fma(dm, u0, dn * u2), mu_lo = fma(dm, u1, dn * u3);
-#pragma unroll
-    for (int i = 0; i < W; i++) {
-        const double xi = x[i], fi = f[i];
-        ReA[i] = fma(xi, fma(xi, fma(xi, qa.w, qa.z), qa.y), qa.x);
-        ImA[i] = fma(xi, fma(xi, fma(xi, qb.w, qb.z), qb.y), qb.x);
-        fd[i] = fma(xi, fma(d3, xi, d2), c1);
-        fdd[i] = fma(2.0 * d3, xi, d2);
-        // SPA factor, common path (X >= 1024): s = 1/sqrt|fdot|, u = 1/X = 3 fddot^2 s^6/(2 pi)
-        s[i] = fast_rsqrt(fabs(fd[i]));
-        const double s2 = s[i] * s[i];
-        uu[i] = 0.477464829275686 * (fdd[i] * fdd[i]) * (s2 * s2 * s2);
-        const double w = uu[i] * uu[i];
-        re[i] = fma(w, fma(w, k13_asym_re[2], k13_asym_re[1]), 1.0) * s[i];
-        im[i] = uu[i] * fma(w, fma(w, k13_asym_im[2], k13_asym_im[1]), k13_asym_im[0]) * s[i];
-        // phase in cycles
-        const double pp = xi * fma(xi, fma(xi, q11, q10), q9);
-        const double pr = xi * fma(xi, fma(xi, q15, q14), q13);
-        double p0 = fi * tj;
-        const double e0 = fma(fi, tj, -p0);
-        p0 -= rint_fast(p0);
-        // |p0 - mu_hi| <~ 20 and |poly| <~ 1e4 cycles: summing them costs <= 1e-12 cycles of rounding, and the
-        // quarter-turn reduction inside sincos_cycles is exact for |c| < 2^20
-        const double poly = fma(fi, xi, -EMRIFD_INV2PI_HI * fma(dm, pp, dn * pr));
-        const double cyc = ((p0 - mu_hi) + (e0 - mu_lo)) + poly;
-        sincos_cycles(cyc, sn[i], cs[i]);
-    }
-#pragma unroll
-    for (int i = 0; i < W; i++)
-        if (!(uu[i] <= 0.0009765625)) { const double2 g = spa_fix(fd[i], fdd[i], s[i], uu[i]); re[i] = g.x; im[i] = g.y; }
-    const double ypr = E.ypr, ypi = E.ypi;
-#if !OPT_SIGN
-    const double sdir = (double)E.dir;
-#endif
-    const bool mirror = E.mirror;
-#pragma unroll
-    for (int i = 0; i < W; i++) {
-        // A * R (conjugated on falling branches); the e^{+-i 3pi/4} of G lives in the entry's harmonics
-#if OPT_SIGN
-        const double gre = re[i], gim = flip_sign(im[i], E.dir < 0 ? 0x80000000u : 0u);
-#else
-        const double gre = re[i], gim = sdir * im[i];
-#endif
-        const double agr = ReA[i] * gre - ImA[i] * gim, agi = ReA[i] * gim + ImA[i] * gre;
-        Cr[i] = agr * cs[i] - agi * sn[i];
-        Ci[i] = agr * sn[i] + agi * cs[i];
-        const int id = id0 + i * ACC_STRIDE;
-        acc[id] = fma(ypr, Cr[i], fma(-ypi, Ci[i], acc[id]));
-        acc[id + BPT * ACC_STRIDE] = fma(ypr, Ci[i], fma(ypi, Cr[i], acc[id + BPT * ACC_STRIDE]));
-    }
-    if (mirror) {
-        const double ymr = E.ymr, ymi = E.ymi;
+__device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)[W], const double c1, const double d2,
+                                         const double d3, const SubEntry &S, const int few, double *__restrict__ acc,
+                                         const int id0, const int im0) {
+    double er[W], ei[W];
+    const int fl = S.flags;
+    {
+        double re[W], im[W], s[W], uu[W], fd[W], fdd[W], sn[W], cs[W];
+        const double tj = S.tj, mu_hi = S.mu_hi, mu_lo = S.mu_lo, p1 = S.p1, p2 = S.p2, p3 = S.p3;
 #pragma unroll
         for (int i = 0; i < W; i++) {
+            const double xi = x[i], fi = f[i];
+            fd[i] = fma(xi, fma(d3, xi, d2), c1);
+            fdd[i] = fma(2.0 * d3, xi, d2);
+            // SPA factor, common path (X >= 1024): s = 1/sqrt|fdot|, u = 1/X = 3 fddot^2 s^6/(2 pi)
+            s[i] = fast_rsqrt(fabs(fd[i]));
+            const double s2 = s[i] * s[i];
+            uu[i] = 0.477464829275686 * (fdd[i] * fdd[i]) * (s2 * s2 * s2);
+            const double w = uu[i] * uu[i];
+            re[i] = fma(w, fma(w, k13_asym_re[2], k13_asym_re[1]), 1.0) * s[i];
+            im[i] = uu[i] * fma(w, fma(w, k13_asym_im[2], k13_asym_im[1]), k13_asym_im[0]) * s[i];
+            // phase in cycles: f t_j as an exact two-product reduced mod 1, the knot phase as a double-double,
+            // only the small polynomial remainder in plain double
+            double p0 = fi * tj;
+            const double e0 = fma(fi, tj, -p0);
+            p0 -= rint_fast(p0);
+            const double poly = fma(fi, xi, xi * fma(xi, fma(xi, p3, p2), p1));
+            const double cyc = ((p0 - mu_hi) + (e0 - mu_lo)) + poly;
+            sincos_cycles(cyc, sn[i], cs[i]);
+        }
+#pragma unroll
+        for (int i = 0; i < W; i++)
+            if (!(uu[i] <= 0.0009765625)) { const double2 g = spa_fix(fd[i], fdd[i], s[i], uu[i], few); re[i] = g.x; im[i] = g.y; }
+        const unsigned int cmask = (fl & SE_FALL) ? 0x80000000u : 0u;
+#pragma unroll
+        for (int i = 0; i < W; i++) { // E = R~ / sqrt|fdot| e^{i phase}  (R conjugated on falling branches)
+            const double gim = flip_sign(im[i], cmask);
+            er[i] = re[i] * cs[i] - gim * sn[i];
+            ei[i] = re[i] * sn[i] + gim * cs[i];
+        }
+    }
+    const double4 *ap = reinterpret_cast<const double4 *>(S.amp);
+    {
+        const double4 qa = ap[0], qb = ap[1];
+#pragma unroll
+        for (int i = 0; i < W; i++) { // W(+-f) += Cp E
+            const double xi = x[i];
+            const double cr = fma(xi, fma(xi, fma(xi, qa.w, qa.z), qa.y), qa.x);
+            const double ci = fma(xi, fma(xi, fma(xi, qb.w, qb.z), qb.y), qb.x);
+            const int id = id0 + i * ACC_STRIDE;
+            acc[id] = fma(cr, er[i], fma(-ci, ei[i], acc[id]));
+            acc[id + BPT * ACC_STRIDE] = fma(cr, ei[i], fma(ci, er[i], acc[id + BPT * ACC_STRIDE]));
+        }
+    }
+    if (fl & SE_MIRROR) {
+        const double4 qc = ap[2], qd = ap[3];
+#pragma unroll
+        for (int i = 0; i < W; i++) { // W(-+f) += Cm conj(E)
+            const double xi = x[i];
+            const double cr = fma(xi, fma(xi, fma(xi, qc.w, qc.z), qc.y), qc.x);
+            const double ci = fma(xi, fma(xi, fma(xi, qd.w, qd.z), qd.y), qd.x);
             const int im_ = im0 + i * ACC_STRIDE;
-            acc[im_] = fma(ymr, Cr[i], fma(ymi, Ci[i], acc[im_]));
-            acc[im_ + BPT * ACC_STRIDE] = fma(ymi, Cr[i], fma(-ymr, Ci[i], acc[im_ + BPT * ACC_STRIDE]));
+            acc[im_] = fma(cr, er[i], fma(ci, ei[i], acc[im_]));
+            acc[im_ + BPT * ACC_STRIDE] = fma(ci, er[i], fma(-cr, ei[i], acc[im_ + BPT * ACC_STRIDE]));
         }
     }
 }
 
-// Hull of the positive-bin indices touched by each chunk of SUM_THREADS work-list records (either through the +f
-// or the -f side): lets mode_sum_kernel skip a whole chunk (no ballot, no barrier pair) when its tile is outside.
+// Hull of the positive-bin indices touched by each chunk of SUM_THREADS group records (either through the +f or the -f side):
+// lets the mode sum skip a whole chunk (no ballot, no barrier pair) when its tile is outside, and empty_tile_kernel classify tiles.
 __global__ void __launch_bounds__(SUM_THREADS) chunk_range_kernel(const emrifd_walker_t *w, const emrifd_branch_t *brs,
-                                                                   long long zero, long long *rng, int cpw) {
+                                                                   const int *leader, const int *gcount, long long zero,
+                                                                   long long *rng, int cpw) {
     __shared__ long long s_lo[SUM_THREADS / 32], s_hi[SUM_THREADS / 32];
     const emrifd_walker_t wd = w[blockIdx.y];
-    const int nrec = wd.K * MAXBR, r = blockIdx.x * SUM_THREADS + threadIdx.x;
+    const int nrec = gcount[blockIdx.y] * MAXBR, r = blockIdx.x * SUM_THREADS + threadIdx.x;
     long long lo = 0x7fffffffffffffffLL, hi = -1;
     if (r < nrec) {
-        const emrifd_branch_t *b = brs + wd.mode_off * MAXBR + r;
+        const emrifd_branch_t *b = brs + (wd.mode_off + leader[wd.mode_off + r / MAXBR]) * MAXBR + (r % MAXBR);
         const long long s0 = b->start, e0 = b->end;
         if (e0 >= s0) {
             if (e0 >= zero) { lo = (s0 > zero ? s0 : zero) - zero; hi = e0 - zero; }
@@ -830,26 +1045,37 @@ __global__ void __launch_bounds__(256) tile_dd_kernel(const double2 *__restrict_
     if (threadIdx.x == 0) { double t = 0; for (int q = 0; q < 8; q++) t += s[q]; out[blockIdx.x] = t; }
 }
 
+// A tile that a bin slice cuts short (a slice end that is neither tile-aligned nor the end of the data) must not take the
+// precomputed whole-tile sum |d~|^2: its bins beyond the slice end belong to another rank.  Such a tile goes through the
+// per-bin path, which stops at the slice end.
+__device__ __forceinline__ bool tile_truncated(const SumParams &p, long long jt0, int tile_bins) {
+    const long long jend = p.j_lo + p.j_cnt;
+    return jt0 + tile_bins > jend && jend != p.n_data;
+}
+
 // Tiles no harmonic touches (most of the band of a non-plunging eps = 1e-2 system): h = 0 is stored and the tile's likelihood
 // term is the precomputed sum |d~|^2.  A kernel of its own because this work is a pure store stream: no shared memory and
 // 8 resident CTAs per SM keep enough stores in flight to approach the HBM write rate, which the two resident CTAs of
 // mode_sum_kernel (register- and smem-limited) cannot.  The walker descriptor and the chunk hulls are fetched together
-// (one memory round trip before the stores).
+// (one memory round trip before the stores).  A walker whose status word is set (bad knots, too many branches) has all its
+// tiles treated as empty: zeros in h, NaN in the likelihood (like_finalize_kernel).
 template <bool WRITE_H, bool LIKE, int BPT>
 __global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p) {
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long *crng = p.chunk_rng + (long long)blockIdx.y * p.cpw * 2;
     const long long c_lo = crng[0], c_hi = crng[1];          // first chunk's hull: independent of the descriptor
     const emrifd_walker_t *wp = p.w + blockIdx.y;
-    const int K = wp->K;
+    const int nrec = p.gcount[blockIdx.y] * MAXBR;
+    const int bad = p.wstatus[blockIdx.y];
     const long long out_off = wp->out_off;
     const long long jt0 = p.j_lo + (p.tile_first + (long long)blockIdx.x * p.tile_stride) * (SUM_THREADS * BPT);
     const long long jend = p.j_lo + p.j_cnt;
     const long long jt1 = (jt0 + (SUM_THREADS * BPT) < jend ? jt0 + (SUM_THREADS * BPT) : jend) - 1;
     bool any = !(c_lo > jt1 || c_hi < jt0);
-    const int nrec = K * MAXBR;
     for (int ch = 1; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
-    if (any || p.no_empty) { // work for mode_sum_kernel's persistent CTAs (processing order does not affect any result)
+    if (bad) any = false;
+    const bool per_bin = LIKE && (p.no_empty || tile_truncated(p, jt0, SUM_THREADS * BPT));
+    if (any || per_bin) { // work for mode_sum_kernel's persistent CTAs (processing order does not affect any result)
         if (tid == 0) p.queue[atomicAdd(&p.qctl[0], 1u)] = ((unsigned long long)blockIdx.y << 32) | blockIdx.x;
         return;
     }
@@ -878,14 +1104,159 @@ __global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p)
     }
 }
 
+// exact frequency of tile-local bin lb from the staged table sF[BPT][SUM_THREADS] (thread lb / BPT owns bin lb)
+template <int BPT>
+__device__ __forceinline__ double tile_binf(const double *sF, int lb) { return sF[(lb % BPT) * SUM_THREADS + lb / BPT]; }
+
+// knot frequency of a group exactly as segment_kernel rounds it
+__device__ __forceinline__ double knot_F(const double *sK, int j, double dm, double dn) {
+    return radd(rmul(dm, sK[3 * j + 1]), rmul(dn, sK[3 * j + 2]));
+}
+
+// Fill warp, step 1: lane i < gcount turns overlapping record s_list[i] into a FillEntry (tile-local bin ranges and the spline
+// segments they fall in, per side) and the warp numbers the sub-entries of the round (exclusive scan).  Returns their total.
+template <int BPT>
+__device__ __noinline__ int fill_entries(const int *leader, const emrifd_branch_t *br, const int *marr, const int *narr,
+                                         int include_minus_m, long long zero, const int *s_list, int gcount, long long jt0,
+                                         long long jt1, const double *sF, const double *sK, FillEntry *ent) {
+    // (leader, br, marr, narr: this walker's blocks.  Scalars by value: a reference to the kernel parameters would force a
+    //  local-memory copy of them)
+    const int lane = threadIdx.x & 31;
+    int nsub = 0;
+    if (lane < gcount) {
+        const int rg = s_list[lane], g = rg / MAXBR;
+        const int k = leader[g];
+        const emrifd_branch_t b = br[k * MAXBR + rg % MAXBR];
+        const int mi = marr[k], ni = narr[k];
+        FillEntry e;
+        e.xa = b.xa; e.xb = b.xb; e.dm = (double)mi; e.dn = (double)ni;
+        e.ja = b.ja; e.jb = b.jb; e.dir = b.dir; e.g = g;
+        e.mirror = (mi > 0) && include_minus_m; e.pad = 0;
+        // tile-local covered ranges: +f bins have full-grid index zero + jt0 + lb, -f bins zero - jt0 - lb
+        const long long ntile = jt1 - jt0 + 1;
+        long long lo = b.start - (zero + jt0), hi = b.end - (zero + jt0);
+        e.s[0] = (int)(lo < 0 ? 0 : (lo > ntile ? ntile : lo));
+        e.e[0] = (int)(hi > ntile - 1 ? ntile - 1 : (hi < -1 ? -1 : hi));
+        lo = (zero - jt0) - b.end; hi = (zero - jt0) - b.start;
+        e.s[1] = (int)(lo < 0 ? 0 : (lo > ntile ? ntile : lo));
+        if (jt0 == 0 && e.s[1] == 0) e.s[1] = 1; // f = 0 is handled on the + side
+        e.e[1] = (int)(hi > ntile - 1 ? ntile - 1 : (hi < -1 ? -1 : hi));
+#pragma unroll
+        for (int sd = 0; sd < 2; sd++) {
+            e.jlo[sd] = 1; e.jhi[sd] = 0;
+            if (e.s[sd] > e.e[sd]) continue;
+            int jj2[2];
+#pragma unroll
+            for (int w = 0; w < 2; w++) { // segment of the side's first / last bin: largest j whose knot frequency is not beyond f
+                const double fb = tile_binf<BPT>(sF, w == 0 ? e.s[sd] : e.e[sd]);
+                const double f = sd == 0 ? fb : -fb;
+                int l2 = b.ja, h2 = b.jb;
+                while (l2 < h2) {
+                    const int mid = (l2 + h2 + 1) >> 1;
+                    const double Fk = knot_F(sK, mid, e.dm, e.dn);
+                    if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) l2 = mid; else h2 = mid - 1;
+                }
+                jj2[w] = l2;
+            }
+            e.jlo[sd] = jj2[0] < jj2[1] ? jj2[0] : jj2[1];
+            e.jhi[sd] = jj2[0] < jj2[1] ? jj2[1] : jj2[0];
+            nsub += e.jhi[sd] - e.jlo[sd] + 1;
+        }
+        e.nsub = nsub;
+        e.off = 0;
+        ent[lane] = e;
+    }
+    int incl = nsub;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane < gcount) ent[lane].off = incl - nsub;
+    return __shfl_sync(0xffffffffu, incl, 31);
+}
+
+// Fill warp, step 2: lane i < gcount writes those of its sub-entries whose index lies in [w0, w0 + SUM_SUBCAP).
+template <int BPT>
+__device__ __noinline__ void fill_subs(const double *coeff, const double *gq, int K, int G, int gcount, int w0, const double *sF,
+                                       const double *sK, const FillEntry *ent, SubEntry *sub) {
+    // (coeff, gq: this walker's blocks)
+    const int lane = threadIdx.x & 31;
+    if (lane >= gcount) return;
+    const FillEntry e = ent[lane];
+    if (e.nsub == 0 || e.off >= w0 + SUM_SUBCAP || e.off + e.nsub <= w0) return;
+    const int R = 2 * K + 4;
+    int idx = e.off;
+    for (int sd = 0; sd < 2; sd++) {
+        const bool fwd = (e.dir > 0) == (sd == 0); // bin index and segment index grow together
+        const double sg = sd == 0 ? 1.0 : -1.0;
+        for (int j = e.jlo[sd]; j <= e.jhi[sd]; j++, idx++) {
+            if (idx < w0 || idx >= w0 + SUM_SUBCAP) continue;
+            SubEntry S;
+            // ---- bins of this side that fall on segment j: P(lb, jj) = "bin lb lies on a segment >= jj" is monotone in lb ----
+            int bnd[2]; // first bin with P(., j) [fwd] / first bin without P(., j + 1) [!fwd]; then the bin after the last one
+#pragma unroll
+            for (int w = 0; w < 2; w++) {
+                const int jj = fwd ? j + w : j + 1 - w;
+                const bool edge = fwd ? (w == 0 ? j == e.jlo[sd] : j == e.jhi[sd]) : (w == 0 ? j == e.jhi[sd] : j == e.jlo[sd]);
+                if (edge) { bnd[w] = w == 0 ? e.s[sd] : e.e[sd] + 1; continue; }
+                const double Fk = knot_F(sK, jj, e.dm, e.dn);
+                int lo = e.s[sd], hi = e.e[sd] + 1; // first lb in [lo, hi] where P flips
+                while (lo < hi) {
+                    const int mid = (lo + hi) >> 1;
+                    const double f = sg * tile_binf<BPT>(sF, mid);
+                    const bool P = e.dir > 0 ? (Fk <= f) : (Fk >= f);
+                    if (P == fwd) hi = mid; else lo = mid + 1;
+                }
+                bnd[w] = lo;
+            }
+            S.s = bnd[0]; S.e = bnd[1] - 1;
+            // ---- per-segment constants ----
+            const double4 qf = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K) * 4);     // f_phi quad
+            const double4 qr = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 1) * 4); // f_r
+            const double4 qP = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 2) * 4); // Phi_phi
+            const double4 qR = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 3) * 4); // Phi_r
+            const double dm = e.dm, dn = e.dn;
+            const double tj = sK[3 * j], hj = sK[3 * (j + 1)] - tj;
+            S.c0 = radd(rmul(dm, qf.x), rmul(dn, qr.x));
+            S.c1 = fma(dm, qf.y, dn * qr.y);
+            S.c2 = fma(dm, qf.z, dn * qr.z);
+            S.c3 = fma(dm, qf.w, dn * qr.w);
+            const double xl0 = (j == e.ja) ? e.xa : 0.0, xh0 = (j == e.jb) ? e.xb : hj;
+            S.xlo = xl0 - 1e-5 * hj; S.xhi = xh0 + 1e-5 * hj;
+            S.tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
+            S.tj = tj;
+            double u[4]; // Phi/(2 pi) mod 1 as double-doubles (hi, lo) for Phi_phi, Phi_r
+#pragma unroll
+            for (int q = 0; q < 2; q++) {
+                const double ph = q == 0 ? qP.x : qR.x;
+                double a = ph * EMRIFD_INV2PI_HI;
+                double er = fma(ph, EMRIFD_INV2PI_HI, -a);
+                a -= rint(a);
+                er = fma(ph, EMRIFD_INV2PI_LO, er);
+                const double hi2 = a + er;
+                u[2 * q] = hi2; u[2 * q + 1] = er - (hi2 - a);
+            }
+            S.mu_hi = fma(dm, u[0], dn * u[2]) - (e.dir < 0 ? 0.25 : 0.0);
+            S.mu_lo = fma(dm, u[1], dn * u[3]);
+            S.p1 = -EMRIFD_INV2PI_HI * fma(dm, qP.y, dn * qR.y);
+            S.p2 = -EMRIFD_INV2PI_HI * fma(dm, qP.z, dn * qR.z);
+            S.p3 = -EMRIFD_INV2PI_HI * fma(dm, qP.w, dn * qR.w);
+            S.amp = gq + ((long long)j * G + e.g) * 16;
+            S.fmask = sd == 0 ? 0u : 0x80000000u;
+            S.flags = (sd ? SE_SIDE : 0) | (e.mirror ? SE_MIRROR : 0) | (e.dir < 0 ? SE_FALL : 0);
+            sub[idx - w0] = S;
+        }
+    }
+}
+
 template <bool WRITE_H, bool LIKE, int BPT>
 __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile_x, const int walker_y, unsigned char *smraw,
                                               int &staged_walker) {
     __shared__ int s_list[SUM_THREADS];
     __shared__ int s_wcount[SUM_THREADS / 32];
+    __shared__ int s_nsub;
 
     const emrifd_walker_t wd = p.w[walker_y];
-    const int L = wd.L, K = wd.K, R = 2 * K + 4;
+    const int L = wd.L;
+    const int G = p.gcount[walker_y];
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * (SUM_THREADS * BPT);
     const long long jend = p.j_lo + p.j_cnt;                                   // exclusive
@@ -897,82 +1268,62 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     const long long pos_lo = zero + jt0, pos_hi = zero + jt1;
     const long long neg_lo = zero - jt1, neg_hi = zero - jt0;
 
-    const double *coeff = p.coeff + wd.coeff_off;
     const emrifd_branch_t *br = p.br + wd.mode_off * MAXBR;
-    const int *marr = p.m + wd.mode_off, *narr = p.n + wd.mode_off;
-    const double2 *ylm = p.ylm + 2 * wd.mode_off;
+    const int *leader = p.leader + wd.mode_off;
+    const double *coeff = p.coeff + wd.coeff_off;
+    const double *gq = p.gq + 16 * wd.teuk_off;
 
-    // dynamic smem: accumulators [4][BPT][SUM_THREADS] | entry cache | T[L] | Q[L][16] | U[L][4]
+    // dynamic smem: accumulators [4][BPT][ACC_STRIDE] | sub-entries | fill entries | sF | sX | knots (t, f_phi, f_r)[L]
     double *acc = reinterpret_cast<double *>(smraw);
-    Entry *ent = reinterpret_cast<Entry *>(acc + 4 * BPT * ACC_STRIDE);
-    double *sF = reinterpret_cast<double *>(ent + SUM_ENT_CAP); // exact bin frequencies        [BPT][SUM_THREADS]
-    double *sX = sF + SUM_SF * BPT * SUM_THREADS;           // roots of the current entry  [BPT][SUM_THREADS]
-    double *sT = sX + BPT * SUM_THREADS;
-    unsigned short *sJ = reinterpret_cast<unsigned short *>(sT + SMEM_PER_KNOT * L); // segment indices [BPT][SUM_THREADS]
-    double *sQ = sT + L, *sU = sT + 17 * L;
-#define ACC(c, b) acc[((c) * BPT + (b)) * ACC_STRIDE + tid]
+    SubEntry *sub = reinterpret_cast<SubEntry *>(acc + 4 * BPT * ACC_STRIDE);
+    FillEntry *ent = reinterpret_cast<FillEntry *>(sub + SUM_SUBCAP);
+    double *sF = reinterpret_cast<double *>(ent + SUM_ECAP); // exact bin frequencies             [BPT][SUM_THREADS]
+    double *sX = sF + BPT * SUM_THREADS;                     // roots of the current sub-entry   [BPT][SUM_THREADS]
+    double *sK = sX + BPT * SUM_THREADS;
     // ---- does any work-list chunk touch this tile? ----
-    const int nrec = K * MAXBR;
+    const int nrec = G * MAXBR;
     const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
     bool any = false;
     for (int ch = 0; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
-    if (!any && (!LIKE || p.tile_dd)) return; // (direct-grid launches only: empty_tile_kernel has dealt with this tile)
+    if (p.wstatus[walker_y]) any = false; // failed walker: zeros (and a NaN likelihood from like_finalize_kernel)
+    // (direct-grid launches only: empty_tile_kernel has dealt with this tile)
+    if (!any && !(LIKE && (p.no_empty || tile_truncated(p, jt0, SUM_THREADS * BPT)))) return;
 #pragma unroll
     for (int i = 0; i < 4 * BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
-#if SUM_SF
 #pragma unroll
     for (int b = 0; b < BPT; b++) {
         const long long jj = j0 + b;
         sF[b * SUM_THREADS + tid] = (b < nb) ? (p.g.fpos ? p.g.fpos[jj] : rmul((double)(int)jj, p.g.val)) : 0.0;
     }
-#define BINF(pF_, b_) ((pF_)[0])
-#define BINF2(pF_, b_) ((pF_)[SUM_THREADS])
-#else
-#define BINF(pF_, b_) (p.g.fpos ? p.g.fpos[j0 + (b_)] : rmul((double)(int)(j0 + (b_)), p.g.val))
-#define BINF2(pF_, b_) BINF(pF_, (b_) + 1)
-#endif
 
-    const double val = p.g.val;
-    const double *fpos = p.g.fpos;
-
-    // ---- if some chunk touches the tile stage the shared tracks right away (knots, the four track quads, reduced
-    //      knot phases) so that the loads overlap the first record scan ----
-    if (any && staged_walker != walker_y) { // (a persistent CTA often gets consecutive tiles of one walker: tracks stay staged)
+    // ---- if some chunk touches the tile stage the walker's knots (time, f_phi, f_r) right away so that the loads overlap
+    //      the first record scan ----
+    if (any && staged_walker != walker_y) { // (a persistent CTA often gets consecutive tiles of one walker: knots stay staged)
         staged_walker = walker_y;
         const double *t = p.t + wd.knot_off;
-        for (int i = tid; i < L; i += SUM_THREADS) sT[i] = t[i];
-        for (int i = tid; i < L * 4; i += SUM_THREADS) {
-            const int jj = i >> 2, q = i & 3;
-            const double4 c = *reinterpret_cast<const double4 *>(coeff + ((long long)jj * R + 2 * K + q) * 4);
-            double *d = sQ + jj * 16 + q * 4;
-            d[0] = c.x; d[1] = c.y; d[2] = c.z; d[3] = c.w;
-            if (q >= 2) { // Phi/(2 pi) mod 1 as a double-double (hi, lo)
-                const double ph = c.x;
-                double a = ph * EMRIFD_INV2PI_HI;
-                double e = fma(ph, EMRIFD_INV2PI_HI, -a);
-                a -= rint(a);
-                e = fma(ph, EMRIFD_INV2PI_LO, e);
-                const double hi = a + e;
-                sU[jj * 4 + (q - 2) * 2 + 0] = hi;
-                sU[jj * 4 + (q - 2) * 2 + 1] = e - (hi - a);
-            }
+        const int R = 2 * wd.K + 4;
+        for (int i = tid; i < L; i += SUM_THREADS) {
+            sK[3 * i] = t[i];
+            sK[3 * i + 1] = coeff[((long long)i * R + 2 * wd.K) * 4];
+            sK[3 * i + 2] = coeff[((long long)i * R + 2 * wd.K + 1) * 4];
         }
     }
-    // (no barrier here: the staged tracks are first read in the entry fill, behind the two barriers of the record scan below,
-    //  so the scan's global loads are in flight together with the staging loads)
+    // (no barrier here: the staged knots and bin frequencies are first read by the fill warp, behind the two barriers of the
+    //  record scan below, so the scan's global loads are in flight together with the staging loads)
 
-    bool used = false; // the entry cache holds a previous chunk that some warp may still be evaluating
+    bool used = false; // the sub-entry cache holds a previous round that some warp may still be evaluating
     for (int base = 0, ch = 0; any && base < nrec; base += SUM_THREADS, ch++) {
         if (crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0) continue; // block-uniform: nothing of this chunk touches the tile
-        // ---- ordered compaction of this chunk's records that overlap the tile ----
+        // ---- ordered compaction of this chunk's group records that overlap the tile ----
         const int r = base + tid;
         bool pred = false;
         if (r < nrec) {
-            const long long s0 = br[r].start, e0 = br[r].end;
+            const emrifd_branch_t *b = br + leader[r / MAXBR] * MAXBR + (r % MAXBR);
+            const long long s0 = b->start, e0 = b->end;
             pred = (e0 >= s0) && ((s0 <= pos_hi && e0 >= pos_lo) || (s0 <= neg_hi && e0 >= neg_lo));
         }
         const unsigned bal = __ballot_sync(0xffffffffu, pred);
-        if (used) __syncthreads(); // every warp is done with the previous chunk's entries (and with s_wcount / s_list)
+        if (used) __syncthreads(); // every warp is done with the previous chunk's sub-entries (and with s_wcount / s_list)
         if (lane == 0) s_wcount[wid] = __popc(bal);
         __syncthreads();
         int off = 0, count = 0;
@@ -980,231 +1331,105 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
         for (int q = 0; q < SUM_THREADS / 32; q++) { const int c = s_wcount[q]; if (q < wid) off += c; count += c; }
         if (pred) s_list[off + __popc(bal & ((1u << lane) - 1))] = r;
         __syncthreads();
-        if (count == 0) continue; // block-uniform
-        for (int g0 = 0; g0 < count; g0 += SUM_ENT_CAP) { // the overlap list is evaluated in groups of SUM_ENT_CAP entries
-        const int gcount = count - g0 < SUM_ENT_CAP ? count - g0 : SUM_ENT_CAP;
-        if (g0 > 0) __syncthreads(); // every warp is done with the previous group's entries
-        if (tid < gcount) { // fill the entry cache (ordered: deterministic summation order)
-            const int rec = s_list[g0 + tid];
-            const int k = rec / MAXBR;                    // record r belongs to mode r / MAXBR (== b.mode): no dependent load
-            const emrifd_branch_t b = br[rec];
-            const int mi = marr[k], ni = narr[k];
-            const double2 yp = ylm[k], ym = ylm[K + k];
-            Entry e;
-            e.xa = b.xa; e.xb = b.xb;
-            e.mode = b.mode; e.dir = b.dir; e.ja = b.ja; e.jb = b.jb;
-            e.dm = (double)mi; e.dn = (double)ni;
-            e.mirror = (mi > 0) && p.include_minus_m; e.pad = 0;
-            // G = e^{i 3pi/4} R/sqrt|fdot| on rising branches and its conjugate on falling ones (sign fdot == dir on a
-            // monotone branch): fold the constant rotation into Y_lm (direct term) and its conjugate into Y_l-m (mirrored term)
-            {
-                const double r2 = 0.7071067811865476, rr_ = -r2, ri_ = b.dir > 0 ? r2 : -r2;
-                e.ypr = yp.x * rr_ - yp.y * ri_; e.ypi = yp.x * ri_ + yp.y * rr_;
-                e.ymr = ym.x * rr_ + ym.y * ri_; e.ymi = ym.y * rr_ - ym.x * ri_;
+        used = false;
+        for (int g0 = 0; g0 < count; g0 += SUM_ECAP) { // the overlap list is handled in rounds of one record per fill-warp lane
+            const int gcount = count - g0 < SUM_ECAP ? count - g0 : SUM_ECAP;
+            if (used) __syncthreads(); // every warp is done with the previous round's sub-entries
+            if (wid == 0) {
+                const int tot = fill_entries<BPT>(leader, br, p.m + wd.mode_off, p.n + wd.mode_off, p.include_minus_m, zero, s_list + g0,
+                                                  gcount, jt0, jt1, sF, sK, ent);
+                if (lane == 0) s_nsub = tot;
+                __syncwarp();
+                fill_subs<BPT>(coeff, gq, wd.K, G, gcount, 0, sF, sK, ent, sub);
             }
-            // tile-local covered ranges: +f bins have full-grid index zero + jt0 + lb, -f bins zero - jt0 - lb
-            const long long ntile = jt1 - jt0 + 1;
-            long long lo = b.start - pos_lo, hi = b.end - pos_lo;
-            e.spos = (int)(lo < 0 ? 0 : (lo > ntile ? ntile : lo));
-            e.epos = (int)(hi > ntile - 1 ? ntile - 1 : (hi < -1 ? -1 : hi));
-            lo = neg_hi - b.end; hi = neg_hi - b.start;
-            e.sneg = (int)(lo < 0 ? 0 : (lo > ntile ? ntile : lo));
-            if (jt0 == 0 && e.sneg == 0) e.sneg = 1; // f = 0 is handled on the + side
-            e.eneg = (int)(hi > ntile - 1 ? ntile - 1 : (hi < -1 ? -1 : hi));
-            // segment hints for the + side: one binary search per tile edge here instead of one per thread
-            e.jlo = b.ja; e.jhi = b.jb;
-            if (e.spos <= e.epos) {
-                int jj2[2];
-#pragma unroll
-                for (int w = 0; w < 2; w++) {
-                    const long long jb_ = jt0 + (w == 0 ? e.spos : e.epos);
-                    const double f = fpos ? fpos[jb_] : rmul((double)(int)jb_, val);
-                    int l2 = b.ja, h2 = b.jb;
-                    while (l2 < h2) {
-                        const int mid = (l2 + h2 + 1) >> 1;
-                        const double Fk = radd(rmul(e.dm, sQ[mid * 16]), rmul(e.dn, sQ[mid * 16 + 4]));
-                        if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) l2 = mid; else h2 = mid - 1;
-                    }
-                    jj2[w] = l2;
+            __syncthreads();
+            used = true;
+            const int tot = s_nsub;
+            for (int w0 = 0; w0 < tot; w0 += SUM_SUBCAP) {
+                if (w0 > 0) {
+                    __syncthreads();
+                    if (wid == 0) fill_subs<BPT>(coeff, gq, wd.K, G, gcount, w0, sF, sK, ent, sub);
+                    __syncthreads();
                 }
-                e.jlo = jj2[0] < jj2[1] ? jj2[0] : jj2[1];
-                e.jhi = jj2[0] < jj2[1] ? jj2[1] : jj2[0];
-            }
-            ent[tid] = e;
-        }
-        __syncthreads();
-        used = true;
-
-        // ---- evaluate: every thread walks its BPT consecutive bins along each listed branch ----
-        if (nb > 0) {
-            const int tb0 = tid * BPT;
-            for (int li = 0; li < gcount; li++) {
-                const Entry &E = ent[li];
-#pragma unroll 1
-                for (int side = 0; side < 2; side++) {
-                    const int s_ = side == 0 ? E.spos : E.sneg, e_ = side == 0 ? E.epos : E.eneg;
+                const int nsw = tot - w0 < SUM_SUBCAP ? tot - w0 : SUM_SUBCAP;
+                if (nb <= 0) continue;
+                // ---- evaluate: every thread walks its BPT consecutive bins along each listed cubic piece ----
+                const int tb0 = tid * BPT;
+                for (int si = 0; si < nsw; si++) {
+                    const SubEntry &S = sub[si];
+                    const int s_ = S.s, e_ = S.e;
                     const int bl = s_ - tb0 > 0 ? s_ - tb0 : 0;
                     const int bh = e_ - tb0 < nb - 1 ? e_ - tb0 : nb - 1;
                     if (bl > bh) continue;
-                    const double sgn = side == 0 ? 1.0 : -1.0;
-                    const unsigned int smask = side == 0 ? 0u : 0x80000000u;
-                    const int k = E.mode, dir = E.dir, ja = E.ja, jb = E.jb;
-                    const double dm = E.dm, dn = E.dn, sdir = (double)dir;
-                    const double *cmode = coeff + (long long)k * 4; // quads of Re A_k at knot 0; Im A_k is K*4 doubles further
-                    const int offd = side * 2 * BPT * ACC_STRIDE + tid;       // direct term -> this side
-                    const int offm = (1 - side) * 2 * BPT * ACC_STRIDE + tid; // mirrored -m term -> other side
-                    // ---- stage 1: segment + root for each of this thread's bins.  Hot path = straight-line:
-                    //      second-order extrapolation from the previous bin + ONE Newton step; everything else
-                    //      (first bin, segment change, slow convergence) goes through the out-of-line slow path ----
+                    const unsigned int smask = S.fmask;
+                    const int fl = S.flags;
+                    const double c0 = S.c0, c1 = S.c1, c2 = S.c2, c3 = S.c3;
+                    const double d2 = 2.0 * c2, d3 = 3.0 * c3;
+                    // ---- stage 1: roots.  First bin through the out-of-line cold solve; the others by second-order extrapolation
+                    //      from a solved bin + ONE Newton step, two at a time (independent chains); a bin that misses the tolerance
+                    //      or the bracket goes through the cold solve ----
                     {
-                        int j = -1;
-                        double segA, segB;            // frequency at the time-start / time-end of the current sub-interval
-                        double c0, c1, c2, c3, d2, d3; // f_mn cubic on the segment, d2 = 2 c2, d3 = 3 c3
-                        double xlo_s, xhi_s, tol;      // slackened bracket and Newton tolerance
-                        double xprev = 0.0, fprev = 0.0, rprev = 0.0;
+                        const double xlo = S.xlo, xhi = S.xhi, tol = S.tol;
+                        const double sdir = (fl & SE_FALL) ? -1.0 : 1.0;
                         const double *pF = sF + tid + bl * SUM_THREADS;
                         double *pX = sX + tid + bl * SUM_THREADS;
-                        unsigned short *pJ = sJ + tid + bl * SUM_THREADS;
-                        for (int b = bl; b <= bh; b++, pF += SUM_THREADS, pX += SUM_THREADS, pJ += SUM_THREADS) {
-#if OPT_SIGN
-                            const double f = flip_sign(BINF(pF, b), smask);
-#else
-                            const double f = sgn * BINF(pF, b);
-#endif
-                            const bool inside = (j >= 0) && (dir > 0 ? (f >= segA && f < segB) : (f <= segA && f > segB));
-                            double x, rr;
-                            bool ok = false;
-                            if (inside) {
-                                const double delta = f - c0;
-                                const double dxl = (f - fprev) * rprev;                 // first-order step
-                                const double curv = fma(2.0 * d3, xprev, d2) * rprev;  // fddot/fdot at the previous root
-                                x = fma(dxl, fma(-0.5 * curv, dxl, 1.0), xprev);        // second-order extrapolation
-                                const double gx = x * fma(x, fma(x, c3, c2), c1) - delta;
-                                rr = fast_rcp(fma(x, fma(d3, x, d2), c1));
-                                const double dx = gx * rr;
-                                x -= dx;
-                                ok = (fabs(dx) <= tol) && (x >= xlo_s) && (x <= xhi_s);
+                        double fb = flip_sign(pF[0], smask);
+                        double xb = solve_slow(c1, c2, c3, fb - c0, xlo, xhi, tol, sdir);
+                        double rb = fast_rcp(fma(xb, fma(d3, xb, d2), c1));
+                        pX[0] = xb;
+                        for (int b = bl + 1; b <= bh; b += 2) {
+                            pF += SUM_THREADS; pX += SUM_THREADS;
+                            const bool two = b < bh;
+                            const double f1 = flip_sign(pF[0], smask);
+                            const double f2 = two ? flip_sign(pF[SUM_THREADS], smask) : f1;
+                            const double kap = fma(2.0 * d3, xb, d2) * rb; // fddot/fdot at the solved bin
+                            const double dl1 = (f1 - fb) * rb, dl2 = (f2 - fb) * rb;
+                            double x1 = fma(dl1, fma(-0.5 * kap, dl1, 1.0), xb), x2 = fma(dl2, fma(-0.5 * kap, dl2, 1.0), xb);
+                            const double g1 = x1 * fma(x1, fma(x1, c3, c2), c1) - (f1 - c0);
+                            const double g2 = x2 * fma(x2, fma(x2, c3, c2), c1) - (f2 - c0);
+                            double r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1)), r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
+                            const double dx1 = g1 * r1, dx2 = g2 * r2;
+                            x1 -= dx1; x2 -= dx2;
+                            if (!(fabs(dx1) <= tol && x1 >= xlo && x1 <= xhi)) {
+                                x1 = solve_slow(c1, c2, c3, f1 - c0, xlo, xhi, tol, sdir);
+                                r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1));
                             }
-                            if (!ok) {
-                                if (!inside) {
-                                    int lo = side == 0 ? E.jlo : ja, hi = side == 0 ? E.jhi : jb;
-                                    if (j >= 0) { // walk from the previous segment
-                                        lo = j;
-                                        if (dir * sgn > 0) { while (lo < jb) { const double Fk = radd(rmul(dm, sQ[(lo + 1) * 16]), rmul(dn, sQ[(lo + 1) * 16 + 4])); if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo++; else break; } }
-                                        else { while (lo > ja) { const double Fk = radd(rmul(dm, sQ[lo * 16]), rmul(dn, sQ[lo * 16 + 4])); if (dir > 0 ? (Fk > f) : (Fk < f)) lo--; else break; } }
-                                    } else {
-                                        while (lo < hi) {
-                                            const int mid = (lo + hi + 1) >> 1;
-                                            const double Fk = radd(rmul(dm, sQ[mid * 16]), rmul(dn, sQ[mid * 16 + 4]));
-                                            if (dir > 0 ? (Fk <= f) : (Fk >= f)) lo = mid; else hi = mid - 1;
-                                        }
-                                    }
-                                    j = lo;
-                                    const double *q = sQ + j * 16;
-                                    const double hj = sT[j + 1] - sT[j];
-                                    c0 = radd(rmul(dm, q[0]), rmul(dn, q[4]));
-                                    c1 = fma(dm, q[1], dn * q[5]);
-                                    c2 = fma(dm, q[2], dn * q[6]);
-                                    c3 = fma(dm, q[3], dn * q[7]);
-                                    d2 = 2.0 * c2; d3 = 3.0 * c3;
-                                    const double xl0 = (j == ja) ? E.xa : 0.0;
-                                    const double xh0 = (j == jb) ? E.xb : hj;
-                                    segA = (j == ja) ? fma(xl0, fma(xl0, fma(xl0, c3, c2), c1), c0) : c0;
-                                    segB = (j == jb) ? fma(xh0, fma(xh0, fma(xh0, c3, c2), c1), c0)
-                                                     : radd(rmul(dm, q[16]), rmul(dn, q[20]));
-                                    tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
-                                    xlo_s = xl0 - 1e-5 * hj; xhi_s = xh0 + 1e-5 * hj;
+                            pX[0] = x1;
+                            if (two) {
+                                if (!(fabs(dx2) <= tol && x2 >= xlo && x2 <= xhi)) {
+                                    x2 = solve_slow(c1, c2, c3, f2 - c0, xlo, xhi, tol, sdir);
+                                    r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
                                 }
-                                x = solve_slow(c1, c2, c3, f - c0, xlo_s, xhi_s, tol, sdir);
-                                rr = fast_rcp(fma(x, fma(d3, x, d2), c1));
+                                pX[SUM_THREADS] = x2;
+                                xb = x2; fb = f2; rb = r2;
+                                pF += SUM_THREADS; pX += SUM_THREADS;
                             }
-                            xprev = x; fprev = f; rprev = rr;
-                            pX[0] = x;
-                            pJ[0] = (unsigned short)j;
-#if OPT_SPLIT && SUM_SF
-                            if (BPT >= 3 && b == 0 && bh == BPT - 1) {
-                                // All bins of the thread lie on this branch (the common case).  Instead of the serial chain
-                                // 0 -> 1 -> 2 -> ..., bins b+1 and b+2 both extrapolate from bin b (steps df and 2 df): two independent
-                                // Newton chains interleave in the issue stream; an odd last bin follows its predecessor.  A bin that
-                                // leaves the segment or misses the tolerance sends the thread back to the serial loop.
-                                // (f is monotone in the bin index, so the first and the last bin decide "inside the segment".)
-                                const double fn1 = flip_sign(pF[SUM_THREADS], smask), fnl = flip_sign(pF[(BPT - 1) * SUM_THREADS], smask);
-                                const bool in_all = dir > 0 ? (fn1 >= segA && fn1 < segB && fnl >= segA && fnl < segB)
-                                                            : (fn1 <= segA && fn1 > segB && fnl <= segA && fnl > segB);
-                                if (in_all) {
-                                    double xs[BPT];
-                                    double xb = x, fb = f, rb = rr, worst = 0.0, xmin = x, xmax = x;
-#pragma unroll
-                                    for (int q = 0; q + 1 < BPT; q += 2) { // from bin q: bins q+1 and (if it exists) q+2
-                                        const bool two = q + 2 < BPT;
-                                        const double kap = fma(2.0 * d3, xb, d2) * rb;
-                                        const double f1 = flip_sign(pF[(q + 1) * SUM_THREADS], smask);
-                                        const double f2 = two ? flip_sign(pF[(q + 2) * SUM_THREADS], smask) : f1;
-                                        const double dl1 = (f1 - fb) * rb, dl2 = (f2 - fb) * rb;
-                                        double x1 = fma(dl1, fma(-0.5 * kap, dl1, 1.0), xb), x2 = fma(dl2, fma(-0.5 * kap, dl2, 1.0), xb);
-                                        const double g1 = x1 * fma(x1, fma(x1, c3, c2), c1) - (f1 - c0);
-                                        const double g2 = x2 * fma(x2, fma(x2, c3, c2), c1) - (f2 - c0);
-                                        const double r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1)), r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
-                                        const double dx1 = g1 * r1, dx2 = g2 * r2;
-                                        x1 -= dx1; x2 -= dx2;
-                                        xs[q + 1] = x1;
-                                        worst = fmax(worst, fmax(fabs(dx1), fabs(dx2)));
-                                        xmin = fmin(xmin, fmin(x1, x2)); xmax = fmax(xmax, fmax(x1, x2));
-                                        if (two) { xs[q + 2] = x2; xb = x2; fb = f2; rb = r2; }
-                                    }
-                                    if (worst <= tol && xmin >= xlo_s && xmax <= xhi_s) {
-#pragma unroll
-                                        for (int q = 1; q < BPT; q++) { pX[q * SUM_THREADS] = xs[q]; pJ[q * SUM_THREADS] = (unsigned short)j; }
-                                        break;
-                                    }
-                                }
-                            }
-#endif
                         }
                     }
-                    // ---- stage 2: evaluate the bins two at a time (same segment) in straight-line code ----
+                    // ---- stage 2: evaluate the bins two at a time in straight-line code ----
                     {
+                        const int side = fl & SE_SIDE;
                         const double *pF = sF + tid + bl * SUM_THREADS;
                         const double *pX = sX + tid + bl * SUM_THREADS;
-                        const unsigned short *pJ = sJ + tid + bl * SUM_THREADS;
-                        int id0 = offd + bl * ACC_STRIDE, im0 = offm + bl * ACC_STRIDE;
-                        for (int b = bl; b <= bh;) {
-                            const int j = pJ[0];
-                            const bool two = (b < bh) && (pJ[SUM_THREADS] == j);
-                            const double *q = sQ + j * 16;
-                            const double4 qa = *reinterpret_cast<const double4 *>(cmode + (long long)j * (R * 4));
-                            const double4 qb = *reinterpret_cast<const double4 *>(cmode + (long long)j * (R * 4) + K * 4);
-                            const double c1 = fma(dm, q[1], dn * q[5]);
-                            const double d2 = 2.0 * fma(dm, q[2], dn * q[6]);
-                            const double d3 = 3.0 * fma(dm, q[3], dn * q[7]);
-                            const double tj = sT[j];
-                            if (two) {
+                        int id0 = side * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE;       // direct term -> this side
+                        int im0 = (1 - side) * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE; // mirrored -m term -> other side
+                        for (int b = bl; b <= bh; b += 2) {
+                            if (b < bh) {
                                 const double x2[2] = {pX[0], pX[SUM_THREADS]};
-#if OPT_SIGN
-                                const double f2[2] = {flip_sign(BINF(pF, b), smask), flip_sign(BINF2(pF, b), smask)};
-#else
-                                const double f2[2] = {sgn * BINF(pF, b), sgn * BINF2(pF, b)};
-#endif
-                                eval_bins<2, BPT>(x2, f2, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
-                                b += 2; pF += 2 * SUM_THREADS; pX += 2 * SUM_THREADS; pJ += 2 * SUM_THREADS;
-                                id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
+                                const double f2[2] = {flip_sign(pF[0], smask), flip_sign(pF[SUM_THREADS], smask)};
+                                eval_sub<2, BPT>(x2, f2, c1, d2, d3, S, p.k13_few, acc, id0, im0);
                             } else {
                                 const double x1[1] = {pX[0]};
-#if OPT_SIGN
-                                const double f1[1] = {flip_sign(BINF(pF, b), smask)};
-#else
-                                const double f1[1] = {sgn * BINF(pF, b)};
-#endif
-                                eval_bins<1, BPT>(x1, f1, c1, d2, d3, qa, qb, tj, q, sU + j * 4, dm, dn, E, acc, id0, im0);
-                                b += 1; pF += SUM_THREADS; pX += SUM_THREADS; pJ += SUM_THREADS;
-                                id0 += ACC_STRIDE; im0 += ACC_STRIDE;
+                                const double f1[1] = {flip_sign(pF[0], smask)};
+                                eval_sub<1, BPT>(x1, f1, c1, d2, d3, S, p.k13_few, acc, id0, im0);
                             }
+                            pF += 2 * SUM_THREADS; pX += 2 * SUM_THREADS;
+                            id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
                         }
                     }
                 }
             }
-        }
-        } // entry groups
+        } // fill rounds
     }
 
     // ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
@@ -1253,7 +1478,6 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
             a2 += h0r * h0r + h0i * h0i + h1r * h1r + h1i * h1i;
         }
     }
-#undef ACC
     if (LIKE) { // per-warp partial sums (no CTA barrier); like_finalize_kernel adds them in a fixed order
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
@@ -1309,7 +1533,7 @@ __global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_direct_kernel(
 
 // deterministic second stage: one CTA per walker
 __global__ void __launch_bounds__(256) like_finalize_kernel(const double *__restrict__ partial, long long ntiles,
-                                                            double *__restrict__ out) {
+                                                            double *__restrict__ out, const int *__restrict__ wstatus) {
     __shared__ double s[3][256];
     const double *pp = partial + (long long)blockIdx.x * ntiles * 3;
     double a0 = 0, a1 = 0, a2 = 0;
@@ -1325,9 +1549,12 @@ __global__ void __launch_bounds__(256) like_finalize_kernel(const double *__rest
         __syncthreads();
     }
     if (threadIdx.x == 0) {
-        out[3 * blockIdx.x + 0] = -0.5 * 4.0 * s[0][0]; // ll = -1/2 * 4 * sum |d~ - h~|^2 (likelihood.py:270-274)
-        out[3 * blockIdx.x + 1] = 4.0 * s[1][0];
-        out[3 * blockIdx.x + 2] = 4.0 * s[2][0];
+        // a walker whose trajectory or work-list was refused reports NaN (Eryn maps NaN to -1e300, red_blue.py:282-284)
+        const bool bad = wstatus && wstatus[blockIdx.x];
+        const double nan = __longlong_as_double(0x7ff8000000000000LL);
+        out[3 * blockIdx.x + 0] = bad ? nan : -0.5 * 4.0 * s[0][0]; // ll = -1/2 * 4 * sum |d~ - h~|^2 (likelihood.py:270-274)
+        out[3 * blockIdx.x + 1] = bad ? nan : 4.0 * s[1][0];
+        out[3 * blockIdx.x + 2] = bad ? nan : 4.0 * s[2][0];
     }
 }
 
@@ -1662,8 +1889,8 @@ static size_t spline_smem_bytes(int L, bool tiled) {
 }
 
 static size_t sum_smem_bytes(int L, int bpt = SUM_BPT) {
-    return sizeof(double) * 4 * bpt * ACC_STRIDE + (8 * SUM_SF + 8 + 2) * bpt * SUM_THREADS + sizeof(Entry) * SUM_ENT_CAP +
-           sizeof(double) * SMEM_PER_KNOT * (size_t)L;
+    return sizeof(double) * 4 * bpt * ACC_STRIDE + sizeof(SubEntry) * SUM_SUBCAP + sizeof(FillEntry) * SUM_ECAP +
+           2 * sizeof(double) * bpt * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
 
 static int ensure_bytes(emrifd_handle *h, void **ptr, int64_t *cap, int64_t need, bool pinned_host = false) {
@@ -1694,6 +1921,10 @@ static int upload_walkers(emrifd_handle *h, const emrifd_walker_t *walkers, int6
     int rc = ensure_bytes(h, (void **)&h->d_walkers, &wc, (int64_t)sizeof(emrifd_walker_t) * B);
     if (rc) return rc;
     h->walkers_cap = wc;
+    if ((int64_t)sizeof(int) * B > h->wstatus_cap) {
+        if ((rc = ensure_bytes(h, (void **)&h->d_wstatus, &h->wstatus_cap, (int64_t)sizeof(int) * B))) return rc;
+        CUDA_TRY(h, cudaMemsetAsync(h->d_wstatus, 0, (size_t)h->wstatus_cap, h->stream));
+    }
     const int slot = h->stage_next;
     h->stage_next = (slot + 1) & 3;
     CUDA_TRY(h, cudaEventSynchronize(h->stage_ev[slot]));
@@ -1707,14 +1938,20 @@ static int upload_walkers(emrifd_handle *h, const emrifd_walker_t *walkers, int6
 static int validate_walkers(emrifd_handle *h, const emrifd_walker_t *w, int64_t B, int *Lmax, int *Kmax) {
     if (!w || B <= 0 || B > 65535) return set_err(h, EMRIFD_ERR_INVALID, "walkers NULL or batch size outside [1, 65535]");
     int lm = 0, km = 0;
+    int64_t nm = 0, nte = 0;
     for (int64_t i = 0; i < B; i++) {
         if (w[i].L < 4) return set_err(h, EMRIFD_ERR_TOO_FEW_KNOTS, "not-a-knot spline needs at least 4 knots");
         if (w[i].L > EMRIFD_MAX_KNOTS) return set_err(h, EMRIFD_ERR_TOO_MANY_KNOTS, "trajectory longer than EMRIFD_MAX_KNOTS");
         if (w[i].K < 1) return set_err(h, EMRIFD_ERR_INVALID, "walker with no modes");
+        if (w[i].knot_off < 0 || w[i].teuk_off < 0 || w[i].mode_off < 0 || w[i].coeff_off < 0 || w[i].out_off < 0)
+            return set_err(h, EMRIFD_ERR_INVALID, "walker descriptor with a negative offset");
         if (w[i].L > lm) lm = w[i].L;
         if (w[i].K > km) km = w[i].K;
+        if (w[i].mode_off + w[i].K > nm) nm = w[i].mode_off + w[i].K;
+        if (w[i].teuk_off + (int64_t)w[i].L * w[i].K > nte) nte = w[i].teuk_off + (int64_t)w[i].L * w[i].K;
     }
     *Lmax = lm; *Kmax = km;
+    h->tot_modes = nm; h->tot_teuk = nte;
     return 0;
 }
 
@@ -1743,32 +1980,34 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     h->stream = (cudaStream_t)stream;
     if (cudaMalloc((void **)&h->d_status, sizeof(int)) != cudaSuccess) { delete h; return EMRIFD_ERR_CUDA; }
     cudaMemset(h->d_status, 0, sizeof(int));
-    for (int i = 0; i < 4; i++) cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming);
-    for (int i = 0; i < 64; i++) { cudaEventCreate(&h->ev_a[i]); cudaEventCreate(&h->ev_b[i]); }
+    bool ok = true; // every set-up call is checked: a handle is either fully usable or not created
+    for (int i = 0; i < 4; i++) ok &= cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    for (int i = 0; i < 64; i++) ok &= cudaEventCreate(&h->ev_a[i]) == cudaSuccess && cudaEventCreate(&h->ev_b[i]) == cudaSuccess;
     int optin = 0;
-    cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device);
+    ok &= cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess;
     const int big = optin - 2048; // static smem of the kernel (< 2 KB) comes out of the same budget
     h->max_dyn_smem = big;
-    cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device);
-    cudaFuncSetAttribute(spline_build_kernel<false, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(spline_build_kernel<false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(spline_build_kernel<true, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(spline_build_kernel<true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(segment_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
-    cudaFuncSetAttribute(mode_select_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, SEL_CAP * 10);
+    ok &= cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && h->num_sms > 0;
+#define SET_ATTR(F_, BYTES_) ok &= cudaFuncSetAttribute(F_, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES_) == cudaSuccess
+    SET_ATTR((spline_build_kernel<false, true>), big);
+    SET_ATTR((spline_build_kernel<false, false>), big);
+    SET_ATTR((spline_build_kernel<true, true>), big);
+    SET_ATTR((spline_build_kernel<true, false>), big);
+    SET_ATTR(segment_kernel, big);
+    SET_ATTR(group_kernel, big);
+    SET_ATTR(mode_select_kernel, SEL_CAP * 10);
 #define SET_SMEM(W_, L_) \
-    cudaFuncSetAttribute(mode_sum_kernel<W_, L_, SUM_BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-    cudaFuncSetAttribute(mode_sum_kernel<W_, L_, SUM_BPT_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-    cudaFuncSetAttribute(mode_sum_direct_kernel<W_, L_, SUM_BPT>, cudaFuncAttributeMaxDynamicSharedMemorySize, big); \
-    cudaFuncSetAttribute(mode_sum_direct_kernel<W_, L_, SUM_BPT_WIDE>, cudaFuncAttributeMaxDynamicSharedMemorySize, big);
+    SET_ATTR((mode_sum_kernel<W_, L_, SUM_BPT>), big); SET_ATTR((mode_sum_kernel<W_, L_, SUM_BPT_WIDE>), big); \
+    SET_ATTR((mode_sum_direct_kernel<W_, L_, SUM_BPT>), big); SET_ATTR((mode_sum_direct_kernel<W_, L_, SUM_BPT_WIDE>), big);
     SET_SMEM(true, false) SET_SMEM(true, true) SET_SMEM(false, true)
 #undef SET_SMEM
+#undef SET_ATTR
     {
         const char *fb = getenv("EMRIFD_BPT");
         h->force_bpt = fb ? atoi(fb) : 0;
         if (h->force_bpt != SUM_BPT && h->force_bpt != SUM_BPT_WIDE) h->force_bpt = 0;
     }
-    if (cudaGetLastError() != cudaSuccess) { delete h; return EMRIFD_ERR_CUDA; }
+    if (!ok || cudaGetLastError() != cudaSuccess) { emrifd_destroy(h); return EMRIFD_ERR_CUDA; }
     *out = h;
     return 0;
 }
@@ -1778,9 +2017,11 @@ int emrifd_destroy(emrifd_handle_t *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_queue); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd); cudaFree(h->d_tiledd_w);
+    cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq);
     if (h->h_ws) cudaFreeHost(h->h_ws);
-    for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); cudaEventDestroy(h->stage_ev[i]); }
-    for (int i = 0; i < 64; i++) { cudaEventDestroy(h->ev_a[i]); cudaEventDestroy(h->ev_b[i]); }
+    for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
+    for (int i = 0; i < 64; i++) { if (h->ev_a[i]) cudaEventDestroy(h->ev_a[i]); if (h->ev_b[i]) cudaEventDestroy(h->ev_b[i]); }
+    cudaGetLastError();
     delete h;
     return 0;
 }
@@ -1858,7 +2099,9 @@ static int batch_segment_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, co
     SegParams p;
     p.w = h->d_walkers; p.t = t; p.coeff = coeff; p.m = m_arr; p.n = n_arr; p.br = branches;
     p.n_eval = (long long *)n_eval;
+    p.wstatus = h->d_wstatus;
     p.g.N = N; p.g.zero = (N - 1) / 2; p.g.val = val; p.g.fpos = fpos;
+    CUDA_TRY(h, cudaMemsetAsync(h->d_wstatus, 0, sizeof(int) * (size_t)B, h->stream));
     if (n_eval) CUDA_TRY(h, cudaMemsetAsync(n_eval, 0, sizeof(int64_t) * 2 * (size_t)B, h->stream));
     // modes per CTA: as many as fit next to the staged tracks (8 at L <= ~600, fewer for very long trajectories)
     int mpc = (int)((h->max_dyn_smem - 72 * (int64_t)Lmax) / (36 * (int64_t)Lmax));
@@ -1925,14 +2168,34 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
         if (rc) return rc;
         p.partial = h->d_partial;
     }
+    // (m, n) groups: index + combined amplitude quads (one stationary point per (group, bin) in the sum)
+    {
+        if (Kmax > GRP_TAB) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum: more than 8192 modes in one walker");
+        int rc;
+        if ((rc = ensure_bytes(h, (void **)&h->d_leader, &h->leader_cap, (int64_t)sizeof(int) * h->tot_modes))) return rc;
+        if ((rc = ensure_bytes(h, (void **)&h->d_gcount, &h->gcount_cap, (int64_t)sizeof(int) * B))) return rc;
+        if ((rc = ensure_bytes(h, (void **)&h->d_gq, &h->gq_cap, (int64_t)sizeof(double) * 16 * h->tot_teuk))) return rc;
+        GroupParams gp;
+        gp.w = h->d_walkers; gp.coeff = coeff; gp.m = m_arr; gp.n = n_arr; gp.ylm = (const double2 *)ylm;
+        gp.leader = h->d_leader; gp.gcount = h->d_gcount; gp.gq = h->d_gq;
+        int64_t nsl = ((int64_t)Lmax * Kmax + 2047) / 2048; // knot slices per walker: ~2048 (knot, mode) pairs per CTA
+        nsl = nsl < 1 ? 1 : (nsl > Lmax ? Lmax : nsl);
+        const size_t gsmem = sizeof(int) * ((size_t)GRP_TAB + 4 * (size_t)Kmax + 1);
+        group_kernel<<<dim3((unsigned)nsl, (unsigned)B), GRP_THREADS, gsmem, h->stream>>>(gp);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        p.leader = h->d_leader; p.gcount = h->d_gcount; p.gq = h->d_gq; p.wstatus = h->d_wstatus; p.k13_few = h->k13_few;
+    }
     const int cpw = (Kmax * MAXBR + SUM_THREADS - 1) / SUM_THREADS;
     {
         int rc = ensure_bytes(h, (void **)&h->d_chunk, &h->chunk_cap, (int64_t)sizeof(long long) * 2 * cpw * B);
         if (rc) return rc;
         dim3 cgrid((unsigned)cpw, (unsigned)B);
-        chunk_range_kernel<<<cgrid, SUM_THREADS, 0, h->stream>>>(h->d_walkers, branches, (N - 1) / 2, h->d_chunk, cpw);
+        chunk_range_kernel<<<cgrid, SUM_THREADS, 0, h->stream>>>(h->d_walkers, branches, h->d_leader, h->d_gcount, (N - 1) / 2, h->d_chunk, cpw);
         h->launches++;
         p.chunk_rng = h->d_chunk; p.cpw = cpw;
+        // per-tile sum |d~|^2 table of the injected data: usable when this launch's tiles coincide with the table's
+        // (a truncated last tile is sent through the per-bin path by the kernels, see tile_truncated)
         p.tile_dd = (like && (j_lo % tile_bins) == 0) ? (bpt == SUM_BPT ? h->d_tiledd : h->d_tiledd_w) : nullptr;
     }
     const size_t smem = sum_smem_bytes(Lmax, bpt);
@@ -1977,7 +2240,7 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     if (like) {
-        like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, ntiles * (SUM_THREADS / 32), like_out);
+        like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, ntiles * (SUM_THREADS / 32), like_out, h->d_wstatus);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -2074,7 +2337,7 @@ int emrifd_inner_product(emrifd_handle_t *h, const double *a, const double *b, i
     if (!h || !a || !b || !freqs || !out || nch <= 0 || n < 2) return set_err(h, EMRIFD_ERR_INVALID, "inner_product: bad argument");
     cudaSetDevice(h->device);
     int64_t nb = (nch * n + 256 * 8 - 1) / (256 * 8);
-    if (nb > 1184) nb = 1184; // 148 SMs x 8 resident CTAs
+    if (nb > (int64_t)h->num_sms * 8) nb = (int64_t)h->num_sms * 8; // 8 resident CTAs per SM
     if (nb < 1) nb = 1;
     int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * 2 * nb);
     if (rc) return rc;
@@ -2091,13 +2354,14 @@ int emrifd_loglike(emrifd_handle_t *h, const double *templates, int64_t B, doubl
     cudaSetDevice(h->device);
     const int64_t n = h->n_data;
     int64_t nb = (2 * n + 256 * 4 - 1) / (256 * 4);
-    const int64_t cap = (1184 + B - 1) / B > 8 ? (1184 + B - 1) / B : 8;
+    const int64_t wave = (int64_t)h->num_sms * 8;
+    const int64_t cap = (wave + B - 1) / B > 8 ? (wave + B - 1) / B : 8;
     if (nb > cap) nb = cap;
     int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * 3 * nb * B);
     if (rc) return rc;
     dim3 grid((unsigned)nb, (unsigned)B);
     loglike_partial_kernel<<<grid, 256, 0, h->stream>>>((const double2 *)templates, (const double2 *)h->d_data, h->d_wfac, n, h->d_partial);
-    like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, nb, out);
+    like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, nb, out, nullptr);
     h->launches += 2;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
@@ -2157,10 +2421,27 @@ int emrifd_loglike_batch_host(emrifd_handle_t *h, const emrifd_walker_t *walkers
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     memcpy(like_out_host, hres, sizeof(double) * 3 * (size_t)B);
     if (st != 0) {
+        // data-dependent failure of some walker(s): their rows are NaN (the per-walker contract of the reference's samplers,
+        // Eryn/eryn/moves/red_blue.py:282-284); the rest of the batch is valid.  emrifd_walker_status tells which and why.
         cudaMemsetAsync(h->d_status, 0, sizeof(int), h->stream);
-        return set_err(h, st, st == EMRIFD_ERR_BRANCHES ? "a mode has more monotone branches than EMRIFD_MAX_BRANCHES"
-                                                         : "trajectory knots are not strictly increasing");
+        set_err(h, st, st == EMRIFD_ERR_BRANCHES ? "a mode has more monotone branches than EMRIFD_MAX_BRANCHES (walker reported as NaN)"
+                                                 : "trajectory knots are not strictly increasing (walker reported as NaN)");
     }
+    return 0;
+}
+
+int emrifd_walker_status(emrifd_handle_t *h, int64_t B, int32_t *status_host) {
+    if (!h || !status_host || B <= 0) return set_err(h, EMRIFD_ERR_INVALID, "walker_status: bad argument");
+    if ((int64_t)sizeof(int) * B > h->wstatus_cap) return set_err(h, EMRIFD_ERR_INVALID, "walker_status: no batch of that size has run on this handle");
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaMemcpyAsync(status_host, h->d_wstatus, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
+    CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int emrifd_set_k13_mode(emrifd_handle_t *h, int mode) {
+    if (!h || (mode != EMRIFD_K13_EXACT && mode != EMRIFD_K13_FEW)) return set_err(h, EMRIFD_ERR_INVALID, "set_k13_mode: mode must be EMRIFD_K13_EXACT or EMRIFD_K13_FEW");
+    h->k13_few = mode == EMRIFD_K13_FEW;
     return 0;
 }
 
@@ -2242,7 +2523,7 @@ int emrifd_bench_fp64_fma(emrifd_handle_t *h, int iters, double *gflops) {
     cudaSetDevice(h->device);
     double *d = nullptr;
     CUDA_TRY(h, cudaMalloc((void **)&d, 8));
-    const int blocks = 148 * 8;
+    const int blocks = h->num_sms * 8;
     cudaEvent_t a, b;
     cudaEventCreate(&a); cudaEventCreate(&b);
     fma_bench_kernel<<<blocks, 256, 0, h->stream>>>(d, 16, 1.0000001, 1e-9); // warm-up

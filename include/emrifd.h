@@ -29,7 +29,7 @@
 extern "C" {
 #endif
 
-#define EMRIFD_VERSION 100
+#define EMRIFD_VERSION 200
 #define EMRIFD_MAX_BRANCHES 4 /* monotone branches per mode (turnovers + 1) */
 #define EMRIFD_MAX_KNOTS 1024 /* sparse trajectory length limit (few: max_init_len = 1000) */
 
@@ -42,6 +42,11 @@ extern "C" {
 #define EMRIFD_ERR_CUDA (-6)          /* CUDA runtime error; see emrifd_last_error */
 #define EMRIFD_ERR_TOO_MANY_KNOTS (-7)
 #define EMRIFD_ERR_NO_DATA (-8)       /* likelihood requested before emrifd_set_data */
+
+/* evaluation of the SPA factor's K_{1/3} (Tutorial_FD_construction_single_mode.ipynb:599-609 uses scipy.special.kv) */
+#define EMRIFD_K13_EXACT 0 /* <= 3e-15 everywhere (default) */
+#define EMRIFD_K13_FEW 1   /* FastEMRIWaveforms' SPAFunc: 14-term ascending series for |X| <= 7, 9-term asymptotic above
+                              (2.5e-7 off at the seam) -- for bit-level comparisons against FEW's CPU backend */
 
 /* flags for the mode-sum entry points */
 #define EMRIFD_INCLUDE_MINUS_M 1 /* add the mirrored -m term (include_minus_m=True) */
@@ -134,8 +139,16 @@ int emrifd_fd_waveform_batch(emrifd_handle_t *h, const emrifd_walker_t *walkers,
                              int64_t N, double val, const double *fpos, int flags,
                              double *coeff, emrifd_branch_t *branches,
                              double *hp, double *hc, double *like_out);
-/* status of the last batch on this handle: reads the device error word. sync. */
+/* status of the last batch on this handle: reads the device error word (first failure of ANY walker). sync. */
 int emrifd_batch_status(emrifd_handle_t *h);
+/* Per-walker status of the last batch that went through emrifd_batch_segment / emrifd_fd_waveform_batch /
+ * emrifd_loglike_batch_host: status_host[B] = 0 or EMRIFD_ERR_KNOT_ORDER / EMRIFD_ERR_BRANCHES.  A failing walker gets
+ * h = 0 and ll = <d|h> = <h|h> = NaN; every other walker of the batch is bit-identical to a clean run.  This is the
+ * reference's per-walker contract: Eryn maps a NaN likelihood to -1e300 (Eryn/eryn/moves/red_blue.py:282-284) and the sweep
+ * skips a failing point (check_mode_by_mode.py:328-330).  sync. */
+int emrifd_walker_status(emrifd_handle_t *h, int64_t B, int32_t *status_host);
+/* EMRIFD_K13_EXACT (default) or EMRIFD_K13_FEW for every later mode sum on this handle. */
+int emrifd_set_k13_mode(emrifd_handle_t *h, int mode);
 
 /* ---- A10/A11: PSD-weighted inner product and likelihood ------------------------------------
  * emrifd_set_data replaces lisatools Likelihood.inject_signal's stored state

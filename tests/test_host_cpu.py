@@ -22,7 +22,7 @@ def test_library_exports_every_declared_symbol():
     lib = ctypes.CDLL(_lib.LIB_PATH)
     for name in declared:
         assert hasattr(lib, name), name
-    assert lib.emrifd_version() == 100
+    assert lib.emrifd_version() == 200
     assert lib.emrifd_sizeof_branch() == _lib.BRANCH_DTYPE.itemsize == 72
     assert lib.emrifd_sizeof_walker() == _lib.WALKER_DTYPE.itemsize
 
