@@ -383,6 +383,7 @@ def main():
     h.check(h.lib.emrifd_batch_segment(h.h, pb.walkers.ctypes.data, B, db.t.data_ptr(), db.coeff.data_ptr(), db.m.data_ptr(),
                                        db.n.data_ptr(), N, val, None, db.branches.data_ptr(), nev.data_ptr()))
     evals, mbe = [int(x) for x in nev.sum(dim=0).cpu().numpy()]
+    gevals = int(engine.group_evaluations(db).sum())    # stationary points actually solved: one per ((m, n) group, bin)
     ll_dev = like[:, 0].cpu().numpy()
     assert np.all(np.isfinite(ll_dev)) and np.allclose(ll_dev, like_host[:, 0], rtol=1e-12, atol=1e-9), "device and e2e paths disagree"
 
@@ -441,7 +442,7 @@ def main():
         "clocks": clocks,
         "roofline": binding,
         "roofline_other_roof": other,
-        "work": {"evals_per_walker": evals / B, "mbe_per_walker": mbe / B, "modes_per_walker": pb.n_modes / B,
+        "work": {"evals_per_walker": evals / B, "group_evals_per_walker": gevals / B, "mbe_per_walker": mbe / B, "modes_per_walker": pb.n_modes / B,
                  "knots_per_walker": pb.n_knots / B},
     }
     if not args.no_cpu_baseline and world == 1:   # the CPU baseline is an N = 1 figure (rank 0 would stall the other ranks' exit)

@@ -864,10 +864,11 @@ struct __align__(16) SubEntry {
     double tol, tj;         // Newton tolerance, knot time
     double mu_hi, mu_lo;    // (m Phi_phi + n Phi_r)(t_j) / 2pi mod 1 as a double-double; -1/4 on falling branches
     double p1, p2, p3;      // -(1/2pi) x (m Phi_phi + n Phi_r) cubic remainder, in cycles
-    const double *amp;      // 16 doubles: quads of Re Cp, Im Cp, Re Cm, Im Cm of (segment, group)
+    double pad;
     int s, e;               // tile-local bin range (inclusive)
     unsigned int fmask;     // 0 / 0x80000000: sign mask applied to the bin frequency
     int flags;
+    double4 amp[4];         // quads of Re Cp, Im Cp, Re Cm, Im Cm of (segment, group)
 };
 // overlapping work-list record of the current fill round (written and read by the fill warp only)
 struct __align__(16) FillEntry {
@@ -969,7 +970,7 @@ __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)
             ei[i] = re[i] * sn[i] + gim * cs[i];
         }
     }
-    const double4 *ap = reinterpret_cast<const double4 *>(S.amp);
+    const double4 *ap = S.amp;
     {
         const double4 qa = ap[0], qb = ap[1];
 #pragma unroll
@@ -1116,17 +1117,16 @@ __device__ __forceinline__ double knot_F(const double *sK, int j, double dm, dou
 // Fill warp, step 1: lane i < gcount turns overlapping record s_list[i] into a FillEntry (tile-local bin ranges and the spline
 // segments they fall in, per side) and the warp numbers the sub-entries of the round (exclusive scan).  Returns their total.
 template <int BPT>
-__device__ __noinline__ int fill_entries(const int *leader, const emrifd_branch_t *br, const int *marr, const int *narr,
-                                         int include_minus_m, long long zero, const int *s_list, int gcount, long long jt0,
+__device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *marr, const int *narr, int include_minus_m,
+                                         long long zero, const int *s_list, const int *s_rec, int gcount, long long jt0,
                                          long long jt1, const double *sF, const double *sK, FillEntry *ent) {
-    // (leader, br, marr, narr: this walker's blocks.  Scalars by value: a reference to the kernel parameters would force a
+    // (br, marr, narr: this walker's blocks.  Scalars by value: a reference to the kernel parameters would force a
     //  local-memory copy of them)
     const int lane = threadIdx.x & 31;
     int nsub = 0;
     if (lane < gcount) {
-        const int rg = s_list[lane], g = rg / MAXBR;
-        const int k = leader[g];
-        const emrifd_branch_t b = br[k * MAXBR + rg % MAXBR];
+        const int g = s_list[lane] / MAXBR, rec = s_rec[lane], k = rec / MAXBR;
+        const emrifd_branch_t b = br[rec];
         const int mi = marr[k], ni = narr[k];
         FillEntry e;
         e.xa = b.xa; e.xb = b.xb; e.dm = (double)mi; e.dn = (double)ni;
@@ -1146,9 +1146,8 @@ __device__ __noinline__ int fill_entries(const int *leader, const emrifd_branch_
             e.jlo[sd] = 1; e.jhi[sd] = 0;
             if (e.s[sd] > e.e[sd]) continue;
             int jj2[2];
-#pragma unroll
-            for (int w = 0; w < 2; w++) { // segment of the side's first / last bin: largest j whose knot frequency is not beyond f
-                const double fb = tile_binf<BPT>(sF, w == 0 ? e.s[sd] : e.e[sd]);
+            { // segment of the side's first bin: largest j whose knot frequency is not beyond f (binary search) ...
+                const double fb = tile_binf<BPT>(sF, e.s[sd]);
                 const double f = sd == 0 ? fb : -fb;
                 int l2 = b.ja, h2 = b.jb;
                 while (l2 < h2) {
@@ -1156,7 +1155,15 @@ __device__ __noinline__ int fill_entries(const int *leader, const emrifd_branch_
                     const double Fk = knot_F(sK, mid, e.dm, e.dn);
                     if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) l2 = mid; else h2 = mid - 1;
                 }
-                jj2[w] = l2;
+                jj2[0] = l2;
+            }
+            { // ... and of its last bin: a short walk from there (a tile rarely spans more than a few segments)
+                const double fb = tile_binf<BPT>(sF, e.e[sd]);
+                const double f = sd == 0 ? fb : -fb;
+                int l2 = jj2[0];
+                while (l2 < b.jb) { const double Fk = knot_F(sK, l2 + 1, e.dm, e.dn); if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) l2++; else break; }
+                while (l2 > b.ja) { const double Fk = knot_F(sK, l2, e.dm, e.dn); if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) break; l2--; }
+                jj2[1] = l2;
             }
             e.jlo[sd] = jj2[0] < jj2[1] ? jj2[0] : jj2[1];
             e.jhi[sd] = jj2[0] < jj2[1] ? jj2[1] : jj2[0];
@@ -1173,84 +1180,86 @@ __device__ __noinline__ int fill_entries(const int *leader, const emrifd_branch_
     return __shfl_sync(0xffffffffu, incl, 31);
 }
 
-// Fill warp, step 2: lane i < gcount writes those of its sub-entries whose index lies in [w0, w0 + SUM_SUBCAP).
+// Fill step 2: thread t < nsw builds sub-entry w0 + t of the round (its record found from the entries' offsets).
 template <int BPT>
-__device__ __noinline__ void fill_subs(const double *coeff, const double *gq, int K, int G, int gcount, int w0, const double *sF,
+__device__ __noinline__ void fill_subs(const double *coeff, const double *gq, int K, int G, int gcount, int w0, int nsw, const double *sF,
                                        const double *sK, const FillEntry *ent, SubEntry *sub) {
     // (coeff, gq: this walker's blocks)
-    const int lane = threadIdx.x & 31;
-    if (lane >= gcount) return;
-    const FillEntry e = ent[lane];
-    if (e.nsub == 0 || e.off >= w0 + SUM_SUBCAP || e.off + e.nsub <= w0) return;
+    const int t = threadIdx.x;
+    if (t >= nsw) return;
+    const int idx = w0 + t;
+    int ei = 0;
+    while (ei < gcount - 1 && idx >= ent[ei].off + ent[ei].nsub) ei++;
+    const FillEntry e = ent[ei];
     const int R = 2 * K + 4;
-    int idx = e.off;
-    for (int sd = 0; sd < 2; sd++) {
-        const bool fwd = (e.dir > 0) == (sd == 0); // bin index and segment index grow together
-        const double sg = sd == 0 ? 1.0 : -1.0;
-        for (int j = e.jlo[sd]; j <= e.jhi[sd]; j++, idx++) {
-            if (idx < w0 || idx >= w0 + SUM_SUBCAP) continue;
-            SubEntry S;
-            // ---- bins of this side that fall on segment j: P(lb, jj) = "bin lb lies on a segment >= jj" is monotone in lb ----
-            int bnd[2]; // first bin with P(., j) [fwd] / first bin without P(., j + 1) [!fwd]; then the bin after the last one
+    const int loc = idx - e.off;
+    const int n0 = e.jhi[0] >= e.jlo[0] ? e.jhi[0] - e.jlo[0] + 1 : 0;
+    const int sd = loc >= n0 ? 1 : 0;
+    const int j = e.jlo[sd] + (sd ? loc - n0 : loc);
+    const bool fwd = (e.dir > 0) == (sd == 0); // bin index and segment index grow together
+    const double sg = sd == 0 ? 1.0 : -1.0;
+    SubEntry S;
+    // ---- per-segment constants (global loads first: they overlap the boundary searches) ----
+    const double4 qf = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K) * 4);     // f_phi quad
+    const double4 qr = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 1) * 4); // f_r
+    const double4 qP = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 2) * 4); // Phi_phi
+    const double4 qR = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 3) * 4); // Phi_r
+    const double4 *ga = reinterpret_cast<const double4 *>(gq + ((long long)j * G + e.g) * 16);
+    S.amp[0] = ga[0]; S.amp[1] = ga[1]; S.amp[2] = ga[2]; S.amp[3] = ga[3];
+    // ---- bins of this side that fall on segment j: P(lb, jj) = "bin lb lies on a segment >= jj" is monotone in lb ----
+    int bnd[2]; // first bin with P(., j) [fwd] / first bin without P(., j + 1) [!fwd]; then the bin after the last one
 #pragma unroll
-            for (int w = 0; w < 2; w++) {
-                const int jj = fwd ? j + w : j + 1 - w;
-                const bool edge = fwd ? (w == 0 ? j == e.jlo[sd] : j == e.jhi[sd]) : (w == 0 ? j == e.jhi[sd] : j == e.jlo[sd]);
-                if (edge) { bnd[w] = w == 0 ? e.s[sd] : e.e[sd] + 1; continue; }
-                const double Fk = knot_F(sK, jj, e.dm, e.dn);
-                int lo = e.s[sd], hi = e.e[sd] + 1; // first lb in [lo, hi] where P flips
-                while (lo < hi) {
-                    const int mid = (lo + hi) >> 1;
-                    const double f = sg * tile_binf<BPT>(sF, mid);
-                    const bool P = e.dir > 0 ? (Fk <= f) : (Fk >= f);
-                    if (P == fwd) hi = mid; else lo = mid + 1;
-                }
-                bnd[w] = lo;
-            }
-            S.s = bnd[0]; S.e = bnd[1] - 1;
-            // ---- per-segment constants ----
-            const double4 qf = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K) * 4);     // f_phi quad
-            const double4 qr = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 1) * 4); // f_r
-            const double4 qP = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 2) * 4); // Phi_phi
-            const double4 qR = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 3) * 4); // Phi_r
-            const double dm = e.dm, dn = e.dn;
-            const double tj = sK[3 * j], hj = sK[3 * (j + 1)] - tj;
-            S.c0 = radd(rmul(dm, qf.x), rmul(dn, qr.x));
-            S.c1 = fma(dm, qf.y, dn * qr.y);
-            S.c2 = fma(dm, qf.z, dn * qr.z);
-            S.c3 = fma(dm, qf.w, dn * qr.w);
-            const double xl0 = (j == e.ja) ? e.xa : 0.0, xh0 = (j == e.jb) ? e.xb : hj;
-            S.xlo = xl0 - 1e-5 * hj; S.xhi = xh0 + 1e-5 * hj;
-            S.tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
-            S.tj = tj;
-            double u[4]; // Phi/(2 pi) mod 1 as double-doubles (hi, lo) for Phi_phi, Phi_r
-#pragma unroll
-            for (int q = 0; q < 2; q++) {
-                const double ph = q == 0 ? qP.x : qR.x;
-                double a = ph * EMRIFD_INV2PI_HI;
-                double er = fma(ph, EMRIFD_INV2PI_HI, -a);
-                a -= rint(a);
-                er = fma(ph, EMRIFD_INV2PI_LO, er);
-                const double hi2 = a + er;
-                u[2 * q] = hi2; u[2 * q + 1] = er - (hi2 - a);
-            }
-            S.mu_hi = fma(dm, u[0], dn * u[2]) - (e.dir < 0 ? 0.25 : 0.0);
-            S.mu_lo = fma(dm, u[1], dn * u[3]);
-            S.p1 = -EMRIFD_INV2PI_HI * fma(dm, qP.y, dn * qR.y);
-            S.p2 = -EMRIFD_INV2PI_HI * fma(dm, qP.z, dn * qR.z);
-            S.p3 = -EMRIFD_INV2PI_HI * fma(dm, qP.w, dn * qR.w);
-            S.amp = gq + ((long long)j * G + e.g) * 16;
-            S.fmask = sd == 0 ? 0u : 0x80000000u;
-            S.flags = (sd ? SE_SIDE : 0) | (e.mirror ? SE_MIRROR : 0) | (e.dir < 0 ? SE_FALL : 0);
-            sub[idx - w0] = S;
+    for (int w = 0; w < 2; w++) {
+        const int jj = fwd ? j + w : j + 1 - w;
+        const bool edge = fwd ? (w == 0 ? j == e.jlo[sd] : j == e.jhi[sd]) : (w == 0 ? j == e.jhi[sd] : j == e.jlo[sd]);
+        if (edge) { bnd[w] = w == 0 ? e.s[sd] : e.e[sd] + 1; continue; }
+        const double Fk = knot_F(sK, jj, e.dm, e.dn);
+        int lo = e.s[sd], hi = e.e[sd] + 1; // first lb in [lo, hi] where P flips
+        while (lo < hi) {
+            const int mid = (lo + hi) >> 1;
+            const double f = sg * tile_binf<BPT>(sF, mid);
+            const bool P = e.dir > 0 ? (Fk <= f) : (Fk >= f);
+            if (P == fwd) hi = mid; else lo = mid + 1;
         }
+        bnd[w] = lo;
     }
+    S.s = bnd[0]; S.e = bnd[1] - 1;
+    const double dm = e.dm, dn = e.dn;
+    const double tj = sK[3 * j], hj = sK[3 * (j + 1)] - tj;
+    S.c0 = radd(rmul(dm, qf.x), rmul(dn, qr.x));
+    S.c1 = fma(dm, qf.y, dn * qr.y);
+    S.c2 = fma(dm, qf.z, dn * qr.z);
+    S.c3 = fma(dm, qf.w, dn * qr.w);
+    const double xl0 = (j == e.ja) ? e.xa : 0.0, xh0 = (j == e.jb) ? e.xb : hj;
+    S.xlo = xl0 - 1e-5 * hj; S.xhi = xh0 + 1e-5 * hj;
+    S.tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
+    S.tj = tj;
+    double u[4]; // Phi/(2 pi) mod 1 as double-doubles (hi, lo) for Phi_phi, Phi_r
+#pragma unroll
+    for (int q = 0; q < 2; q++) {
+        const double ph = q == 0 ? qP.x : qR.x;
+        double a = ph * EMRIFD_INV2PI_HI;
+        double er = fma(ph, EMRIFD_INV2PI_HI, -a);
+        a -= rint(a);
+        er = fma(ph, EMRIFD_INV2PI_LO, er);
+        const double hi2 = a + er;
+        u[2 * q] = hi2; u[2 * q + 1] = er - (hi2 - a);
+    }
+    S.mu_hi = fma(dm, u[0], dn * u[2]) - (e.dir < 0 ? 0.25 : 0.0);
+    S.mu_lo = fma(dm, u[1], dn * u[3]);
+    S.p1 = -EMRIFD_INV2PI_HI * fma(dm, qP.y, dn * qR.y);
+    S.p2 = -EMRIFD_INV2PI_HI * fma(dm, qP.z, dn * qR.z);
+    S.p3 = -EMRIFD_INV2PI_HI * fma(dm, qP.w, dn * qR.w);
+    S.pad = 0.0;
+    S.fmask = sd == 0 ? 0u : 0x80000000u;
+    S.flags = (sd ? SE_SIDE : 0) | (e.mirror ? SE_MIRROR : 0) | (e.dir < 0 ? SE_FALL : 0);
+    sub[t] = S;
 }
 
 template <bool WRITE_H, bool LIKE, int BPT>
 __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile_x, const int walker_y, unsigned char *smraw,
                                               int &staged_walker) {
-    __shared__ int s_list[SUM_THREADS];
+    __shared__ int s_list[SUM_THREADS], s_rec[SUM_THREADS];
     __shared__ int s_wcount[SUM_THREADS / 32];
     __shared__ int s_nsub;
 
@@ -1273,13 +1282,12 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     const double *coeff = p.coeff + wd.coeff_off;
     const double *gq = p.gq + 16 * wd.teuk_off;
 
-    // dynamic smem: accumulators [4][BPT][ACC_STRIDE] | sub-entries | fill entries | sF | sX | knots (t, f_phi, f_r)[L]
+    // dynamic smem: accumulators [4][BPT][ACC_STRIDE] | sub-entries | fill entries | sF | knots (t, f_phi, f_r)[L]
     double *acc = reinterpret_cast<double *>(smraw);
     SubEntry *sub = reinterpret_cast<SubEntry *>(acc + 4 * BPT * ACC_STRIDE);
     FillEntry *ent = reinterpret_cast<FillEntry *>(sub + SUM_SUBCAP);
     double *sF = reinterpret_cast<double *>(ent + SUM_ECAP); // exact bin frequencies             [BPT][SUM_THREADS]
-    double *sX = sF + BPT * SUM_THREADS;                     // roots of the current sub-entry   [BPT][SUM_THREADS]
-    double *sK = sX + BPT * SUM_THREADS;
+    double *sK = sF + BPT * SUM_THREADS;
     // ---- does any work-list chunk touch this tile? ----
     const int nrec = G * MAXBR;
     const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
@@ -1288,6 +1296,16 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     if (p.wstatus[walker_y]) any = false; // failed walker: zeros (and a NaN likelihood from like_finalize_kernel)
     // (direct-grid launches only: empty_tile_kernel has dealt with this tile)
     if (!any && !(LIKE && (p.no_empty || tile_truncated(p, jt0, SUM_THREADS * BPT)))) return;
+    if (LIKE) { // the read-out's data lines: start them towards L2 now (a third of them come from DRAM)
+        const int lb0 = wid * (32 * BPT) + lane * BPT; // BPT consecutive bins of the warp's read-out range per lane
+        if (jt0 + lb0 <= jt1) {
+            const long long j = jt0 + lb0;
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + j));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + p.n_data + j));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + j));
+            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + p.n_data + j));
+        }
+    }
 #pragma unroll
     for (int i = 0; i < 4 * BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
 #pragma unroll
@@ -1317,9 +1335,10 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
         // ---- ordered compaction of this chunk's group records that overlap the tile ----
         const int r = base + tid;
         bool pred = false;
+        int rec = 0;
         if (r < nrec) {
-            const emrifd_branch_t *b = br + leader[r / MAXBR] * MAXBR + (r % MAXBR);
-            const long long s0 = b->start, e0 = b->end;
+            rec = leader[r / MAXBR] * MAXBR + (r % MAXBR);
+            const long long s0 = br[rec].start, e0 = br[rec].end;
             pred = (e0 >= s0) && ((s0 <= pos_hi && e0 >= pos_lo) || (s0 <= neg_hi && e0 >= neg_lo));
         }
         const unsigned bal = __ballot_sync(0xffffffffu, pred);
@@ -1329,29 +1348,25 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
         int off = 0, count = 0;
 #pragma unroll
         for (int q = 0; q < SUM_THREADS / 32; q++) { const int c = s_wcount[q]; if (q < wid) off += c; count += c; }
-        if (pred) s_list[off + __popc(bal & ((1u << lane) - 1))] = r;
+        if (pred) { const int pos = off + __popc(bal & ((1u << lane) - 1)); s_list[pos] = r; s_rec[pos] = rec; }
         __syncthreads();
         used = false;
         for (int g0 = 0; g0 < count; g0 += SUM_ECAP) { // the overlap list is handled in rounds of one record per fill-warp lane
             const int gcount = count - g0 < SUM_ECAP ? count - g0 : SUM_ECAP;
             if (used) __syncthreads(); // every warp is done with the previous round's sub-entries
             if (wid == 0) {
-                const int tot = fill_entries<BPT>(leader, br, p.m + wd.mode_off, p.n + wd.mode_off, p.include_minus_m, zero, s_list + g0,
-                                                  gcount, jt0, jt1, sF, sK, ent);
+                const int tot = fill_entries<BPT>(br, p.m + wd.mode_off, p.n + wd.mode_off, p.include_minus_m, zero, s_list + g0,
+                                                  s_rec + g0, gcount, jt0, jt1, sF, sK, ent);
                 if (lane == 0) s_nsub = tot;
-                __syncwarp();
-                fill_subs<BPT>(coeff, gq, wd.K, G, gcount, 0, sF, sK, ent, sub);
             }
             __syncthreads();
             used = true;
             const int tot = s_nsub;
             for (int w0 = 0; w0 < tot; w0 += SUM_SUBCAP) {
-                if (w0 > 0) {
-                    __syncthreads();
-                    if (wid == 0) fill_subs<BPT>(coeff, gq, wd.K, G, gcount, w0, sF, sK, ent, sub);
-                    __syncthreads();
-                }
                 const int nsw = tot - w0 < SUM_SUBCAP ? tot - w0 : SUM_SUBCAP;
+                if (w0 > 0) __syncthreads(); // the previous pass has been evaluated
+                fill_subs<BPT>(coeff, gq, wd.K, G, gcount, w0, nsw, sF, sK, ent, sub); // one thread per sub-entry
+                __syncthreads();
                 if (nb <= 0) continue;
                 // ---- evaluate: every thread walks its BPT consecutive bins along each listed cubic piece ----
                 const int tb0 = tid * BPT;
@@ -1362,24 +1377,25 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
                     const int bh = e_ - tb0 < nb - 1 ? e_ - tb0 : nb - 1;
                     if (bl > bh) continue;
                     const unsigned int smask = S.fmask;
-                    const int fl = S.flags;
-                    const double c0 = S.c0, c1 = S.c1, c2 = S.c2, c3 = S.c3;
-                    const double d2 = 2.0 * c2, d3 = 3.0 * c3;
-                    // ---- stage 1: roots.  First bin through the out-of-line cold solve; the others by second-order extrapolation
-                    //      from a solved bin + ONE Newton step, two at a time (independent chains); a bin that misses the tolerance
-                    //      or the bracket goes through the cold solve ----
-                    {
-                        const double xlo = S.xlo, xhi = S.xhi, tol = S.tol;
-                        const double sdir = (fl & SE_FALL) ? -1.0 : 1.0;
-                        const double *pF = sF + tid + bl * SUM_THREADS;
-                        double *pX = sX + tid + bl * SUM_THREADS;
-                        double fb = flip_sign(pF[0], smask);
-                        double xb = solve_slow(c1, c2, c3, fb - c0, xlo, xhi, tol, sdir);
-                        double rb = fast_rcp(fma(xb, fma(d3, xb, d2), c1));
-                        pX[0] = xb;
-                        for (int b = bl + 1; b <= bh; b += 2) {
-                            pF += SUM_THREADS; pX += SUM_THREADS;
-                            const bool two = b < bh;
+                    const int side = S.flags & SE_SIDE;
+                    const double sdir = (S.flags & SE_FALL) ? -1.0 : 1.0;
+                    const double c1 = S.c1;
+                    const double d2 = 2.0 * S.c2, d3 = 3.0 * S.c3;
+                    const double *pF = sF + tid + bl * SUM_THREADS;
+                    int id0 = side * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE;       // direct term -> this side
+                    int im0 = (1 - side) * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE; // mirrored -m term -> other side
+                    // The thread's first bin goes through the out-of-line cold solve; after that the bins are taken two at a
+                    // time: roots by second-order extrapolation from the last solved bin + ONE Newton step (two independent
+                    // chains; a bin that misses the tolerance or the bracket falls back to the cold solve), then both bins are
+                    // evaluated in straight-line code.  (In the first pair the first bin's extrapolation step is zero.)
+                    double fb = flip_sign(pF[0], smask);
+                    double xb = solve_slow(c1, S.c2, S.c3, fb - S.c0, S.xlo, S.xhi, S.tol, sdir);
+                    double rb = fast_rcp(fma(xb, fma(d3, xb, d2), c1));
+                    for (int b = bl; b <= bh; b += 2) {
+                        const bool two = b < bh;
+                        double xx[2], ff[2];
+                        {
+                            const double c0 = S.c0, c2 = S.c2, c3 = S.c3, xlo = S.xlo, xhi = S.xhi, tol = S.tol;
                             const double f1 = flip_sign(pF[0], smask);
                             const double f2 = two ? flip_sign(pF[SUM_THREADS], smask) : f1;
                             const double kap = fma(2.0 * d3, xb, d2) * rb; // fddot/fdot at the solved bin
@@ -1394,38 +1410,21 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
                                 x1 = solve_slow(c1, c2, c3, f1 - c0, xlo, xhi, tol, sdir);
                                 r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1));
                             }
-                            pX[0] = x1;
-                            if (two) {
-                                if (!(fabs(dx2) <= tol && x2 >= xlo && x2 <= xhi)) {
-                                    x2 = solve_slow(c1, c2, c3, f2 - c0, xlo, xhi, tol, sdir);
-                                    r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
-                                }
-                                pX[SUM_THREADS] = x2;
-                                xb = x2; fb = f2; rb = r2;
-                                pF += SUM_THREADS; pX += SUM_THREADS;
+                            if (two && !(fabs(dx2) <= tol && x2 >= xlo && x2 <= xhi)) {
+                                x2 = solve_slow(c1, c2, c3, f2 - c0, xlo, xhi, tol, sdir);
+                                r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
                             }
+                            xx[0] = x1; xx[1] = x2; ff[0] = f1; ff[1] = f2;
+                            xb = two ? x2 : x1; fb = f2; rb = two ? r2 : r1;
                         }
-                    }
-                    // ---- stage 2: evaluate the bins two at a time in straight-line code ----
-                    {
-                        const int side = fl & SE_SIDE;
-                        const double *pF = sF + tid + bl * SUM_THREADS;
-                        const double *pX = sX + tid + bl * SUM_THREADS;
-                        int id0 = side * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE;       // direct term -> this side
-                        int im0 = (1 - side) * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE; // mirrored -m term -> other side
-                        for (int b = bl; b <= bh; b += 2) {
-                            if (b < bh) {
-                                const double x2[2] = {pX[0], pX[SUM_THREADS]};
-                                const double f2[2] = {flip_sign(pF[0], smask), flip_sign(pF[SUM_THREADS], smask)};
-                                eval_sub<2, BPT>(x2, f2, c1, d2, d3, S, p.k13_few, acc, id0, im0);
-                            } else {
-                                const double x1[1] = {pX[0]};
-                                const double f1[1] = {flip_sign(pF[0], smask)};
-                                eval_sub<1, BPT>(x1, f1, c1, d2, d3, S, p.k13_few, acc, id0, im0);
-                            }
-                            pF += 2 * SUM_THREADS; pX += 2 * SUM_THREADS;
-                            id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
+                        if (two) {
+                            eval_sub<2, BPT>(xx, ff, c1, d2, d3, S, p.k13_few, acc, id0, im0);
+                        } else {
+                            const double x1[1] = {xx[0]}, f1[1] = {ff[0]};
+                            eval_sub<1, BPT>(x1, f1, c1, d2, d3, S, p.k13_few, acc, id0, im0);
                         }
+                        pF += 2 * SUM_THREADS;
+                        id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
                     }
                 }
             }
@@ -1436,46 +1435,61 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
     // Warp-local transposed read-out: a warp owns 32*BPT consecutive bins (its lanes' bins); in iteration i lane l
     // finalises bin 32*i + l of them, so the warp stores 512 contiguous bytes per array and reads the data stream the
     // same way.  Only __syncwarp is needed: warps that finish early read out while the others still evaluate.
+    // The data loads of a group of iterations are issued together, ahead of the stores (which could alias them for all the
+    // compiler knows), so their latencies overlap.
     __syncwarp();
     double a0 = 0, a1 = 0, a2 = 0;
     const int ntile = (int)(jt1 - jt0 + 1);
+    constexpr int RG = BPT % 3 == 0 ? 3 : (BPT % 2 == 0 ? 2 : 1); // read-out group
 #pragma unroll
-    for (int i = 0; i < BPT; i++) {
-        const int lb = wid * (32 * BPT) + i * 32 + lane;
-        if (lb >= ntile) continue;
-        const long long j = jt0 + lb;
-        const int own = lb / BPT, bb = lb % BPT;
-        const double *ap = acc + bb * ACC_STRIDE + own;
-        double wpr = ap[0], wpi = ap[BPT * ACC_STRIDE], wmr = ap[2 * BPT * ACC_STRIDE], wmi = ap[3 * BPT * ACC_STRIDE];
-        if (j == 0) { wpr += wmr; wpi += wmi; wmr = wpr; wmi = wpi; }
-        const double pr_ = 0.5 * (-wmr - wpr), pi_ = 0.5 * (-wmi + wpi);
-        const double xr_ = 0.5 * (wmi + wpi), xi_ = 0.5 * (-wmr + wpr);
-        const double sc = wd.scale, c2 = wd.cos2psi, s2 = wd.sin2psi;
-        const double hpr = sc * (c2 * pr_ - s2 * xr_), hpi = sc * (c2 * pi_ - s2 * xi_);
-        const double hxr = sc * (s2 * pr_ + c2 * xr_), hxi = sc * (s2 * pi_ + c2 * xi_);
-        if (WRITE_H) {
-            if (p.mask_positive) {
-                const long long o = wd.out_off + (j - p.j_lo);
-                p.hp[o] = make_double2(hpr, hpi);
-                p.hc[o] = make_double2(hxr, hxi);
-            } else {
-                const long long o = wd.out_off + zero;
-                p.hp[o + j] = make_double2(hpr, hpi);
-                p.hc[o + j] = make_double2(hxr, hxi);
-                if (j > 0) { // Hermitian mirror: h(-f) = conj h(f)
-                    p.hp[o - j] = make_double2(hpr, -hpi);
-                    p.hc[o - j] = make_double2(hxr, -hxi);
-                }
+    for (int i0 = 0; i0 < BPT; i0 += RG) {
+        double2 d0[RG], d1[RG];
+        double w0[RG], w1[RG];
+        if (LIKE) {
+#pragma unroll
+            for (int ii = 0; ii < RG; ii++) {
+                const int lb = wid * (32 * BPT) + (i0 + ii) * 32 + lane;
+                const long long j = jt0 + (lb < ntile ? lb : 0);
+                d0[ii] = p.dw[j]; d1[ii] = p.dw[p.n_data + j];
+                w0[ii] = p.wf[j]; w1[ii] = p.wf[p.n_data + j];
             }
         }
-        if (LIKE) {
-            const double2 d0 = p.dw[j], d1 = p.dw[p.n_data + j];
-            const double w0 = p.wf[j], w1 = p.wf[p.n_data + j];
-            const double h0r = hpr * w0, h0i = hpi * w0, h1r = hxr * w1, h1i = hxi * w1;
-            const double r0 = d0.x - h0r, i0 = d0.y - h0i, r1 = d1.x - h1r, i1 = d1.y - h1i;
-            a0 += r0 * r0 + i0 * i0 + r1 * r1 + i1 * i1;
-            a1 += d0.x * h0r + d0.y * h0i + d1.x * h1r + d1.y * h1i;
-            a2 += h0r * h0r + h0i * h0i + h1r * h1r + h1i * h1i;
+#pragma unroll
+        for (int ii = 0; ii < RG; ii++) {
+            const int lb = wid * (32 * BPT) + (i0 + ii) * 32 + lane;
+            if (lb >= ntile) continue;
+            const long long j = jt0 + lb;
+            const int own = lb / BPT, bb = lb % BPT;
+            const double *ap = acc + bb * ACC_STRIDE + own;
+            double wpr = ap[0], wpi = ap[BPT * ACC_STRIDE], wmr = ap[2 * BPT * ACC_STRIDE], wmi = ap[3 * BPT * ACC_STRIDE];
+            if (j == 0) { wpr += wmr; wpi += wmi; wmr = wpr; wmi = wpi; }
+            const double pr_ = 0.5 * (-wmr - wpr), pi_ = 0.5 * (-wmi + wpi);
+            const double xr_ = 0.5 * (wmi + wpi), xi_ = 0.5 * (-wmr + wpr);
+            const double sc = wd.scale, c2 = wd.cos2psi, s2 = wd.sin2psi;
+            const double hpr = sc * (c2 * pr_ - s2 * xr_), hpi = sc * (c2 * pi_ - s2 * xi_);
+            const double hxr = sc * (s2 * pr_ + c2 * xr_), hxi = sc * (s2 * pi_ + c2 * xi_);
+            if (WRITE_H) {
+                if (p.mask_positive) {
+                    const long long o = wd.out_off + (j - p.j_lo);
+                    p.hp[o] = make_double2(hpr, hpi);
+                    p.hc[o] = make_double2(hxr, hxi);
+                } else {
+                    const long long o = wd.out_off + zero;
+                    p.hp[o + j] = make_double2(hpr, hpi);
+                    p.hc[o + j] = make_double2(hxr, hxi);
+                    if (j > 0) { // Hermitian mirror: h(-f) = conj h(f)
+                        p.hp[o - j] = make_double2(hpr, -hpi);
+                        p.hc[o - j] = make_double2(hxr, -hxi);
+                    }
+                }
+            }
+            if (LIKE) {
+                const double h0r = hpr * w0[ii], h0i = hpi * w0[ii], h1r = hxr * w1[ii], h1i = hxi * w1[ii];
+                const double r0 = d0[ii].x - h0r, q0 = d0[ii].y - h0i, r1 = d1[ii].x - h1r, q1 = d1[ii].y - h1i;
+                a0 += r0 * r0 + q0 * q0 + r1 * r1 + q1 * q1;
+                a1 += d0[ii].x * h0r + d0[ii].y * h0i + d1[ii].x * h1r + d1[ii].y * h1i;
+                a2 += h0r * h0r + h0i * h0i + h1r * h1r + h1i * h1i;
+            }
         }
     }
     if (LIKE) { // per-warp partial sums (no CTA barrier); like_finalize_kernel adds them in a fixed order
@@ -1890,7 +1904,7 @@ static size_t spline_smem_bytes(int L, bool tiled) {
 
 static size_t sum_smem_bytes(int L, int bpt = SUM_BPT) {
     return sizeof(double) * 4 * bpt * ACC_STRIDE + sizeof(SubEntry) * SUM_SUBCAP + sizeof(FillEntry) * SUM_ECAP +
-           2 * sizeof(double) * bpt * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
+           sizeof(double) * bpt * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
 
 static int ensure_bytes(emrifd_handle *h, void **ptr, int64_t *cap, int64_t need, bool pinned_host = false) {
@@ -1985,7 +1999,7 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     for (int i = 0; i < 64; i++) ok &= cudaEventCreate(&h->ev_a[i]) == cudaSuccess && cudaEventCreate(&h->ev_b[i]) == cudaSuccess;
     int optin = 0;
     ok &= cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess;
-    const int big = optin - 2048; // static smem of the kernel (< 2 KB) comes out of the same budget
+    const int big = optin - 4096; // static smem of the kernels (< 4 KB) comes out of the same budget
     h->max_dyn_smem = big;
     ok &= cudaDeviceGetAttribute(&h->num_sms, cudaDevAttrMultiProcessorCount, device) == cudaSuccess && h->num_sms > 0;
 #define SET_ATTR(F_, BYTES_) ok &= cudaFuncSetAttribute(F_, cudaFuncAttributeMaxDynamicSharedMemorySize, BYTES_) == cudaSuccess

@@ -97,6 +97,20 @@ class DeviceBatch:
         return self.coeff[o:o + L * R * 4].cpu().numpy().reshape(L, R, 4)
 
 
+def group_evaluations(db):
+    """Stationary points the mode sum actually solves: one per ((m, n) group, bin), i.e. the work-list records of the first
+    mode of every distinct (m, n) pair of a walker (csrc/emrifd.cu group_kernel).  Returns an int64 array [B]."""
+    br = db.branches_host()
+    m, n = db.m.cpu().numpy(), db.n.cpu().numpy()
+    per_mode = np.where(br["end"] >= br["start"], br["end"] - br["start"] + 1, 0).sum(axis=1)
+    out = np.zeros(db.pb.B, dtype=np.int64)
+    for i, w in enumerate(db.pb.walkers):
+        o, K = int(w["mode_off"]), int(w["K"])
+        _, first = np.unique(np.stack([m[o:o + K], n[o:o + K]], axis=1), axis=0, return_index=True)
+        out[i] = per_mode[o:o + K][first].sum()
+    return out
+
+
 def grid_from_frequency(frequency):
     """Validate a two-sided frequency array: odd length, symmetric, one zero in the middle
     (FDInterpolatedModeSum asserts exactly one zero; emri_pe.py:339-342 builds f_arr this way).
