@@ -106,6 +106,7 @@ class Handle:
         if stream is None:
             stream = torch.cuda.current_stream(self.torch_device).cuda_stream
         self.stream = int(stream)
+        self.data_owner = None      # the object whose injected data emrifd_set_data last pointed this handle at
         hp = C.c_void_p()
         rc = self.lib.emrifd_create(self.device, C.c_void_p(self.stream), C.byref(hp))
         if rc != 0:
@@ -172,7 +173,14 @@ def get_handle(device=None):
     key = (os.getpid(), int(device))
     if key not in _handles:
         _handles[key] = Handle(device)
-    return _handles[key]
+    h = _handles[key]
+    # follow torch's CURRENT stream (a `with torch.cuda.stream(s):` block, a non-default-stream worker): tensors are allocated
+    # and uploaded on it by the Python layer, so the kernels must be ordered on it too
+    cur = int(torch.cuda.current_stream(h.torch_device).cuda_stream)
+    if cur != h.stream:
+        h.check(h.lib.emrifd_set_stream(h.h, C.c_void_p(cur)))
+        h.stream = cur
+    return h
 
 
 def ptr(x):

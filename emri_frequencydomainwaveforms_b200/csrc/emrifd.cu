@@ -1661,7 +1661,7 @@ struct SelParams {
     const int *samp_walker;  // [nsamp]
     const double2 *ylm;      // [B][M + Mneg]
     const int *neg_src;      // [Mneg] index of the +m mode each -m copy belongs to
-    int M, Mneg;
+    int M, Mneg, B;
     double eps;
     unsigned char *flags;    // [B][M], zero-initialised by the caller
 };
@@ -1682,6 +1682,7 @@ __global__ void __launch_bounds__(SEL_THREADS) mode_select_kernel(SelParams p) {
     __shared__ double s_total;
     __shared__ int s_count, s_end;
     const int samp = blockIdx.x, w = p.samp_walker[samp], Mtot = p.M + p.Mneg;
+    if (w < 0 || w >= p.B) return; // a sample that names no walker of the batch is ignored (never an out-of-bounds flag write)
     const double2 *A = p.teuk + (long long)samp * p.M;
     const double2 *Y = p.ylm + (long long)w * Mtot;
     double part = 0.0;
@@ -2468,7 +2469,7 @@ int emrifd_mode_select(emrifd_handle_t *h, const double *teuk, int64_t nsamp, in
     cudaSetDevice(h->device);
     SelParams p;
     p.teuk = (const double2 *)teuk; p.samp_walker = samp_walker; p.ylm = (const double2 *)ylm; p.neg_src = neg_src;
-    p.M = (int)M; p.Mneg = (int)Mneg; p.eps = eps; p.flags = flags;
+    p.M = (int)M; p.Mneg = (int)Mneg; p.B = (int)B; p.eps = eps; p.flags = flags;
     CUDA_TRY(h, cudaMemsetAsync(flags, 0, (size_t)(B * M), h->stream));
     const size_t smem = SEL_CAP * (sizeof(double) + sizeof(unsigned short));
     mode_select_kernel<<<(unsigned)nsamp, SEL_THREADS, smem, h->stream>>>(p);

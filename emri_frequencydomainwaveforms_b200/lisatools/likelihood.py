@@ -23,7 +23,7 @@ class FDTemplateModel:
         self.gen = waveform_generator
         self.base = waveform_generator.waveform_generator       # FastSchwarzschildEccentricFlux
         self._device = device
-        self._data_key = None
+        self._data_ref = None
         self._data = None
         self.f_arr = f_arr
         self.last_h2d_bytes = 0
@@ -43,7 +43,10 @@ class FDTemplateModel:
         kw = dict(kwargs)
         kw.pop("mask_positive", None)
         out = self.gen(*params, mask_positive=True, **kw)
-        return [out[0], out[1]] if isinstance(out, (list, tuple)) else [out.real, -out.imag]
+        if not isinstance(out, (list, tuple)):
+            # h+ - i hx of two COMPLEX frequency-domain channels cannot be split back into them
+            raise ValueError("FDTemplateModel needs a generator built with return_list=True (frequency-domain h+, hx are complex).")
+        return [out[0], out[1]]
 
     # ---- host producers for a batch of full parameter vectors [nb, 14] ----------------------------
     def prepare_batch(self, params, T=1.0, dt=10.0, eps=1e-5, mode_selection=None, **kwargs):
@@ -64,10 +67,13 @@ class FDTemplateModel:
     def set_data(self, data, noise_factor):
         """data: whitened injection channels [2][n]; noise_factor [2][n] (likelihood.py:213-220)."""
         import torch
-        key = (id(data), id(noise_factor))
-        if key == self._data_key:
-            return
         h = self.handle
+        # The injected data live on the (process-wide, per-device) handle: another model or a Likelihood may have replaced
+        # them since this model's last call.  Re-upload unless this model still owns the handle's data AND is handed the very
+        # same objects (held by reference, so their ids cannot be recycled).
+        same = self._data_ref is not None and self._data_ref[0] is data and self._data_ref[1] is noise_factor
+        if same and getattr(h, "data_owner", None) is self:
+            return
         to_np = lambda x: x.detach().cpu().numpy() if torch.is_tensor(x) else np.asarray(x)
         d = np.ascontiguousarray(np.stack([to_np(c) for c in data]), dtype=np.complex128)
         w = np.ascontiguousarray(np.stack([to_np(c) for c in noise_factor]), dtype=np.float64)
@@ -82,7 +88,8 @@ class FDTemplateModel:
         dd = torch.from_numpy(d.view(np.float64)).to(h.torch_device)
         ww = torch.from_numpy(w).to(h.torch_device)
         h.check(h.lib.emrifd_set_data(h.h, dd.data_ptr(), ww.data_ptr(), d.shape[1]))
-        self._data, self._data_key, self.n_data = (dd, ww), key, d.shape[1]
+        self._data, self._data_ref, self.n_data = (dd, ww), (data, noise_factor), d.shape[1]
+        h.data_owner = self
 
     def get_ll(self, params, data=None, noise_factor=None, T=1.0, dt=10.0, eps=1e-5, f_arr=None,
                include_minus_m=True, mode_selection=None, N=None, **kwargs):
@@ -96,14 +103,16 @@ class FDTemplateModel:
         if self._data is None:
             raise ValueError("No data set: pass (data, noise_factor) or call set_data first.")
         h = self.handle
+        if getattr(h, "data_owner", None) is not self:     # someone else used the handle since: point it back at this model's data
+            h.check(h.lib.emrifd_set_data(h.h, self._data[0].data_ptr(), self._data[1].data_ptr(), self.n_data))
+            h.data_owner = self
         f_arr = self.f_arr if f_arr is None else f_arr
         if f_arr is not None:
             f_host = f_arr.detach().cpu().numpy() if torch.is_tensor(f_arr) else np.asarray(f_arr)
             Ngrid, fpos = engine.grid_from_frequency(f_host)
-            key = ("fpos", id(f_arr))
-            if getattr(self, "_fpos_key", None) != key:
+            if getattr(self, "_fpos_ref", None) is not f_arr:     # cached by reference (an id() could be recycled)
                 self._fpos_dev = torch.from_numpy(fpos).to(h.torch_device)
-                self._fpos_key = key
+                self._fpos_ref = f_arr
             fpos_dev, val = self._fpos_dev, 0.0
         else:
             Ngrid = 2 * self.n_data - 1 if N is None else int(N)
@@ -124,7 +133,10 @@ class FDTemplateModel:
             if db is not None:
                 self.last_h2d_bytes = db.h2d_bytes
                 out = engine.run_loglike(db, Ngrid, val, fpos_dev, include_minus_m=include_minus_m).cpu().numpy()
-                h.status()
+                # a walker the device refused (non-monotone knots, too many branches) comes back as NaN -- Eryn maps that to
+                # -1e300 (Eryn/eryn/moves/red_blue.py:282-284); the other walkers of the batch are unaffected
+                self.last_walker_status = np.zeros(len(ok), dtype=np.int32)
+                self.last_walker_status[ok] = h.walker_status(db.pb.B)
                 ll[ok] = out[:, 0]
                 self.last_dh_hh = out[:, 1:]
             return ll
@@ -134,6 +146,8 @@ class FDTemplateModel:
             pb = engine.PackedBatch(items)
             self.last_h2d_bytes = pb.h2d_bytes()
             out = engine.run_loglike_host(pb, h, Ngrid, val, fpos_dev, include_minus_m=include_minus_m)
+            self.last_walker_status = np.zeros(len(ok), dtype=np.int32)
+            self.last_walker_status[ok] = h.walker_status(pb.B)
             ll[ok] = out[:, 0]
             self.last_dh_hh = out[:, 1:]
         return ll
@@ -243,6 +257,7 @@ class Likelihood:
             raise ValueError("templates must be [num_likes, 2, data_length]")
         out = torch.empty((B, 3), dtype=torch.float64, device=h.torch_device)
         h.check(h.lib.emrifd_set_data(h.h, self._d_dev.data_ptr(), self._w_dev.data_ptr(), self.data_length))
+        h.data_owner = self
         h.check(h.lib.emrifd_loglike(h.h, tm.data_ptr(), B, out.data_ptr()))
         return np.atleast_1d(out[:, 0].cpu().numpy())
 

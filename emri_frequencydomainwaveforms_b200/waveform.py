@@ -23,6 +23,24 @@ from .utils.utility import fundamental_frequencies_hz
 from .utils.ylm import GetYlms
 
 
+_warned_standins = False
+
+
+def _warn_standins(traj, amp):
+    """One warning per process: the class keeps FEW's name, but its DEFAULT producers are offline stand-ins."""
+    global _warned_standins
+    if _warned_standins:
+        return
+    _warned_standins = True
+    import warnings
+    what = " and ".join(w for w, on in (("trajectory (leading-order Peters fluxes + exact geodesic frequencies)", traj),
+                                        ("amplitudes (SyntheticAmplitude, FEW's 3843-mode layout)", amp)) if on)
+    warnings.warn("FastSchwarzschildEccentricFlux is using this package's stand-in " + what + ": FastEMRIWaveforms' flux grid and "
+                  "ROMAN amplitude weights are Zenodo downloads that are not available here, so waveforms differ physically from "
+                  "few's.  Pass inspiral_generator= / amplitude_generator= (any objects with few's call signatures) to use the "
+                  "real producers; the frequency-domain summation and likelihood below them are unchanged.", UserWarning, stacklevel=3)
+
+
 class FastSchwarzschildEccentricFlux:
     """Schwarzschild eccentric FD waveform in the source frame (mirror of few.waveform's class)."""
 
@@ -37,6 +55,8 @@ class FastSchwarzschildEccentricFlux:
         if sk.get("output_type", "td") != "fd":
             raise ValueError("This package implements the frequency-domain path only: pass "
                              "sum_kwargs=dict(output_type='fd', ...).")
+        if inspiral_generator is None or amplitude_generator is None:
+            _warn_standins(inspiral_generator is None, amplitude_generator is None)
         self.inspiral_generator = inspiral_generator or EMRIInspiral(func="SchwarzEccFlux")
         self.amplitude_generator = amplitude_generator or SyntheticAmplitude()
         amp = self.amplitude_generator

@@ -297,6 +297,12 @@ int orc_segment_build(const double *t, const double *coeff, int L, int K,
 /* SPA factor: R(X) = K_{1/3}(-iX) e^{-iX} sqrt(2X/pi) e^{-i pi/4}      */
 /* and S(X) = R(X)/X^{1/6} for the small-X (turnover) regime            */
 /* ------------------------------------------------------------------ */
+/* K_{1/3} evaluation mode: 0 = math-exact (default); 1 = FastEMRIWaveforms-compatible ([UPSTREAM-MEMORY]):
+   14-term ascending series (to X^26) for |X| <= 7 and the 9-term asymptotic series above -- 2.5e-7 off at the seam. */
+static int g_k13_few = 0;
+void orc_set_k13_mode(int few) { g_k13_few = few != 0; }
+int orc_get_k13_mode(void) { return g_k13_few; }
+
 static void k13_series_S(real Xr, real *Sre, real *Sim) {
     /* S = sqrt(2pi/3) e^{-i pi/4} e^{-iX} [2^{1/3} e^{i pi/6} B - 2^{-1/3} X^{2/3} e^{-i pi/6} A]
        A = sum (-X^2/4)^k/(k! Gamma(k+4/3)),  B = sum (-X^2/4)^k/(k! Gamma(k+2/3))
@@ -307,11 +313,12 @@ static void k13_series_S(real Xr, real *Sre, real *Sim) {
     const qreal G23 = 1.354117939426400416945288028154513785Q; /* Gamma(2/3) */
     qreal q = -X * X / 4.0Q;
     qreal ta = 1.0Q / G43, tb = 1.0Q / G23, A = ta, B = tb;
-    for (int k = 1; k < 400; k++) {
+    const int kmax = g_k13_few ? 14 : 400; /* FEW mode: exactly 14 terms of each series */
+    for (int k = 1; k < kmax; k++) {
         ta *= q / ((qreal)k * ((qreal)k + 1.0Q / 3.0Q));
         tb *= q / ((qreal)k * ((qreal)k - 1.0Q / 3.0Q));
         A += ta; B += tb;
-        if (k > (int)(Xr) + 2 && fabsq(ta) < 1e-40Q * fabsq(A) && fabsq(tb) < 1e-40Q * fabsq(B)) break;
+        if (!g_k13_few && k > (int)(Xr) + 2 && fabsq(ta) < 1e-40Q * fabsq(A) && fabsq(tb) < 1e-40Q * fabsq(B)) break;
     }
     qreal c13 = cbrtq(2.0Q);
     qreal x23 = cbrtq(X); x23 *= x23;
@@ -331,11 +338,12 @@ static void k13_asym_R(real X, real *Rre, real *Rim) {
     real a = R_(1.0), u = R_(1.0) / X, p = R_(1.0);
     real re = R_(1.0), im = R_(0.0);
     real last = R_(1.0);
-    for (int k = 1; k < ASYM_TERMS; k++) {
+    const int nterms = g_k13_few ? 9 : ASYM_TERMS; /* FEW mode: a_0 .. a_8, no optimal truncation */
+    for (int k = 1; k < nterms; k++) {
         a *= (R_(4.0) / R_(9.0) - (real)((2 * k - 1) * (2 * k - 1))) / (R_(8.0) * (real)k);
         p *= u;
         real term = a * p;
-        if (r_fabs(term) > r_fabs(last)) break; /* optimal truncation */
+        if (!g_k13_few && r_fabs(term) > r_fabs(last)) break; /* optimal truncation */
         last = term;
         switch (k & 3) {
             case 0: re += term; break;
@@ -350,7 +358,7 @@ static void k13_asym_R(real X, real *Rre, real *Rim) {
 /* returns R(X) for X >= 1 regime and S(X) = R/X^{1/6} always; which!=0 => small branch used */
 void orc_spa_R(double Xd, double *Rre, double *Rim) {
     real X = (real)Xd, re, im;
-    if (X < (real)SERIES_XMAX) {
+    if (X < (g_k13_few ? (real)7.0 : (real)SERIES_XMAX)) {
         k13_series_S(X, &re, &im);
         real x16 = r_sqrt(r_cbrt(X));
         re *= x16; im *= x16;
@@ -377,7 +385,7 @@ static void spa_G(real fdot, real fddot, real *Gre, real *Gim) {
             real sc = r_cbrt(r_sqrt(R_(2.0) * ORC_PI / R_(3.0)) / r_fabs(fddot));
             re *= sc; im *= sc;
         } else {
-            if (X < (real)SERIES_XMAX) {
+            if (X < (g_k13_few ? (real)7.0 : (real)SERIES_XMAX)) {
                 k13_series_S(X, &re, &im);
                 real x16 = r_sqrt(r_cbrt(X)); re *= x16; im *= x16;
             }

@@ -22,8 +22,9 @@ BRANCH_DTYPE = np.dtype([
 
 def build(force=False):
     """Compile the oracle with its Makefile (gcc, -ffp-contract=off)."""
-    need = force or not all(os.path.exists(os.path.join(_BUILD, f))
-                            for f in ("liboracle_f64.so", "liboracle_quad.so"))
+    src = os.path.join(_HERE, "emrifd_oracle.c")
+    libs = [os.path.join(_BUILD, f) for f in ("liboracle_f64.so", "liboracle_quad.so")]
+    need = force or not all(os.path.exists(f) and os.path.getmtime(f) >= os.path.getmtime(src) for f in libs)
     if need:
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
 
@@ -53,6 +54,12 @@ class Oracle:
         L.orc_loglike.argtypes = [_dp, _dp, _dp, C.c_int, C.c_int64, _dp]
         L.orc_spa_R.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
         L.orc_spa_S.argtypes = [C.c_double, C.POINTER(C.c_double), C.POINTER(C.c_double)]
+        L.orc_set_k13_mode.argtypes = [C.c_int]
+
+    def set_k13_mode(self, mode):
+        """"exact" (default) or "few": FastEMRIWaveforms' SPAFunc truncations (14-term ascending series for |X| <= 7, 9-term
+        asymptotic above; SURVEY.md A.2 [UPSTREAM-MEMORY])."""
+        self.lib.orc_set_k13_mode({"exact": 0, "few": 1}[mode])
 
     # -- A3 ---------------------------------------------------------------------------------
     def spline_build(self, t, y):

@@ -1,6 +1,7 @@
 """CPU tests of the host logic and of the C-ABI library's export table (no compute without a GPU)."""
 import ctypes
 import os
+import sys
 import re
 
 import numpy as np
@@ -232,3 +233,54 @@ def test_bench_reference_arm_prints_one_json_line():
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["cores"] >= 1 and d["cpu_baseline"]["value"] == d["value"]
     assert d["e2e"] == {"value": d["value"], "unit": "walkers/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in d["config"] and "model" not in d["config"]
+
+
+def test_reference_likelihood_adopts_the_plugin():
+    """The reference's OWN Likelihood (LISAanalysistools/lisatools/sampling/likelihood.py) hands the whole batch to a template
+    model that has ``get_ll`` (:70-72) and, with fill_data_noise=True, appends (injection_channels, noise_factor) (:330-331).
+    A stub with FDTemplateModel's ``get_ll`` signature records what it is called with: parameters already filled / transformed
+    by eryn's TransformContainer, subset chunking, the whitened data and noise factor of inject_signal, the waveform kwargs."""
+    ref = "/root/reference"
+    if not os.path.isdir(ref):
+        pytest.skip("/root/reference is not on this machine")
+    import inspect
+    for sub in ("LISAanalysistools", "Eryn"):
+        if os.path.join(ref, sub) not in sys.path:
+            sys.path.insert(0, os.path.join(ref, sub))
+    from lisatools.sampling.likelihood import Likelihood as RefLikelihood
+    from eryn.utils import TransformContainer
+    from emri_frequencydomainwaveforms_b200.lisatools.likelihood import FDTemplateModel
+
+    calls = []
+
+    class Stub:
+        def __call__(self, *params, **kw):          # used once by inject_signal(params=...): [h+, hx] on f >= 0
+            n = 64
+            return [np.full(n, params[0] * 1e-30 + 0j), np.full(n, params[1] * 1e-30 + 0j)]
+
+        def get_ll(self, params, data=None, noise_factor=None, T=1.0, dt=10.0, eps=1e-5, **kwargs):
+            calls.append(dict(params=np.array(params), data=data, noise_factor=noise_factor, T=T, dt=dt, eps=eps, extra=kwargs))
+            return -np.arange(len(params), dtype=float)
+
+    # the plug-in's signature is what the reference will call: same leading parameters as the stub
+    sig = list(inspect.signature(FDTemplateModel.get_ll).parameters)
+    assert sig[:4] == ["self", "params", "data", "noise_factor"]
+    fill = {"ndim_full": 14, "fill_inds": np.array([2, 5, 6, 7, 8, 9, 10, 12]), "fill_values": np.array([0.0, 1.0, 1.0, 0.3, 0.4, 0.5, 0.6, 0.0])}
+    tc = TransformContainer(parameter_transforms={(0, 1): lambda lnM, lneta: (np.exp(lnM), np.exp(lnM) * np.exp(lneta))}, fill_dict=fill)   # emri_pe.py:161-206
+    f_arr = np.linspace(0.0, 1e-2, 64)
+    like = RefLikelihood(Stub(), 2, f_arr=f_arr, parameter_transforms={"emri": tc}, fill_data_noise=True, vectorized=False,
+                         transpose_params=False, subset=3, use_gpu=False)
+    assert like.like_here is False                                                  # likelihood.py:70-72: the plug-in took over
+    inj6 = np.array([np.log(1e6), np.log(1e-5), 12.0, 0.35, 1.0, 2.0])
+    like.inject_signal(params=inj6.copy(), waveform_kwargs=dict(T=1.0), noise_fn=lambda f, **kw: np.full(len(f), 4.0), noise_kwargs={}, add_noise=False)
+    params = np.tile(inj6, (7, 1)) + 1e-3 * np.arange(7)[:, None]
+    out = like(params, T=0.5, dt=15.0, eps=1e-2)
+    assert [len(c["params"]) for c in calls] == [3, 3, 1]                           # subset chunking (likelihood.py:313-319)
+    assert np.array_equal(out, np.concatenate([-np.arange(3.0), -np.arange(3.0), -np.arange(1.0)]))
+    c = calls[0]
+    assert c["params"].shape == (3, 14) and np.allclose(c["params"][:, 0], np.exp(params[:3, 0]))      # (ln M, ln eta) -> (M, mu), 8 filled
+    assert np.allclose(c["params"][:, 1], np.exp(params[:3, 0] + params[:3, 1])) and np.allclose(c["params"][:, 6], 1.0)
+    assert c["data"] is like.injection_channels and c["noise_factor"] is like.noise_factor            # likelihood.py:330-331
+    assert (c["T"], c["dt"], c["eps"]) == (0.5, 15.0, 1e-2)
+    df = f_arr[1] - f_arr[0]
+    assert np.allclose(np.asarray(like.noise_factor), np.sqrt(df / 4.0))                                # likelihood.py:218-220

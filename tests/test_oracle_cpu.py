@@ -188,3 +188,57 @@ def test_mode_select_restatement_matches_host_selector(generator):
     for (l, m) in [(2, 2), (2, -2), (5, 3), (10, -7), (10, 0)]:
         from emri_frequencydomainwaveforms_b200.utils.ylm import spin_weighted_ylm
         assert abs(ylm_ref(l, m, 0.9, 2.2) - spin_weighted_ylm(-2, l, m, 0.9, 2.2)) < 1e-15
+
+
+# ---- the oracle against the reference's own statement of the per-harmonic construction ------------------------------
+def test_cell26_golden_pins_oracle_conventions(oracle_quad):
+    """tests/golden/cell26_golden.npz holds W(f) computed by the body of the reference notebook's FD_waveform
+    (Tutorial_FD_construction_single_mode.ipynb:548-623, cell 26: SciPy CubicSpline + scipy.special.kv) on three monotone single
+    harmonics (f_mn > 0 rising twice, f_mn < 0 falling), generated by tests/golden/make_cell26_golden.py.  The oracle must
+    reproduce it after undoing its final flip / split, W(f) = -[h+ - i hx](-f): identical support (bin index sets), the sign,
+    flip, conjugation and +-m conventions exactly (overlap real and positive), values to the accuracy of the cell's own
+    approximations (t(f) from a spline of the inverse function, fddot from a spline through the fdot knots): measured mismatch
+    1.5e-13 / 8.2e-10 / 1.7e-14, asserted <= 1e-8."""
+    g = np.load(os.path.join(GOLD, "cell26_golden.npz"))
+    assert len(g["names"]) == 3
+    for name in g["names"]:
+        M, mu, T, dt, N, scale = g[f"{name}.params"]
+        N = int(N)
+        l, m, n = (int(x) for x in g[f"{name}.lmn"])
+        get = lambda k: g[f"{name}.{k}"]
+        hp, hc, *_ = oracle_quad.fd_sum(get("t"), get("teuk_modes"), get("ylms"), get("Phi_phi"), get("Phi_r"), np.array([m], dtype=np.int32),
+                                        np.array([n], dtype=np.int32), get("f_phi"), get("f_r"), N, 1.0 / (N * dt), scale=scale)
+        W_or = -np.flip(hp - 1j * hc)                     # S = h+ - i hx = -flip(W)
+        W_ref = np.fft.fftshift(g[f"{name}.W"])           # the cell works on an fftfreq-ordered grid
+        assert np.array_equal(W_or != 0, W_ref != 0), name                       # identical bin index sets, both signs of f
+        sup = W_ref != 0
+        zero = (N - 1) // 2
+        if "negative" in name:
+            assert np.all(np.where(sup)[0][np.abs(W_ref[sup]) > 0.5 * np.abs(W_ref).max()] < zero)   # the direct term lives at f < 0
+        ip = np.vdot(W_ref[sup], W_or[sup])
+        nrm = np.sqrt(np.vdot(W_ref[sup], W_ref[sup]).real * np.vdot(W_or[sup], W_or[sup]).real)
+        assert abs(ip.imag) / nrm <= 1e-5 and 1.0 - ip.real / nrm <= 1e-8, (name, ip / nrm)
+        rel = np.abs(W_or[sup] - W_ref[sup]) / np.abs(W_ref).max()
+        assert np.median(rel) <= 1e-7 and rel.max() <= 5e-3, (name, np.median(rel), rel.max())
+        # a wrong convention is far outside these bounds: conjugating, flipping or negating W gives overlap <= 0 or ~ 0
+        for wrong in (np.conj(W_or), np.flip(W_or), -W_or):
+            assert np.vdot(W_ref[sup], wrong[sup]).real / nrm < 0.9
+
+
+def test_k13_few_mode_differs_only_near_the_seam(oracle_f64):
+    """EMRIFD_K13_FEW / Oracle.set_k13_mode("few"): FastEMRIWaveforms' SPAFunc truncations (14-term ascending series for
+    |X| <= 7, 9-term asymptotic series above).  Against the exact evaluation the two differ by <= 1e-6 just
+    below the seam (9.8e-7 at X = 6.96 from the truncated series, 2.4e-7 just above from the asymptotic one) and agree to
+    rounding away from it."""
+    Xs = np.concatenate([np.logspace(-3, 0, 20), np.linspace(1, 40, 300), np.logspace(np.log10(40), 6, 30)])
+    try:
+        oracle_f64.set_k13_mode("exact")
+        exact = np.array([oracle_f64.spa_R(x) for x in Xs])
+        oracle_f64.set_k13_mode("few")
+        few = np.array([oracle_f64.spa_R(x) for x in Xs])
+    finally:
+        oracle_f64.set_k13_mode("exact")
+    d = np.abs(few - exact) / np.abs(exact)
+    assert d.max() <= 2e-6 and 4.0 < Xs[d.argmax()] < 9.0
+    assert d[(Xs < 3.0) | (Xs > 30.0)].max() <= 1e-10
+    assert d[(Xs > 6.0) & (Xs < 8.0)].max() >= 1e-8          # the switch really changes the evaluation at the seam
