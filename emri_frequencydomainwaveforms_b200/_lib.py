@@ -35,7 +35,7 @@ SYMBOLS = [
     "emrifd_loglike", "emrifd_loglike_batch_host", "emrifd_bench_fp64_fma", "emrifd_launch_count",
     "emrifd_sum_kernel_time", "emrifd_mode_select", "emrifd_ylm_batch", "emrifd_mode_compact_count",
     "emrifd_mode_compact_gather", "emrifd_tile_bins", "emrifd_batch_sum_cyclic",
-    "emrifd_synth_amplitude", "emrifd_walker_status", "emrifd_set_k13_mode"]
+    "emrifd_synth_amplitude", "emrifd_walker_status", "emrifd_walker_status_dev", "emrifd_set_k13_mode"]
 
 _lib = None
 
@@ -71,6 +71,7 @@ def load():
                                              vp, vp, vp, vp, vp]
     lib.emrifd_batch_status.argtypes = [vp]
     lib.emrifd_walker_status.argtypes = [vp, i64, vp]
+    lib.emrifd_walker_status_dev.argtypes = [vp, i64, vp]
     lib.emrifd_set_k13_mode.argtypes = [vp, i32]
     lib.emrifd_set_data.argtypes = [vp, vp, vp, i64]
     lib.emrifd_inner_product.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
@@ -133,6 +134,13 @@ class Handle:
         out = np.zeros(int(B), dtype=np.int32)
         self.check(self.lib.emrifd_walker_status(self.h, int(B), out.ctypes.data))
         self.lib.emrifd_batch_status(self.h)   # clear the sticky batch word: the failures have been reported per walker
+        return out
+
+    def walker_status_async(self, B):
+        """The same status words as a device int32 tensor, copied on the handle's stream without a sync."""
+        import torch
+        out = torch.empty(int(B), dtype=torch.int32, device=self.torch_device)
+        self.check(self.lib.emrifd_walker_status_dev(self.h, int(B), out.data_ptr()))
         return out
 
     def set_k13_mode(self, mode):

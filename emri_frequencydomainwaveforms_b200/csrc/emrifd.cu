@@ -36,11 +36,13 @@
 #define SUM_BPT 4 /* consecutive bins per thread: the tile size every API-visible quantity refers to (emrifd_tile_bins) */
 #endif
 #ifndef SUM_BPT_WIDE
-#define SUM_BPT_WIDE 6 /* wider variant used when its shared memory still lets two CTAs share an SM (short trajectories):
-                          the cold root solve and the entry loop are amortised over 6 bins instead of 4 */
+#define SUM_BPT_WIDE 6 /* wider variant (the cold root solve and the sub-entry loop amortised over 6 bins instead of 4), used only when
+                          SUM_MINB of its CTAs fit on an SM: with the round-2 kernel (80 registers, three CTAs per SM) 4 bins and
+                          24 resident warps beat 6 bins and 16 warps (4.40 vs 4.65 ms on the bench batch), so it is an A/B variant
+                          (EMRIFD_BPT=6) rather than the default */
 #endif
 #ifndef SUM_MINB
-#define SUM_MINB 2 /* resident CTAs per SM the register allocation is tuned for */
+#define SUM_MINB 3 /* resident CTAs per SM the register allocation is tuned for (3 x 256 threads x 80 registers) */
 #endif
 #ifndef SUM_ENT_CAP
 #define SUM_ENT_CAP 64 /* entry-cache capacity: work-list entries evaluated per pass (a chunk's overlap list is walked in groups) */
@@ -92,6 +94,8 @@ struct emrifd_handle {
     // per-walker status words, (m, n) group index and combined amplitude quads (workspace of the mode sum)
     int *d_wstatus; int64_t wstatus_cap;
     int *d_leader; int64_t leader_cap;
+    int *d_gmem; int64_t gmem_cap;
+    int *d_goff; int64_t goff_cap;
     int *d_gcount; int64_t gcount_cap;
     double *d_gq; int64_t gq_cap;
     int64_t tot_modes, tot_teuk; // packed sizes of the batch validated last (sum K, sum L*K)
@@ -730,17 +734,22 @@ struct GroupParams {
     const double2 *ylm;
     int *leader; // [sum K]: walker block at mode_off, its first G entries = mode index of each group's first member
     int *gcount; // [B] number of groups G
+    int *gmem;   // [sum K]: walker block at mode_off = member modes, grouped (ascending mode index inside a group)
+    int *goff;   // [sum K + B]: walker w's block at mode_off + w = G + 1 offsets into its gmem block
     double *gq;  // walker block at 16 * teuk_off doubles: [L][G][16] = quads of Re Cp, Im Cp, Re Cm, Im Cm
 };
 
-__global__ void __launch_bounds__(GRP_THREADS) group_kernel(GroupParams p) {
-    extern __shared__ int gsm[]; // tab [GRP_TAB] | grp [K] | mem [K] | lead [K] | off [K + 1]
-    __shared__ int s_mn[4], s_warp[GRP_THREADS / 32], s_base;
-    const emrifd_walker_t wd = p.w[blockIdx.y];
-    const int K = wd.K, L = wd.L, R = 2 * K + 4;
+// Step 1, one CTA per walker: distinct (m, n) pairs numbered in order of first occurrence, and the member list of every group
+// in ascending mode order (a fixed summation order for the combination).
+__global__ void __launch_bounds__(GRP_THREADS) group_index_kernel(GroupParams p) {
+    extern __shared__ int gsm[]; // tab [GRP_TAB] | grp [K] | first [K] | cur [K]
+    __shared__ int s_mn[4], s_warp[GRP_THREADS / 32], s_base, s_g[GRP_THREADS];
+    const emrifd_walker_t wd = p.w[blockIdx.x];
+    const int K = wd.K;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int *marr = p.m + wd.mode_off, *narr = p.n + wd.mode_off;
-    int *tab = gsm, *grp = gsm + GRP_TAB, *mem = grp + K, *lead = mem + K, *off = lead + K;
+    int *tab = gsm, *grp = gsm + GRP_TAB, *first = grp + K, *cur = first + K;
+    int *lead = p.leader + wd.mode_off, *mem = p.gmem + wd.mode_off, *off = p.goff + wd.mode_off + blockIdx.x;
     if (tid == 0) { s_mn[0] = INT_MAX; s_mn[1] = INT_MIN; s_mn[2] = INT_MAX; s_mn[3] = INT_MIN; s_base = 0; }
     __syncthreads();
     {
@@ -756,27 +765,27 @@ __global__ void __launch_bounds__(GRP_THREADS) group_kernel(GroupParams p) {
     __syncthreads();
     const int mmin = s_mn[0], nmin = s_mn[2];
     const long long mspan = (long long)s_mn[1] - mmin + 1, nspan = (long long)s_mn[3] - nmin + 1;
-    // ---- first member of every mode's group -> mem[k] ----
+    // ---- first member of every mode's group -> first[k] ----
     if (mspan * nspan <= GRP_TAB) {
         const int cells = (int)(mspan * nspan), ns = (int)nspan;
         for (int i = tid; i < cells; i += GRP_THREADS) tab[i] = INT_MAX;
         __syncthreads();
         for (int k = tid; k < K; k += GRP_THREADS) atomicMin(&tab[(marr[k] - mmin) * ns + (narr[k] - nmin)], k);
         __syncthreads();
-        for (int k = tid; k < K; k += GRP_THREADS) mem[k] = tab[(marr[k] - mmin) * ns + (narr[k] - nmin)];
+        for (int k = tid; k < K; k += GRP_THREADS) first[k] = tab[(marr[k] - mmin) * ns + (narr[k] - nmin)];
     } else {
         for (int k = tid; k < K; k += GRP_THREADS) {
             const int mk = marr[k], nk = narr[k];
             int j = 0;
             while (j < k && !(marr[j] == mk && narr[j] == nk)) j++;
-            mem[k] = j;
+            first[k] = j;
         }
     }
     __syncthreads();
     // ---- number the groups in order of first occurrence ----
     for (int k0 = 0; k0 < K; k0 += GRP_THREADS) {
         const int k = k0 + tid;
-        const bool f = k < K && mem[k] == k;
+        const bool f = k < K && first[k] == k;
         const unsigned bal = __ballot_sync(0xffffffffu, f);
         if (lane == 0) s_warp[wid] = __popc(bal);
         __syncthreads();
@@ -788,64 +797,77 @@ __global__ void __launch_bounds__(GRP_THREADS) group_kernel(GroupParams p) {
         __syncthreads();
     }
     const int G = s_base;
-    for (int k = tid; k < K; k += GRP_THREADS) if (mem[k] != k) grp[k] = grp[mem[k]];
-    for (int g = tid; g <= G; g += GRP_THREADS) off[g] = 0;
+    for (int k = tid; k < K; k += GRP_THREADS) if (first[k] != k) grp[k] = grp[first[k]];
+    for (int g = tid; g < G; g += GRP_THREADS) cur[g] = 0;
     __syncthreads();
-    // ---- member lists (CSR), ascending mode index inside a group: fixed summation order ----
-    for (int k = tid; k < K; k += GRP_THREADS) atomicAdd(&off[grp[k] + 1], 1);
+    // ---- group sizes -> offsets (cur is the count first, then the fill cursor) ----
+    for (int k = tid; k < K; k += GRP_THREADS) atomicAdd(&cur[grp[k]], 1);
     __syncthreads();
     if (wid == 0) {
         int carry = 0;
         for (int g0 = 0; g0 < G; g0 += 32) {
             const int g = g0 + lane;
-            int v = g < G ? off[g + 1] : 0;
+            const int c = g < G ? cur[g] : 0;
+            int v = c;
             for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
-            if (g < G) off[g + 1] = carry + v;
+            if (g < G) { off[g] = carry + v - c; cur[g] = 0; }
             carry += __shfl_sync(0xffffffffu, v, 31);
         }
+        if (lane == 0) { off[G] = carry; p.gcount[blockIdx.x] = G; }
     }
     __syncthreads();
-    for (int g = tid; g < G; g += GRP_THREADS) {
-        int o = off[g];
-        const int oe = off[g + 1];
-        for (int k = lead[g]; o < oe; k++) if (grp[k] == g) mem[o++] = k;
+    // ---- stable fill, a chunk of GRP_THREADS modes at a time: slot = start + members of earlier chunks + earlier threads of
+    //      this chunk with the same group ----
+    for (int k0 = 0; k0 < K; k0 += GRP_THREADS) {
+        const int k = k0 + tid, g = k < K ? grp[k] : -1;
+        s_g[tid] = g;
+        __syncthreads();
+        if (g >= 0) {
+            int rank = 0;
+            for (int t = 0; t < tid; t++) rank += (s_g[t] == g);
+            mem[off[g] + cur[g] + rank] = k;
+        }
+        __syncthreads();
+        if (g >= 0) atomicAdd(&cur[g], 1);
+        __syncthreads();
     }
-    __syncthreads();
-    if (blockIdx.x == 0) {
-        for (int g = tid; g < G; g += GRP_THREADS) p.leader[wd.mode_off + g] = lead[g];
-        if (tid == 0) p.gcount[blockIdx.y] = G;
-    }
-    // ---- combined quads of this CTA's knots ----
+}
+
+// Step 2, grid (knot slices, walkers): the combined quads of a slice of knots.
+__global__ void __launch_bounds__(GRP_THREADS) group_combine_kernel(GroupParams p) {
+    const emrifd_walker_t wd = p.w[blockIdx.y];
+    const int K = wd.K, L = wd.L, R = 2 * K + 4, tid = threadIdx.x;
+    const int G = p.gcount[blockIdx.y];
+    const int *mem = p.gmem + wd.mode_off, *off = p.goff + wd.mode_off + blockIdx.y;
     const double2 *ylm = p.ylm + 2 * wd.mode_off;
     const double *coeff = p.coeff + wd.coeff_off;
     double *gq = p.gq + 16 * wd.teuk_off;
     const double r2 = 0.7071067811865476;
-    for (int j = blockIdx.x; j < L; j += gridDim.x) {
-        for (int g = tid; g < G; g += GRP_THREADS) {
-            double pr[4] = {0, 0, 0, 0}, pi[4] = {0, 0, 0, 0}, mr[4] = {0, 0, 0, 0}, mi[4] = {0, 0, 0, 0};
-            for (int i = off[g]; i < off[g + 1]; i++) {
-                const int k = mem[i];
-                const double4 a4 = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + k) * 4);
-                const double4 b4 = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + K + k) * 4);
-                const double2 yp = ylm[k], ym = ylm[K + k];
-                // Y_lm e^{+i 3pi/4} and Y_l-m e^{-i 3pi/4}
-                const double ypr = -r2 * (yp.x + yp.y), ypi = r2 * (yp.x - yp.y);
-                const double ymr = r2 * (ym.y - ym.x), ymi = -r2 * (ym.x + ym.y);
-                const double a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
+    for (int item = blockIdx.x * GRP_THREADS + tid; item < L * G; item += gridDim.x * GRP_THREADS) {
+        const int j = item / G, g = item - j * G;
+        double pr[4] = {0, 0, 0, 0}, pi[4] = {0, 0, 0, 0}, mr[4] = {0, 0, 0, 0}, mi[4] = {0, 0, 0, 0};
+        for (int i = off[g]; i < off[g + 1]; i++) {
+            const int k = mem[i];
+            const double4 a4 = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + k) * 4);
+            const double4 b4 = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + K + k) * 4);
+            const double2 yp = ylm[k], ym = ylm[K + k];
+            // Y_lm e^{+i 3pi/4} and Y_l-m e^{-i 3pi/4}
+            const double ypr = -r2 * (yp.x + yp.y), ypi = r2 * (yp.x - yp.y);
+            const double ymr = r2 * (ym.y - ym.x), ymi = -r2 * (ym.x + ym.y);
+            const double a[4] = {a4.x, a4.y, a4.z, a4.w}, b[4] = {b4.x, b4.y, b4.z, b4.w};
 #pragma unroll
-                for (int c = 0; c < 4; c++) {
-                    pr[c] = fma(ypr, a[c], fma(-ypi, b[c], pr[c])); // Y (a + i b)
-                    pi[c] = fma(ypr, b[c], fma(ypi, a[c], pi[c]));
-                    mr[c] = fma(ymr, a[c], fma(ymi, b[c], mr[c]));  // Y_- (a - i b)
-                    mi[c] = fma(ymi, a[c], fma(-ymr, b[c], mi[c]));
-                }
+            for (int c = 0; c < 4; c++) {
+                pr[c] = fma(ypr, a[c], fma(-ypi, b[c], pr[c])); // Y (a + i b)
+                pi[c] = fma(ypr, b[c], fma(ypi, a[c], pi[c]));
+                mr[c] = fma(ymr, a[c], fma(ymi, b[c], mr[c]));  // Y_- (a - i b)
+                mi[c] = fma(ymi, a[c], fma(-ymr, b[c], mi[c]));
             }
-            double4 *o = reinterpret_cast<double4 *>(gq + ((long long)j * G + g) * 16);
-            o[0] = make_double4(pr[0], pr[1], pr[2], pr[3]);
-            o[1] = make_double4(pi[0], pi[1], pi[2], pi[3]);
-            o[2] = make_double4(mr[0], mr[1], mr[2], mr[3]);
-            o[3] = make_double4(mi[0], mi[1], mi[2], mi[3]);
         }
+        double4 *o = reinterpret_cast<double4 *>(gq + (long long)item * 16);
+        o[0] = make_double4(pr[0], pr[1], pr[2], pr[3]);
+        o[1] = make_double4(pi[0], pi[1], pi[2], pi[3]);
+        o[2] = make_double4(mr[0], mr[1], mr[2], mr[3]);
+        o[3] = make_double4(mi[0], mi[1], mi[2], mi[3]);
     }
 }
 
@@ -880,7 +902,7 @@ struct __align__(16) FillEntry {
     int nsub, pad;
 };
 #ifndef SUM_SUBCAP
-#define SUM_SUBCAP 64 /* sub-entries evaluated per pass */
+#define SUM_SUBCAP 32 /* sub-entries evaluated per pass */
 #endif
 #define SUM_ECAP 32   /* work-list records per fill round: one per lane of the fill warp */
 
@@ -2009,7 +2031,7 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     SET_ATTR((spline_build_kernel<true, true>), big);
     SET_ATTR((spline_build_kernel<true, false>), big);
     SET_ATTR(segment_kernel, big);
-    SET_ATTR(group_kernel, big);
+    SET_ATTR(group_index_kernel, big);
     SET_ATTR(mode_select_kernel, SEL_CAP * 10);
 #define SET_SMEM(W_, L_) \
     SET_ATTR((mode_sum_kernel<W_, L_, SUM_BPT>), big); SET_ATTR((mode_sum_kernel<W_, L_, SUM_BPT_WIDE>), big); \
@@ -2032,7 +2054,7 @@ int emrifd_destroy(emrifd_handle_t *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_queue); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd); cudaFree(h->d_tiledd_w);
-    cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq);
+    cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq); cudaFree(h->d_gmem); cudaFree(h->d_goff);
     if (h->h_ws) cudaFreeHost(h->h_ws);
     for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
     for (int i = 0; i < 64; i++) { if (h->ev_a[i]) cudaEventDestroy(h->ev_a[i]); if (h->ev_b[i]) cudaEventDestroy(h->ev_b[i]); }
@@ -2162,13 +2184,10 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     p.include_minus_m = (flags & EMRIFD_INCLUDE_MINUS_M) != 0; p.mask_positive = mask_pos;
     p.hp = (double2 *)hp; p.hc = (double2 *)hc;
     p.dw = (const double2 *)h->d_data; p.wf = h->d_wfac; p.n_data = h->n_data;
-    // bins per thread: the wide variant when two of its CTAs still fit on an SM (short trajectories), else the base one
+    // bins per thread: always the base variant (4 bins, 1024-bin tiles, three CTAs per SM), so that a walker's result does not depend
+    // on which batch it is evaluated in; the wide variant is an explicit A/B choice (EMRIFD_BPT=6)
     int bpt = bpt_req ? bpt_req : h->force_bpt;
-    if (!bpt) {
-        int fit = 0;
-        cudaOccupancyMaxActiveBlocksPerMultiprocessor(&fit, mode_sum_kernel<true, true, SUM_BPT_WIDE>, SUM_THREADS, sum_smem_bytes(Lmax, SUM_BPT_WIDE));
-        bpt = fit >= SUM_MINB ? SUM_BPT_WIDE : SUM_BPT;
-    }
+    if (!bpt) bpt = SUM_BPT;
     const int64_t tile_bins = (int64_t)SUM_THREADS * bpt;
     const int64_t ntiles_all = (j_cnt + tile_bins - 1) / tile_bins;
     if (tile_stride < 1 || tile_first < 0) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum: bad tile_first / tile_stride");
@@ -2190,14 +2209,17 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
         if ((rc = ensure_bytes(h, (void **)&h->d_leader, &h->leader_cap, (int64_t)sizeof(int) * h->tot_modes))) return rc;
         if ((rc = ensure_bytes(h, (void **)&h->d_gcount, &h->gcount_cap, (int64_t)sizeof(int) * B))) return rc;
         if ((rc = ensure_bytes(h, (void **)&h->d_gq, &h->gq_cap, (int64_t)sizeof(double) * 16 * h->tot_teuk))) return rc;
+        if ((rc = ensure_bytes(h, (void **)&h->d_gmem, &h->gmem_cap, (int64_t)sizeof(int) * h->tot_modes))) return rc;
+        if ((rc = ensure_bytes(h, (void **)&h->d_goff, &h->goff_cap, (int64_t)sizeof(int) * (h->tot_modes + B)))) return rc;
         GroupParams gp;
         gp.w = h->d_walkers; gp.coeff = coeff; gp.m = m_arr; gp.n = n_arr; gp.ylm = (const double2 *)ylm;
-        gp.leader = h->d_leader; gp.gcount = h->d_gcount; gp.gq = h->d_gq;
-        int64_t nsl = ((int64_t)Lmax * Kmax + 2047) / 2048; // knot slices per walker: ~2048 (knot, mode) pairs per CTA
-        nsl = nsl < 1 ? 1 : (nsl > Lmax ? Lmax : nsl);
-        const size_t gsmem = sizeof(int) * ((size_t)GRP_TAB + 4 * (size_t)Kmax + 1);
-        group_kernel<<<dim3((unsigned)nsl, (unsigned)B), GRP_THREADS, gsmem, h->stream>>>(gp);
-        h->launches++;
+        gp.leader = h->d_leader; gp.gcount = h->d_gcount; gp.gmem = h->d_gmem; gp.goff = h->d_goff; gp.gq = h->d_gq;
+        const size_t gsmem = sizeof(int) * ((size_t)GRP_TAB + 3 * (size_t)Kmax);
+        group_index_kernel<<<(unsigned)B, GRP_THREADS, gsmem, h->stream>>>(gp);
+        int64_t nsl = ((int64_t)Lmax * Kmax + 2047) / 2048; // CTAs per walker: ~2048 (knot, mode) pairs each
+        nsl = nsl < 1 ? 1 : (nsl > 1024 ? 1024 : nsl);
+        group_combine_kernel<<<dim3((unsigned)nsl, (unsigned)B), GRP_THREADS, 0, h->stream>>>(gp);
+        h->launches += 2;
         CUDA_TRY(h, cudaGetLastError());
         p.leader = h->d_leader; p.gcount = h->d_gcount; p.gq = h->d_gq; p.wstatus = h->d_wstatus; p.k13_few = h->k13_few;
     }
@@ -2451,6 +2473,14 @@ int emrifd_walker_status(emrifd_handle_t *h, int64_t B, int32_t *status_host) {
     cudaSetDevice(h->device);
     CUDA_TRY(h, cudaMemcpyAsync(status_host, h->d_wstatus, sizeof(int) * (size_t)B, cudaMemcpyDeviceToHost, h->stream));
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
+    return 0;
+}
+
+int emrifd_walker_status_dev(emrifd_handle_t *h, int64_t B, int32_t *status_dev) {
+    if (!h || !status_dev || B <= 0) return set_err(h, EMRIFD_ERR_INVALID, "walker_status_dev: bad argument");
+    if ((int64_t)sizeof(int) * B > h->wstatus_cap) return set_err(h, EMRIFD_ERR_INVALID, "walker_status_dev: no batch of that size has run on this handle");
+    cudaSetDevice(h->device);
+    CUDA_TRY(h, cudaMemcpyAsync(status_dev, h->d_wstatus, sizeof(int) * (size_t)B, cudaMemcpyDeviceToDevice, h->stream));
     return 0;
 }
 

@@ -11,6 +11,8 @@ Two pieces:
   evaluates the whole walker batch in ONE fused launch sequence (spline -> segmentation -> mode sum
   + |d~ - h~|^2), never materialising h(f) in HBM.
 """
+import os
+
 import numpy as np
 
 from .. import _lib, engine
@@ -19,8 +21,10 @@ from .. import _lib, engine
 class FDTemplateModel:
     """Batched FD template + likelihood plugin around a ``GenerateEMRIWaveform``-shaped generator."""
 
-    def __init__(self, waveform_generator, f_arr=None, device=None, producers="auto"):
+    def __init__(self, waveform_generator, f_arr=None, device=None, producers="auto", chunk=64):
         self.gen = waveform_generator
+        self.chunk = int(chunk)     # walkers per launch sequence; larger parameter batches are pipelined chunk by chunk
+        self._side = None           # (handle, stream) of the producer pipeline
         self.base = waveform_generator.waveform_generator       # FastSchwarzschildEccentricFlux
         self._device = device
         self._data_ref = None
@@ -126,6 +130,8 @@ class FDTemplateModel:
             from ..waveform import ssb_transform_batch
             ang = np.stack(ssb_transform_batch(P[:, 7], P[:, 8], P[:, 9], P[:, 10],
                                                detector_frame=getattr(self.gen, "frame", "detector") == "detector"), axis=1)
+            if len(P) > self.chunk:
+                return self._get_ll_pipelined(P, ang, h, Ngrid, val, fpos_dev, T, dt, eps, include_minus_m)
             db, ok = self.base.prepare_batch_device(P[:, 0], P[:, 1], P[:, 3], P[:, 4], ang[:, 0], ang[:, 1], dist=P[:, 6],
                                                     Phi_phi0=P[:, 11], Phi_r0=P[:, 13], T=T, dt=dt, eps=eps,
                                                     cos2psi=ang[:, 2], sin2psi=ang[:, 3], handle=h)
@@ -151,6 +157,85 @@ class FDTemplateModel:
             ll[ok] = out[:, 0]
             self.last_dh_hh = out[:, 1:]
         return ll
+
+
+def _fdtm_pipelined(self, P, ang, h, Ngrid, val, fpos_dev, T, dt, eps, include_minus_m):
+    """Large parameter batches (a whole tempered ensemble in one call): chunks of ``self.chunk`` walkers, the producers of
+    chunk k+1 -- host trajectory ODE (threaded), H2D of the sparse tracks, device amplitudes / Ylm / mode selection /
+    compaction, on a side stream through a handle of their own -- overlap the spline / segment / sum + likelihood of chunk k
+    on the caller's stream.  Results are identical to chunk-by-chunk calls (walkers are independent)."""
+    import torch
+    from concurrent.futures import ThreadPoolExecutor
+    nb, ck = len(P), self.chunk
+    NW = 2     # producer threads: two chunks are being prepared while a third is summed
+    if self._side is None or self._side[0][0].device != h.device:
+        self._side = []
+        for _ in range(NW):
+            st = torch.cuda.Stream(device=h.torch_device)
+            self._side.append((_lib.Handle(h.device, st.cuda_stream), st))
+    starts = list(range(0, nb, ck))
+    cores = len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1")))
+    nthr = max(1, min(cores // NW, 16))
+
+    import time
+    trace = [] if os.environ.get("EMRIFD_TRACE") else None
+
+    def prep(i):
+        t0 = time.perf_counter()
+        h2, side = self._side[i % NW]
+        sl = slice(starts[i], min(starts[i] + ck, nb))
+        with torch.cuda.stream(side):
+            db, ok = self.base.prepare_batch_device(P[sl, 0], P[sl, 1], P[sl, 3], P[sl, 4], ang[sl, 0], ang[sl, 1], dist=P[sl, 6],
+                                                    Phi_phi0=P[sl, 11], Phi_r0=P[sl, 13], T=T, dt=dt, eps=eps,
+                                                    cos2psi=ang[sl, 2], sin2psi=ang[sl, 3], handle=h2, nthreads=nthr)
+            ev = torch.cuda.Event()
+            ev.record(side)
+        if trace is not None:
+            trace.append(("prep", i, round(1e3 * (time.perf_counter() - t0), 2), getattr(db, "stage_ms", None)))
+        return db, ok, ev, sl
+
+    ll = np.full(nb, np.nan)
+    self.last_walker_status = np.zeros(nb, dtype=np.int32)
+    self.last_dh_hh = np.full((nb, 2), np.nan)
+    self.last_h2d_bytes = 0
+    main = torch.cuda.current_stream(h.torch_device)
+    import sys
+    # two Python threads hand the GIL back and forth a dozen times per chunk; with the default 5 ms switch interval every
+    # hand-over can stall the other thread for milliseconds -- as long as a whole chunk takes on the device
+    sw = sys.getswitchinterval()
+    sys.setswitchinterval(2e-5)
+    try:
+        with ThreadPoolExecutor(max_workers=NW) as ex:
+            futs = {i: ex.submit(prep, i) for i in range(min(NW, len(starts)))}
+            pending = None                     # (like tensor, db, ok, slice) of the chunk whose kernels are in flight
+            for i in range(len(starts) + 1):
+                cur = None
+                if i < len(starts):
+                    db, ok, ev, sl = futs.pop(i).result()
+                    if i + NW < len(starts):
+                        futs[i + NW] = ex.submit(prep, i + NW)
+                    if db is not None:
+                        main.wait_event(ev)
+                        db.handle = h          # the sum runs on the caller's handle (its stream, its injected data)
+                        self.last_h2d_bytes += db.h2d_bytes
+                        cur = (engine.run_loglike(db, Ngrid, val, fpos_dev, include_minus_m=include_minus_m), db, ok, sl,
+                               h.walker_status_async(db.pb.B))
+                if pending is not None:        # read the previous chunk back while this one runs
+                    like_t, db_p, ok_p, sl_p, st_p = pending
+                    out = like_t.cpu().numpy()
+                    idx = np.arange(sl_p.start, sl_p.stop)[ok_p]
+                    self.last_walker_status[idx] = st_p.cpu().numpy()
+                    ll[idx] = out[:, 0]
+                    self.last_dh_hh[idx] = out[:, 1:]
+                pending = cur
+    finally:
+        sys.setswitchinterval(sw)
+    if trace is not None:
+        print("EMRIFD_TRACE", trace, flush=True)
+    return ll
+
+
+FDTemplateModel._get_ll_pipelined = _fdtm_pipelined
 
 
 class Likelihood:

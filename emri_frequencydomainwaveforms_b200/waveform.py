@@ -183,12 +183,16 @@ class FastSchwarzschildEccentricFlux:
                | (theta < 0.0) | (theta > np.pi) | ~(M > 0.0) | ~(mu > 0.0))
         ok &= np.isfinite(M) & np.isfinite(mu) & np.isfinite(p0) & np.isfinite(e0) & np.isfinite(theta) & np.isfinite(phi)
         ig = self.inspiral_generator
-        nthreads = nthreads or min(len(os.sched_getaffinity(0)), 16)
+        if not nthreads:    # this process's share of the host cores (one process per GPU: torchrun exports LOCAL_WORLD_SIZE)
+            nthreads = max(1, min(len(os.sched_getaffinity(0)) // max(1, int(os.environ.get("LOCAL_WORLD_SIZE", "1"))), 16))
         sel = np.where(ok)[0]
         if len(sel) == 0:
             return None, ok
+        import time as _time
+        _t0 = _time.perf_counter()
         out, lens = _hostlib.trajectory_batch(M[sel], mu[sel], p0[sel], e0[sel], Phi_phi0[sel], Phi_r0[sel], T, ig.rtol, ig.atol,
                                               ig.max_init_len, nthreads=nthreads)
+        _stage = (nthreads, round(1e3 * (_time.perf_counter() - _t0), 2))     # (threads, host trajectory ms): diagnostics
         good = lens >= 4
         ok[sel[~good]] = False
         sel, out, lens = sel[good], [o[good] for o in out], lens[good].astype(np.int64)
@@ -231,6 +235,7 @@ class FastSchwarzschildEccentricFlux:
         tracks = dict(t=tr_dev[0], Phi_phi=tr_dev[3], Phi_r=tr_dev[4], f_phi=tr_dev[5], f_r=tr_dev[6])
         db = engine.DeviceBatch.from_device_parts(h, w, tracks, teuk, m_out, n_out, ylm)
         db.keep_idx, db.h2d_bytes = keep_idx, int(tr.nbytes + samp_walker.numel() * 4 + 2 * 8 * B + w.nbytes)
+        db.stage_ms = _stage
         db.p_e_host = (tr[1], tr[2])
         ends = np.cumsum(lens) - 1
         db.t_first, db.t_last = tr[0][ends - lens + 1], tr[0][ends]      # per walker: output sizing (few SummationBase)

@@ -147,6 +147,8 @@ int emrifd_batch_status(emrifd_handle_t *h);
  * reference's per-walker contract: Eryn maps a NaN likelihood to -1e300 (Eryn/eryn/moves/red_blue.py:282-284) and the sweep
  * skips a failing point (check_mode_by_mode.py:328-330).  sync. */
 int emrifd_walker_status(emrifd_handle_t *h, int64_t B, int32_t *status_host);
+/* same words copied to a DEVICE buffer on the handle's stream, no sync (pipelined callers read them back with the results) */
+int emrifd_walker_status_dev(emrifd_handle_t *h, int64_t B, int32_t *status_dev);
 /* EMRIFD_K13_EXACT (default) or EMRIFD_K13_FEW for every later mode sum on this handle. */
 int emrifd_set_k13_mode(emrifd_handle_t *h, int mode);
 

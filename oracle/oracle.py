@@ -212,3 +212,69 @@ def ylm_ref(l, m, theta, phi):
         tot += (-1.0) ** (k - mm + mp) / den * cb ** (2 * l - 2 * k + mm - mp) * sb ** (2 * k - mm + mp)
     d = sqrt(factorial(l + mp) * factorial(l - mp) * factorial(l + mm) * factorial(l - mm)) * tot
     return sqrt((2 * l + 1) / (4.0 * pi)) * d * complex(cos(m * phi), sin(m * phi))
+
+
+# ---- optimised CPU baseline (timed by bench.py only; validated against the oracle in tests/test_oracle_cpu.py) -------------
+def _cpu_tag():
+    """The fast baseline is compiled with -march=native, so its file name carries the host CPU model: a library built on
+    another machine (the build container vs the GPU box) is never loaded."""
+    import hashlib
+    try:
+        model = [l for l in open("/proc/cpuinfo") if l.startswith(("model name", "flags"))][:2]
+    except OSError:
+        model = []
+    return hashlib.sha1("".join(model).encode()).hexdigest()[:10]
+
+
+class FastCPU:
+    """ctypes front-end of oracle/emrifd_cpu_fast.c: one walker's f >= 0 waveform and/or likelihood sums on the implicit grid,
+    from the oracle's (bit-exact) spline coefficients and work-list.  ``Oracle('f64')`` supplies those."""
+
+    def __init__(self, oracle=None):
+        self.orc = oracle or Oracle("f64")
+        path = os.path.join(_BUILD, f"libcpufast_{_cpu_tag()}.so")
+        src = os.path.join(_HERE, "emrifd_cpu_fast.c")
+        if not os.path.exists(path) or os.path.getmtime(path) < os.path.getmtime(src):
+            subprocess.check_call(["make", "-C", _HERE, "-s", "-B", "cpufast", f"CPUFAST={path}"])
+        self.lib = C.CDLL(path)
+        self.lib.cpuf_sum.argtypes = [_dp, _dp, C.c_int, C.c_int, _ip, _ip, _dp, C.c_int64, C.c_double, C.c_void_p, _ip, C.c_int,
+                                      C.c_double, C.c_double, C.c_double, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, _dp,
+                                      C.c_void_p]
+        self.lib.cpuf_set_num_threads.argtypes = [C.c_int]
+
+    def num_threads(self):
+        return int(self.lib.cpuf_num_threads())
+
+    def set_num_threads(self, n):
+        self.lib.cpuf_set_num_threads(int(n))
+        self.orc.lib.orc_set_num_threads(int(n))
+
+    def prepare(self, it, N, val):
+        """Spline coefficients + work-list of one walker (the oracle's exact double code)."""
+        y = np.concatenate([it["teuk_modes"].T.real, it["teuk_modes"].T.imag, np.stack([it["f_phi"], it["f_r"], it["Phi_phi"], it["Phi_r"]])])
+        coeff = self.orc.spline_build(it["t"], y)
+        br, nbr = self.orc.segment_build(it["t"], coeff, it["m_arr"], it["n_arr"], N, val)
+        return coeff, br, nbr
+
+    def sum(self, it, N, val, data_w=None, wfac=None, want_h=True, include_minus_m=True, prepared=None):
+        """Returns (hp, hc [npos] or None, like3, n_eval)."""
+        coeff, br, nbr = prepared or self.prepare(it, N, val)
+        L, R, _ = coeff.shape
+        K = (R - 4) // 2
+        npos = (N + 1) // 2
+        hp = np.zeros(2 * npos) if want_h else None
+        hc = np.zeros(2 * npos) if want_h else None
+        like3 = np.zeros(3)
+        nev = C.c_int64(0)
+        dw = None if data_w is None else np.ascontiguousarray(data_w, dtype=np.complex128).view(np.float64)
+        wf = None if wfac is None else np.ascontiguousarray(wfac, dtype=np.float64)
+        ylm = np.ascontiguousarray(it["ylms"], dtype=np.complex128).view(np.float64)
+        rc = self.lib.cpuf_sum(np.ascontiguousarray(it["t"], dtype=np.float64), np.ascontiguousarray(coeff), L, K,
+                               np.ascontiguousarray(it["m_arr"], dtype=np.int32), np.ascontiguousarray(it["n_arr"], dtype=np.int32), ylm,
+                               int(N), float(val), br.ctypes.data, np.ascontiguousarray(nbr, dtype=np.int32), int(include_minus_m),
+                               float(it.get("scale", 1.0)), float(it.get("cos2psi", 1.0)), float(it.get("sin2psi", 0.0)),
+                               None if dw is None else dw.ctypes.data, None if wf is None else wf.ctypes.data,
+                               None if hp is None else hp.ctypes.data, None if hc is None else hc.ctypes.data, like3, C.addressof(nev))
+        if rc:
+            raise ValueError(f"cpuf_sum failed rc={rc}")
+        return (hp.view(np.complex128) if want_h else None, hc.view(np.complex128) if want_h else None, like3, nev.value)

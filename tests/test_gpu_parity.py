@@ -594,8 +594,7 @@ def test_bench_line_contract(torch_cuda):
     import subprocess
     import sys
     root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
-    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3", "--batch", "8", "--distinct", "2",
-                          "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=root)
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--steps", "2", "--warmup", "3", "--batch", "8", "--no-cpu-baseline"], capture_output=True, text=True, timeout=900, cwd=root)
     assert out.returncode == 0, out.stderr[-2000:]
     lines = [l for l in out.stdout.splitlines() if l.strip()]
     assert len(lines) == 1
@@ -607,4 +606,8 @@ def test_bench_line_contract(torch_cuda):
     assert d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
     r = d["roofline"]
     assert r["bound"] in ("hbm", "fp64") and 0 < r["frac"] < 1.5 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9 and r["traffic"]
-    assert d["e2e_from_parameters"]["value"] > 0
+    assert d["e2e_from_parameters"]["value"] > 0 and d["e2e_from_parameters"]["finite"]
+    assert d["cfg1"]["walkers_per_s"] > 0 and 0 < d["cfg1"]["hbm_frac"] < 1.3
+    c4 = d["cfg4_binsharded"]
+    assert c4["modes"] == 3843 and c4["solves"] < c4["mode_evals"] / 4 and c4["ms_per_likelihood"] > 0 and abs(c4["ll_1rank"]) <= 1e-10 * c4["hh"]
+    assert r["executed_flops_per_solve"] > 100 and r["solves_per_launch"] > 0

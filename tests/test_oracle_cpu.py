@@ -242,3 +242,26 @@ def test_k13_few_mode_differs_only_near_the_seam(oracle_f64):
     assert d.max() <= 2e-6 and 4.0 < Xs[d.argmax()] < 9.0
     assert d[(Xs < 3.0) | (Xs > 30.0)].max() <= 1e-10
     assert d[(Xs > 6.0) & (Xs < 8.0)].max() >= 1e-8          # the switch really changes the evaluation at the seam
+
+
+@pytest.mark.parametrize("name", list(CASES))
+def test_fast_cpu_baseline_matches_oracle(name, generator, oracle_quad):
+    """oracle/emrifd_cpu_fast.c (the optimised double CPU implementation that bench.py times as `cpu_baseline` and as the
+    `--impl reference` arm) against the binary128 oracle: waveform <= 1e-9 of max|h|, identical support, likelihood sums."""
+    from oracle.oracle import FastCPU
+    fast = FastCPU()
+    it = make_item(generator, name)
+    N = it["N"]
+    n, val = (N + 1) // 2, 1.0 / (N * it["dt"])
+    hp_o, hc_o, *_ = oracle_waveform(oracle_quad, it)
+    hp_o, hc_o = hp_o[n - 1:], hc_o[n - 1:]
+    rng = np.random.default_rng(4)
+    w = np.full((2, n), 2.0e19)
+    d = np.stack([hp_o, hc_o]) * w + 1e-3 * np.abs(hp_o).max() * w * (rng.normal(size=(2, n)) + 1j * rng.normal(size=(2, n)))
+    hp, hc, like, nev = fast.sum(it, N, val, data_w=d, wfac=w)
+    assert rel_err(hp, hp_o) <= 1e-9 and rel_err(hc, hc_o) <= 1e-9
+    assert np.array_equal(hp != 0, hp_o != 0)
+    ref = oracle_quad.loglike(d, np.stack([hp_o, hc_o]), w)
+    assert np.allclose(like, ref, rtol=1e-9, atol=1e-9 * abs(ref[2]))
+    _, _, like2, nev2 = fast.sum(it, N, val, data_w=d, wfac=w, want_h=False)            # likelihood only: same sums
+    assert np.allclose(like2, like, rtol=1e-13) and nev2 == nev and 0 < nev <= oracle_quad.last_n_eval
