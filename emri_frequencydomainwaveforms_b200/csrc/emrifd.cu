@@ -29,34 +29,25 @@
 #include "k13_tables.h"
 
 #define MAXBR EMRIFD_MAX_BRANCHES
-#ifndef SUM_THREADS
-#define SUM_THREADS 256
+// mode-sum CTA: SUM_CW consumer warps (bin owners: they evaluate and read out) + one producer warp (record scan, sub-entry fill)
+#ifndef SUM_CW
+#define SUM_CW 11
 #endif
+#define SUM_CT (SUM_CW * 32)      /* consumer threads */
+#define SUM_THREADS (SUM_CT + 32) /* + the producer warp */
 #ifndef SUM_BPT
-#define SUM_BPT 4 /* consecutive bins per thread: the tile size every API-visible quantity refers to (emrifd_tile_bins) */
-#endif
-#ifndef SUM_BPT_WIDE
-#define SUM_BPT_WIDE 6 /* wider variant (the cold root solve and the sub-entry loop amortised over 6 bins instead of 4), used only when
-                          SUM_MINB of its CTAs fit on an SM: with the round-2 kernel (80 registers, three CTAs per SM) 4 bins and
-                          24 resident warps beat 6 bins and 16 warps (4.40 vs 4.65 ms on the bench batch), so it is an A/B variant
-                          (EMRIFD_BPT=6) rather than the default */
+#define SUM_BPT 4 /* consecutive bins per consumer thread */
 #endif
 #ifndef SUM_MINB
-#define SUM_MINB 3 /* resident CTAs per SM the register allocation is tuned for (3 x 256 threads x 80 registers) */
+#define SUM_MINB 2 /* resident CTAs per SM the register allocation is tuned for (2 x 384 threads x 80 registers: 22 consumer warps per SM) */
 #endif
-#ifndef SUM_ENT_CAP
-#define SUM_ENT_CAP 64 /* entry-cache capacity: work-list entries evaluated per pass (a chunk's overlap list is walked in groups) */
+#ifndef SUM_RING
+#define SUM_RING 4 /* passes (of up to SUM_SUBCAP sub-entries) in flight between the producer warp and the consumer warps */
 #endif
-#ifndef SUM_SF
-#define SUM_SF 1 /* 1: exact bin frequencies staged in smem; 0: recomputed per use (8 B/bin less smem) */
-#endif
-#ifdef SUM_MAXNREG
-#define SUM_BOUNDS __maxnreg__(SUM_MAXNREG)
-#else
+#define SUM_CHUNK 256 /* group records per chunk of the work-list (chunk_range_kernel's hull granularity) */
 #define SUM_BOUNDS __launch_bounds__(SUM_THREADS, SUM_MINB)
-#endif
-#define SUM_TILE (SUM_THREADS * SUM_BPT)
-#define ACC_STRIDE (SUM_THREADS + 4) /* row stride of the smem accumulators: conflict-free own-slot and transposed access */
+#define SUM_TILE (SUM_CT * SUM_BPT) /* bins per tile: the tile size every API-visible quantity refers to (emrifd_tile_bins) */
+#define ACC_STRIDE (SUM_CT + 4) /* row stride of the smem accumulators: conflict-free own-slot and transposed access */
 #define SEG_THREADS 128
 #define SMEM_PER_KNOT 3 /* doubles staged per knot by the mode sum: t, f_phi, f_r */
 
@@ -78,11 +69,8 @@ struct emrifd_handle {
     int64_t partial_cap;
     long long *d_chunk; // per-chunk bin hulls
     int64_t chunk_cap;
-    double *d_tiledd;   // per-tile sum |d~|^2 of the injected data (tiles of SUM_THREADS * SUM_BPT bins)
+    double *d_tiledd;   // per-tile sum |d~|^2 of the injected data (tiles of SUM_TILE bins)
     int64_t tiledd_cap;
-    double *d_tiledd_w; // same for the wide tiles (SUM_THREADS * SUM_BPT_WIDE bins)
-    int64_t tiledd_w_cap;
-    int force_bpt;      // 0 = choose per launch; else SUM_BPT or SUM_BPT_WIDE (EMRIFD_BPT environment variable, for A/B runs)
     const double *d_data; // whitened data [2][n]
     const double *d_wfac; // noise factor  [2][n]
     int64_t n_data;
@@ -1019,14 +1007,14 @@ __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)
     }
 }
 
-// Hull of the positive-bin indices touched by each chunk of SUM_THREADS group records (either through the +f or the -f side):
+// Hull of the positive-bin indices touched by each chunk of SUM_CHUNK group records (either through the +f or the -f side):
 // lets the mode sum skip a whole chunk (no ballot, no barrier pair) when its tile is outside, and empty_tile_kernel classify tiles.
-__global__ void __launch_bounds__(SUM_THREADS) chunk_range_kernel(const emrifd_walker_t *w, const emrifd_branch_t *brs,
+__global__ void __launch_bounds__(SUM_CHUNK) chunk_range_kernel(const emrifd_walker_t *w, const emrifd_branch_t *brs,
                                                                    const int *leader, const int *gcount, long long zero,
                                                                    long long *rng, int cpw) {
-    __shared__ long long s_lo[SUM_THREADS / 32], s_hi[SUM_THREADS / 32];
+    __shared__ long long s_lo[SUM_CHUNK / 32], s_hi[SUM_CHUNK / 32];
     const emrifd_walker_t wd = w[blockIdx.y];
-    const int nrec = gcount[blockIdx.y] * MAXBR, r = blockIdx.x * SUM_THREADS + threadIdx.x;
+    const int nrec = gcount[blockIdx.y] * MAXBR, r = blockIdx.x * SUM_CHUNK + threadIdx.x;
     long long lo = 0x7fffffffffffffffLL, hi = -1;
     if (r < nrec) {
         const emrifd_branch_t *b = brs + (wd.mode_off + leader[wd.mode_off + r / MAXBR]) * MAXBR + (r % MAXBR);
@@ -1046,7 +1034,7 @@ __global__ void __launch_bounds__(SUM_THREADS) chunk_range_kernel(const emrifd_w
     if ((threadIdx.x & 31) == 0) { s_lo[threadIdx.x >> 5] = lo; s_hi[threadIdx.x >> 5] = hi; }
     __syncthreads();
     if (threadIdx.x == 0) {
-        for (int q = 1; q < SUM_THREADS / 32; q++) { lo = s_lo[q] < lo ? s_lo[q] : lo; hi = s_hi[q] > hi ? s_hi[q] : hi; }
+        for (int q = 1; q < SUM_CHUNK / 32; q++) { lo = s_lo[q] < lo ? s_lo[q] : lo; hi = s_hi[q] > hi ? s_hi[q] : hi; }
         long long *o = rng + ((long long)blockIdx.y * cpw + blockIdx.x) * 2;
         o[0] = lo; o[1] = hi;
     }
@@ -1078,26 +1066,28 @@ __device__ __forceinline__ bool tile_truncated(const SumParams &p, long long jt0
 
 // Tiles no harmonic touches (most of the band of a non-plunging eps = 1e-2 system): h = 0 is stored and the tile's likelihood
 // term is the precomputed sum |d~|^2.  A kernel of its own because this work is a pure store stream: no shared memory and
-// 8 resident CTAs per SM keep enough stores in flight to approach the HBM write rate, which the two resident CTAs of
+// 8 resident CTAs per SM keep enough stores in flight to approach the HBM write rate, which the resident CTAs of
 // mode_sum_kernel (register- and smem-limited) cannot.  The walker descriptor and the chunk hulls are fetched together
 // (one memory round trip before the stores).  A walker whose status word is set (bad knots, too many branches) has all its
 // tiles treated as empty: zeros in h, NaN in the likelihood (like_finalize_kernel).
+#define EMPTY_THREADS 256
 template <bool WRITE_H, bool LIKE, int BPT>
-__global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p) {
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+__global__ void __launch_bounds__(EMPTY_THREADS, 8) empty_tile_kernel(SumParams p) {
+    constexpr int TILE = SUM_CT * BPT;
+    const int tid = threadIdx.x;
     const long long *crng = p.chunk_rng + (long long)blockIdx.y * p.cpw * 2;
     const long long c_lo = crng[0], c_hi = crng[1];          // first chunk's hull: independent of the descriptor
     const emrifd_walker_t *wp = p.w + blockIdx.y;
     const int nrec = p.gcount[blockIdx.y] * MAXBR;
     const int bad = p.wstatus[blockIdx.y];
     const long long out_off = wp->out_off;
-    const long long jt0 = p.j_lo + (p.tile_first + (long long)blockIdx.x * p.tile_stride) * (SUM_THREADS * BPT);
+    const long long jt0 = p.j_lo + (p.tile_first + (long long)blockIdx.x * p.tile_stride) * TILE;
     const long long jend = p.j_lo + p.j_cnt;
-    const long long jt1 = (jt0 + (SUM_THREADS * BPT) < jend ? jt0 + (SUM_THREADS * BPT) : jend) - 1;
+    const long long jt1 = (jt0 + TILE < jend ? jt0 + TILE : jend) - 1;
     bool any = !(c_lo > jt1 || c_hi < jt0);
-    for (int ch = 1; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
+    for (int ch = 1; ch * SUM_CHUNK < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
     if (bad) any = false;
-    const bool per_bin = LIKE && (p.no_empty || tile_truncated(p, jt0, SUM_THREADS * BPT));
+    const bool per_bin = LIKE && (p.no_empty || tile_truncated(p, jt0, TILE));
     if (any || per_bin) { // work for mode_sum_kernel's persistent CTAs (processing order does not affect any result)
         if (tid == 0) p.queue[atomicAdd(&p.qctl[0], 1u)] = ((unsigned long long)blockIdx.y << 32) | blockIdx.x;
         return;
@@ -1106,10 +1096,8 @@ __global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p)
     if (WRITE_H) {
         const double2 z = make_double2(0.0, 0.0);
         const long long zero = p.g.zero;
-#pragma unroll
-        for (int i = 0; i < BPT; i++) {
-            const int lb = wid * (32 * BPT) + i * 32 + lane;
-            if (lb >= ntile_) continue;
+#pragma unroll 2
+        for (int lb = tid; lb < ntile_; lb += EMPTY_THREADS) {
             const long long j = jt0 + lb;
             if (p.mask_positive) {
                 const long long o = out_off + (j - p.j_lo);
@@ -1121,38 +1109,39 @@ __global__ void __launch_bounds__(SUM_THREADS, 8) empty_tile_kernel(SumParams p)
             }
         }
     }
-    if (LIKE && lane == 0) {
-        double *o = p.partial + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * (SUM_THREADS / 32) + wid) * 3;
-        o[0] = (wid == 0) ? p.tile_dd[jt0 / (SUM_THREADS * BPT)] : 0.0; o[1] = 0.0; o[2] = 0.0;
+    if (LIKE && tid < SUM_CW) { // the partial-sum slots of the tile's consumer warps
+        double *o = p.partial + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * SUM_CW + tid) * 3;
+        o[0] = (tid == 0) ? p.tile_dd[jt0 / TILE] : 0.0; o[1] = 0.0; o[2] = 0.0;
     }
 }
 
-// exact frequency of tile-local bin lb from the staged table sF[BPT][SUM_THREADS] (thread lb / BPT owns bin lb)
-template <int BPT>
-__device__ __forceinline__ double tile_binf(const double *sF, int lb) { return sF[(lb % BPT) * SUM_THREADS + lb / BPT]; }
+// exact frequency of tile-local bin lb, as every kernel of the path computes it
+__device__ __forceinline__ double tile_binf(const Grid &g, long long jt0, int lb) {
+    const long long jj = jt0 + lb;
+    return g.fpos ? g.fpos[jj] : rmul((double)(int)jj, g.val);
+}
 
 // knot frequency of a group exactly as segment_kernel rounds it
 __device__ __forceinline__ double knot_F(const double *sK, int j, double dm, double dn) {
     return radd(rmul(dm, sK[3 * j + 1]), rmul(dn, sK[3 * j + 2]));
 }
 
-// Fill warp, step 1: lane i < gcount turns overlapping record s_list[i] into a FillEntry (tile-local bin ranges and the spline
-// segments they fall in, per side) and the warp numbers the sub-entries of the round (exclusive scan).  Returns their total.
-template <int BPT>
+// Producer warp, step 1: lane i < gcount turns overlapping record s_list[i] into a FillEntry (tile-local bin ranges and the
+// spline segments they fall in, per side) and the warp numbers the sub-entries of the round (exclusive scan).  Returns their total.
 __device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *marr, const int *narr, int include_minus_m,
                                          long long zero, const int *s_list, const int *s_rec, int gcount, long long jt0,
-                                         long long jt1, const double *sF, const double *sK, FillEntry *ent) {
+                                         long long jt1, Grid g, const double *sK, FillEntry *ent) {
     // (br, marr, narr: this walker's blocks.  Scalars by value: a reference to the kernel parameters would force a
     //  local-memory copy of them)
     const int lane = threadIdx.x & 31;
     int nsub = 0;
     if (lane < gcount) {
-        const int g = s_list[lane] / MAXBR, rec = s_rec[lane], k = rec / MAXBR;
+        const int gi = s_list[lane] / MAXBR, rec = s_rec[lane], k = rec / MAXBR;
         const emrifd_branch_t b = br[rec];
         const int mi = marr[k], ni = narr[k];
         FillEntry e;
         e.xa = b.xa; e.xb = b.xb; e.dm = (double)mi; e.dn = (double)ni;
-        e.ja = b.ja; e.jb = b.jb; e.dir = b.dir; e.g = g;
+        e.ja = b.ja; e.jb = b.jb; e.dir = b.dir; e.g = gi;
         e.mirror = (mi > 0) && include_minus_m; e.pad = 0;
         // tile-local covered ranges: +f bins have full-grid index zero + jt0 + lb, -f bins zero - jt0 - lb
         const long long ntile = jt1 - jt0 + 1;
@@ -1169,7 +1158,7 @@ __device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *m
             if (e.s[sd] > e.e[sd]) continue;
             int jj2[2];
             { // segment of the side's first bin: largest j whose knot frequency is not beyond f (binary search) ...
-                const double fb = tile_binf<BPT>(sF, e.s[sd]);
+                const double fb = tile_binf(g, jt0, e.s[sd]);
                 const double f = sd == 0 ? fb : -fb;
                 int l2 = b.ja, h2 = b.jb;
                 while (l2 < h2) {
@@ -1180,7 +1169,7 @@ __device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *m
                 jj2[0] = l2;
             }
             { // ... and of its last bin: a short walk from there (a tile rarely spans more than a few segments)
-                const double fb = tile_binf<BPT>(sF, e.e[sd]);
+                const double fb = tile_binf(g, jt0, e.e[sd]);
                 const double f = sd == 0 ? fb : -fb;
                 int l2 = jj2[0];
                 while (l2 < b.jb) { const double Fk = knot_F(sK, l2 + 1, e.dm, e.dn); if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) l2++; else break; }
@@ -1199,15 +1188,15 @@ __device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *m
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) { const int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
     if (lane < gcount) ent[lane].off = incl - nsub;
+    __syncwarp();
     return __shfl_sync(0xffffffffu, incl, 31);
 }
 
-// Fill step 2: thread t < nsw builds sub-entry w0 + t of the round (its record found from the entries' offsets).
-template <int BPT>
-__device__ __noinline__ void fill_subs(const double *coeff, const double *gq, int K, int G, int gcount, int w0, int nsw, const double *sF,
-                                       const double *sK, const FillEntry *ent, SubEntry *sub) {
+// Producer warp, step 2: lane t < nsw builds sub-entry w0 + t of the round (its record found from the entries' offsets) in `sub`.
+__device__ __noinline__ void fill_subs(const double *coeff, const double *gq, int K, int G, int gcount, int w0, int nsw, Grid g,
+                                       long long jt0, const double *sK, const FillEntry *ent, SubEntry *sub) {
     // (coeff, gq: this walker's blocks)
-    const int t = threadIdx.x;
+    const int t = threadIdx.x & 31;
     if (t >= nsw) return;
     const int idx = w0 + t;
     int ei = 0;
@@ -1239,7 +1228,7 @@ __device__ __noinline__ void fill_subs(const double *coeff, const double *gq, in
         int lo = e.s[sd], hi = e.e[sd] + 1; // first lb in [lo, hi] where P flips
         while (lo < hi) {
             const int mid = (lo + hi) >> 1;
-            const double f = sg * tile_binf<BPT>(sF, mid);
+            const double f = sg * tile_binf(g, jt0, mid);
             const bool P = e.dir > 0 ? (Fk <= f) : (Fk >= f);
             if (P == fwd) hi = mid; else lo = mid + 1;
         }
@@ -1278,188 +1267,172 @@ __device__ __noinline__ void fill_subs(const double *coeff, const double *gq, in
     sub[t] = S;
 }
 
-template <bool WRITE_H, bool LIKE, int BPT>
-__device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile_x, const int walker_y, unsigned char *smraw,
-                                              int &staged_walker) {
-    __shared__ int s_list[SUM_THREADS], s_rec[SUM_THREADS];
-    __shared__ int s_wcount[SUM_THREADS / 32];
-    __shared__ int s_nsub;
+// ---- mbarrier helpers (CTA-local producer/consumer hand-off of the sub-entry ring) ----
+__device__ __forceinline__ unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
 
-    const emrifd_walker_t wd = p.w[walker_y];
-    const int L = wd.L;
-    const int G = p.gcount[walker_y];
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
-    const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * (SUM_THREADS * BPT);
-    const long long jend = p.j_lo + p.j_cnt;                                   // exclusive
-    const long long jt1 = (jt0 + (SUM_THREADS * BPT) < jend ? jt0 + (SUM_THREADS * BPT) : jend) - 1; // inclusive
-    const long long j0 = jt0 + (long long)tid * BPT;                       // this thread's first bin
-    int nb = (int)(jt1 - j0 + 1);                                              // its number of valid bins
-    nb = nb < 0 ? 0 : (nb > BPT ? BPT : nb);
+#define PASS_FIRST 1 /* first pass of its tile: the consumers clear their accumulators and compute their bin frequencies */
+#define PASS_LAST 2  /* last pass of its tile: the consumers read out after evaluating it */
+#define PASS_QUIT 4  /* no more tiles */
+struct SumShared { // static shared memory of the mode-sum CTA
+    unsigned long long full[SUM_RING], empty[SUM_RING]; // mbarriers: pass published / pass released by all consumer warps
+    int4 hdr[SUM_RING];                                 // (tile, walker, sub-entries in the pass, PASS_* flags)
+    int list[64], rec[64];                              // producer: overlapping group records waiting for a fill round
+};
+
+// ------------------------------------------------------------------------------------------------------------------
+// Producer warp.  For every tile it owns (persistent launch: pulled from the queue empty_tile_kernel filled; direct launch: the
+// CTA's own tile) it scans the walker's group records in order, turns the overlapping ones into sub-entries (fill_entries /
+// fill_subs, 32 per pass) and publishes the passes through the ring.  It runs ahead of the consumers by up to SUM_RING passes --
+// across tile boundaries -- so the dependent global loads of the fill (record -> branch -> coefficient quads) never stall them.
+// A pass is published one step late (when the next one has been built, or the tile ends), so that the last pass of a tile
+// can carry PASS_LAST.
+// ------------------------------------------------------------------------------------------------------------------
+template <bool LIKE, int BPT, bool PERSISTENT>
+__device__ __forceinline__ void sum_producer(const SumParams &p, SumShared &sh, SubEntry *ring, FillEntry *ent, double *sK) {
+    constexpr int TILE = SUM_CT * BPT;
+    const int lane = threadIdx.x & 31;
     const long long zero = p.g.zero;
-    const long long pos_lo = zero + jt0, pos_hi = zero + jt1;
-    const long long neg_lo = zero - jt1, neg_hi = zero - jt0;
-
-    const emrifd_branch_t *br = p.br + wd.mode_off * MAXBR;
-    const int *leader = p.leader + wd.mode_off;
-    const double *coeff = p.coeff + wd.coeff_off;
-    const double *gq = p.gq + 16 * wd.teuk_off;
-
-    // dynamic smem: accumulators [4][BPT][ACC_STRIDE] | sub-entries | fill entries | sF | knots (t, f_phi, f_r)[L]
-    double *acc = reinterpret_cast<double *>(smraw);
-    SubEntry *sub = reinterpret_cast<SubEntry *>(acc + 4 * BPT * ACC_STRIDE);
-    FillEntry *ent = reinterpret_cast<FillEntry *>(sub + SUM_SUBCAP);
-    double *sF = reinterpret_cast<double *>(ent + SUM_ECAP); // exact bin frequencies             [BPT][SUM_THREADS]
-    double *sK = sF + BPT * SUM_THREADS;
-    // ---- does any work-list chunk touch this tile? ----
-    const int nrec = G * MAXBR;
-    const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
-    bool any = false;
-    for (int ch = 0; ch * SUM_THREADS < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
-    if (p.wstatus[walker_y]) any = false; // failed walker: zeros (and a NaN likelihood from like_finalize_kernel)
-    // (direct-grid launches only: empty_tile_kernel has dealt with this tile)
-    if (!any && !(LIKE && (p.no_empty || tile_truncated(p, jt0, SUM_THREADS * BPT)))) return;
-    if (LIKE) { // the read-out's data lines: start them towards L2 now (a third of them come from DRAM)
-        const int lb0 = wid * (32 * BPT) + lane * BPT; // BPT consecutive bins of the warp's read-out range per lane
-        if (jt0 + lb0 <= jt1) {
-            const long long j = jt0 + lb0;
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + j));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + p.n_data + j));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + j));
-            asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + p.n_data + j));
-        }
+    const long long jend = p.j_lo + p.j_cnt; // exclusive
+    int it = 0;                              // passes acquired so far
+    int pending = -1;                        // slot built but not yet published
+    int staged_walker = -1;
+    const unsigned long long none = ~0ull;
+    const unsigned int nq = PERSISTENT ? p.qctl[0] : 1u;
+    unsigned long long q = none, qn = none;
+    if (PERSISTENT) {
+        if (lane == 0) { const unsigned int i0 = atomicAdd(&p.qctl[1], 1u); q = i0 < nq ? p.queue[i0] : none; }
+        q = __shfl_sync(0xffffffffu, q, 0);
+    } else {
+        q = ((unsigned long long)blockIdx.y << 32) | blockIdx.x;
     }
-#pragma unroll
-    for (int i = 0; i < 4 * BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
-#pragma unroll
-    for (int b = 0; b < BPT; b++) {
-        const long long jj = j0 + b;
-        sF[b * SUM_THREADS + tid] = (b < nb) ? (p.g.fpos ? p.g.fpos[jj] : rmul((double)(int)jj, p.g.val)) : 0.0;
-    }
-
-    // ---- if some chunk touches the tile stage the walker's knots (time, f_phi, f_r) right away so that the loads overlap
-    //      the first record scan ----
-    if (any && staged_walker != walker_y) { // (a persistent CTA often gets consecutive tiles of one walker: knots stay staged)
-        staged_walker = walker_y;
-        const double *t = p.t + wd.knot_off;
-        const int R = 2 * wd.K + 4;
-        for (int i = tid; i < L; i += SUM_THREADS) {
-            sK[3 * i] = t[i];
-            sK[3 * i + 1] = coeff[((long long)i * R + 2 * wd.K) * 4];
-            sK[3 * i + 2] = coeff[((long long)i * R + 2 * wd.K + 1) * 4];
+    while (q != none) {
+        if (PERSISTENT) { // the next item: in flight during this tile
+            if (lane == 0) { const unsigned int i1 = atomicAdd(&p.qctl[1], 1u); qn = i1 < nq ? p.queue[i1] : none; }
         }
-    }
-    // (no barrier here: the staged knots and bin frequencies are first read by the fill warp, behind the two barriers of the
-    //  record scan below, so the scan's global loads are in flight together with the staging loads)
-
-    bool used = false; // the sub-entry cache holds a previous round that some warp may still be evaluating
-    for (int base = 0, ch = 0; any && base < nrec; base += SUM_THREADS, ch++) {
-        if (crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0) continue; // block-uniform: nothing of this chunk touches the tile
-        // ---- ordered compaction of this chunk's group records that overlap the tile ----
-        const int r = base + tid;
-        bool pred = false;
-        int rec = 0;
-        if (r < nrec) {
-            rec = leader[r / MAXBR] * MAXBR + (r % MAXBR);
-            const long long s0 = br[rec].start, e0 = br[rec].end;
-            pred = (e0 >= s0) && ((s0 <= pos_hi && e0 >= pos_lo) || (s0 <= neg_hi && e0 >= neg_lo));
-        }
-        const unsigned bal = __ballot_sync(0xffffffffu, pred);
-        if (used) __syncthreads(); // every warp is done with the previous chunk's sub-entries (and with s_wcount / s_list)
-        if (lane == 0) s_wcount[wid] = __popc(bal);
-        __syncthreads();
-        int off = 0, count = 0;
-#pragma unroll
-        for (int q = 0; q < SUM_THREADS / 32; q++) { const int c = s_wcount[q]; if (q < wid) off += c; count += c; }
-        if (pred) { const int pos = off + __popc(bal & ((1u << lane) - 1)); s_list[pos] = r; s_rec[pos] = rec; }
-        __syncthreads();
-        used = false;
-        for (int g0 = 0; g0 < count; g0 += SUM_ECAP) { // the overlap list is handled in rounds of one record per fill-warp lane
-            const int gcount = count - g0 < SUM_ECAP ? count - g0 : SUM_ECAP;
-            if (used) __syncthreads(); // every warp is done with the previous round's sub-entries
-            if (wid == 0) {
-                const int tot = fill_entries<BPT>(br, p.m + wd.mode_off, p.n + wd.mode_off, p.include_minus_m, zero, s_list + g0,
-                                                  s_rec + g0, gcount, jt0, jt1, sF, sK, ent);
-                if (lane == 0) s_nsub = tot;
-            }
-            __syncthreads();
-            used = true;
-            const int tot = s_nsub;
-            for (int w0 = 0; w0 < tot; w0 += SUM_SUBCAP) {
-                const int nsw = tot - w0 < SUM_SUBCAP ? tot - w0 : SUM_SUBCAP;
-                if (w0 > 0) __syncthreads(); // the previous pass has been evaluated
-                fill_subs<BPT>(coeff, gq, wd.K, G, gcount, w0, nsw, sF, sK, ent, sub); // one thread per sub-entry
-                __syncthreads();
-                if (nb <= 0) continue;
-                // ---- evaluate: every thread walks its BPT consecutive bins along each listed cubic piece ----
-                const int tb0 = tid * BPT;
-                for (int si = 0; si < nsw; si++) {
-                    const SubEntry &S = sub[si];
-                    const int s_ = S.s, e_ = S.e;
-                    const int bl = s_ - tb0 > 0 ? s_ - tb0 : 0;
-                    const int bh = e_ - tb0 < nb - 1 ? e_ - tb0 : nb - 1;
-                    if (bl > bh) continue;
-                    const unsigned int smask = S.fmask;
-                    const int side = S.flags & SE_SIDE;
-                    const double sdir = (S.flags & SE_FALL) ? -1.0 : 1.0;
-                    const double c1 = S.c1;
-                    const double d2 = 2.0 * S.c2, d3 = 3.0 * S.c3;
-                    const double *pF = sF + tid + bl * SUM_THREADS;
-                    int id0 = side * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE;       // direct term -> this side
-                    int im0 = (1 - side) * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE; // mirrored -m term -> other side
-                    // The thread's first bin goes through the out-of-line cold solve; after that the bins are taken two at a
-                    // time: roots by second-order extrapolation from the last solved bin + ONE Newton step (two independent
-                    // chains; a bin that misses the tolerance or the bracket falls back to the cold solve), then both bins are
-                    // evaluated in straight-line code.  (In the first pair the first bin's extrapolation step is zero.)
-                    double fb = flip_sign(pF[0], smask);
-                    double xb = solve_slow(c1, S.c2, S.c3, fb - S.c0, S.xlo, S.xhi, S.tol, sdir);
-                    double rb = fast_rcp(fma(xb, fma(d3, xb, d2), c1));
-                    for (int b = bl; b <= bh; b += 2) {
-                        const bool two = b < bh;
-                        double xx[2], ff[2];
-                        {
-                            const double c0 = S.c0, c2 = S.c2, c3 = S.c3, xlo = S.xlo, xhi = S.xhi, tol = S.tol;
-                            const double f1 = flip_sign(pF[0], smask);
-                            const double f2 = two ? flip_sign(pF[SUM_THREADS], smask) : f1;
-                            const double kap = fma(2.0 * d3, xb, d2) * rb; // fddot/fdot at the solved bin
-                            const double dl1 = (f1 - fb) * rb, dl2 = (f2 - fb) * rb;
-                            double x1 = fma(dl1, fma(-0.5 * kap, dl1, 1.0), xb), x2 = fma(dl2, fma(-0.5 * kap, dl2, 1.0), xb);
-                            const double g1 = x1 * fma(x1, fma(x1, c3, c2), c1) - (f1 - c0);
-                            const double g2 = x2 * fma(x2, fma(x2, c3, c2), c1) - (f2 - c0);
-                            double r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1)), r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
-                            const double dx1 = g1 * r1, dx2 = g2 * r2;
-                            x1 -= dx1; x2 -= dx2;
-                            if (!(fabs(dx1) <= tol && x1 >= xlo && x1 <= xhi)) {
-                                x1 = solve_slow(c1, c2, c3, f1 - c0, xlo, xhi, tol, sdir);
-                                r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1));
-                            }
-                            if (two && !(fabs(dx2) <= tol && x2 >= xlo && x2 <= xhi)) {
-                                x2 = solve_slow(c1, c2, c3, f2 - c0, xlo, xhi, tol, sdir);
-                                r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
-                            }
-                            xx[0] = x1; xx[1] = x2; ff[0] = f1; ff[1] = f2;
-                            xb = two ? x2 : x1; fb = f2; rb = two ? r2 : r1;
-                        }
-                        if (two) {
-                            eval_sub<2, BPT>(xx, ff, c1, d2, d3, S, p.k13_few, acc, id0, im0);
-                        } else {
-                            const double x1[1] = {xx[0]}, f1[1] = {ff[0]};
-                            eval_sub<1, BPT>(x1, f1, c1, d2, d3, S, p.k13_few, acc, id0, im0);
-                        }
-                        pF += 2 * SUM_THREADS;
-                        id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
-                    }
+        const int tile_x = (int)(q & 0xffffffffu), walker_y = (int)(q >> 32);
+        const emrifd_walker_t wd = p.w[walker_y];
+        const int G = p.gcount[walker_y];
+        const int nrec = G * MAXBR;
+        const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * TILE;
+        const long long jt1 = (jt0 + TILE < jend ? jt0 + TILE : jend) - 1; // inclusive
+        const long long pos_lo = zero + jt0, pos_hi = zero + jt1, neg_lo = zero - jt1, neg_hi = zero - jt0;
+        const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
+        bool any = false;
+        for (int ch = 0; ch * SUM_CHUNK < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
+        if (p.wstatus[walker_y]) any = false; // failed walker: zeros (and a NaN likelihood from like_finalize_kernel)
+        const bool per_bin = LIKE && (p.no_empty || tile_truncated(p, jt0, TILE));
+        if (any || per_bin) { // (else: direct-grid launch on a tile empty_tile_kernel has dealt with)
+            const emrifd_branch_t *br = p.br + wd.mode_off * MAXBR;
+            const int *leader = p.leader + wd.mode_off;
+            const double *coeff = p.coeff + wd.coeff_off;
+            const double *gq = p.gq + 16 * wd.teuk_off;
+            if (any && staged_walker != walker_y) { // knots (time, f_phi, f_r) of this walker: stay staged across its tiles
+                staged_walker = walker_y;
+                const double *t = p.t + wd.knot_off;
+                const int R = 2 * wd.K + 4;
+                for (int i = lane; i < wd.L; i += 32) {
+                    sK[3 * i] = t[i];
+                    sK[3 * i + 1] = coeff[((long long)i * R + 2 * wd.K) * 4];
+                    sK[3 * i + 2] = coeff[((long long)i * R + 2 * wd.K + 1) * 4];
                 }
+                __syncwarp();
             }
-        } // fill rounds
+            int pflags = PASS_FIRST; // flags of the next pass built for this tile
+            int count = 0;           // overlapping records waiting in sh.list
+            // a fill round: the first (up to) 32 waiting records, one per lane, become sub-entries; passes of SUM_SUBCAP go out
+            auto fill_round = [&]() {
+                const int gcount = count < 32 ? count : 32;
+                const int tot = fill_entries(br, p.m + wd.mode_off, p.n + wd.mode_off, p.include_minus_m, zero, sh.list, sh.rec, gcount,
+                                             jt0, jt1, p.g, sK, ent);
+                for (int w0 = 0; w0 < tot; w0 += SUM_SUBCAP) {
+                    const int nsw = tot - w0 < SUM_SUBCAP ? tot - w0 : SUM_SUBCAP;
+                    if (pending >= 0) { if (lane == 0) mbar_arrive(&sh.full[pending]); pending = -1; }
+                    const int slot = it % SUM_RING;
+                    mbar_wait(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
+                    it++;
+                    fill_subs(coeff, gq, wd.K, G, gcount, w0, nsw, p.g, jt0, sK, ent, ring + slot * SUM_SUBCAP);
+                    if (lane == 0) sh.hdr[slot] = make_int4(tile_x, walker_y, nsw, pflags);
+                    pflags = 0;
+                    __syncwarp();
+                    pending = slot;
+                }
+                // drop the records of this round from the list
+                const int left = count - gcount;
+                int mv_l = 0, mv_r = 0;
+                if (lane < left) { mv_l = sh.list[32 + lane]; mv_r = sh.rec[32 + lane]; }
+                __syncwarp();
+                if (lane < left) { sh.list[lane] = mv_l; sh.rec[lane] = mv_r; }
+                __syncwarp();
+                count = left;
+            };
+            for (int base = 0; any && base < nrec; base += 32) {
+                const int ch = base / SUM_CHUNK;
+                if (crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0) { base = (ch + 1) * SUM_CHUNK - 32; continue; } // chunk outside the tile
+                // ---- ordered compaction of the group records that overlap the tile ----
+                const int r = base + lane;
+                bool pred = false;
+                int rec = 0;
+                if (r < nrec) {
+                    rec = leader[r / MAXBR] * MAXBR + (r % MAXBR);
+                    const long long s0 = br[rec].start, e0 = br[rec].end;
+                    pred = (e0 >= s0) && ((s0 <= pos_hi && e0 >= pos_lo) || (s0 <= neg_hi && e0 >= neg_lo));
+                }
+                const unsigned bal = __ballot_sync(0xffffffffu, pred);
+                if (pred) { const int pos = count + __popc(bal & ((1u << lane) - 1)); sh.list[pos] = r; sh.rec[pos] = rec; }
+                count += __popc(bal);
+                __syncwarp();
+                if (count >= 32) fill_round();
+            }
+            if (count > 0) fill_round();
+            // ---- end of the tile: its last pass carries PASS_LAST (a tile without sub-entries gets an empty pass) ----
+            if (pending < 0 || (pflags & PASS_FIRST)) {
+                if (pending >= 0) { if (lane == 0) mbar_arrive(&sh.full[pending]); pending = -1; }
+                const int slot = it % SUM_RING;
+                mbar_wait(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
+                it++;
+                if (lane == 0) sh.hdr[slot] = make_int4(tile_x, walker_y, 0, PASS_FIRST | PASS_LAST);
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&sh.full[slot]);
+            } else {
+                if (lane == 0) { sh.hdr[pending].w |= PASS_LAST; mbar_arrive(&sh.full[pending]); }
+                pending = -1;
+            }
+        }
+        if (PERSISTENT) q = __shfl_sync(0xffffffffu, qn, 0); else q = none;
     }
+    { // no more tiles
+        const int slot = it % SUM_RING;
+        mbar_wait(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
+        if (lane == 0) { sh.hdr[slot] = make_int4(0, 0, 0, PASS_QUIT); mbar_arrive(&sh.full[slot]); }
+    }
+}
 
-    // ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
-    // Warp-local transposed read-out: a warp owns 32*BPT consecutive bins (its lanes' bins); in iteration i lane l
-    // finalises bin 32*i + l of them, so the warp stores 512 contiguous bytes per array and reads the data stream the
-    // same way.  Only __syncwarp is needed: warps that finish early read out while the others still evaluate.
-    // The data loads of a group of iterations are issued together, ahead of the stores (which could alias them for all the
-    // compiler knows), so their latencies overlap.
-    __syncwarp();
+// ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
+// Warp-local transposed read-out: a warp owns 32*BPT consecutive bins (its lanes' bins); in iteration i lane l
+// finalises bin 32*i + l of them, so the warp stores 512 contiguous bytes per array and reads the data stream the
+// same way.  Only __syncwarp is needed.  The data loads of a group of iterations are issued together, ahead of the
+// stores (which could alias them for all the compiler knows), so their latencies overlap.
+template <bool WRITE_H, bool LIKE, int BPT>
+__device__ __forceinline__ void sum_readout(const SumParams &p, const int tile_x, const int walker_y, const long long jt0,
+                                            const long long jt1, const double *acc) {
+    const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    const emrifd_walker_t *wp = p.w + walker_y;
+    const double sc = wp->scale, c2 = wp->cos2psi, s2 = wp->sin2psi;
+    const long long out_off = wp->out_off;
+    const long long zero = p.g.zero;
     double a0 = 0, a1 = 0, a2 = 0;
     const int ntile = (int)(jt1 - jt0 + 1);
     constexpr int RG = BPT % 3 == 0 ? 3 : (BPT % 2 == 0 ? 2 : 1); // read-out group
@@ -1487,16 +1460,15 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
             if (j == 0) { wpr += wmr; wpi += wmi; wmr = wpr; wmi = wpi; }
             const double pr_ = 0.5 * (-wmr - wpr), pi_ = 0.5 * (-wmi + wpi);
             const double xr_ = 0.5 * (wmi + wpi), xi_ = 0.5 * (-wmr + wpr);
-            const double sc = wd.scale, c2 = wd.cos2psi, s2 = wd.sin2psi;
             const double hpr = sc * (c2 * pr_ - s2 * xr_), hpi = sc * (c2 * pi_ - s2 * xi_);
             const double hxr = sc * (s2 * pr_ + c2 * xr_), hxi = sc * (s2 * pi_ + c2 * xi_);
             if (WRITE_H) {
                 if (p.mask_positive) {
-                    const long long o = wd.out_off + (j - p.j_lo);
+                    const long long o = out_off + (j - p.j_lo);
                     p.hp[o] = make_double2(hpr, hpi);
                     p.hc[o] = make_double2(hxr, hxi);
                 } else {
-                    const long long o = wd.out_off + zero;
+                    const long long o = out_off + zero;
                     p.hp[o + j] = make_double2(hpr, hpi);
                     p.hc[o + j] = make_double2(hxr, hxi);
                     if (j > 0) { // Hermitian mirror: h(-f) = conj h(f)
@@ -1514,7 +1486,7 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
             }
         }
     }
-    if (LIKE) { // per-warp partial sums (no CTA barrier); like_finalize_kernel adds them in a fixed order
+    if (LIKE) { // per-warp partial sums; like_finalize_kernel adds them in a fixed order
 #pragma unroll
         for (int o = 16; o > 0; o >>= 1) {
             a0 += __shfl_down_sync(0xffffffffu, a0, o);
@@ -1522,49 +1494,146 @@ __device__ __forceinline__ void mode_sum_tile(const SumParams &p, const int tile
             a2 += __shfl_down_sync(0xffffffffu, a2, o);
         }
         if (lane == 0) {
-            double *o = p.partial + (((long long)walker_y * p.ntiles + tile_x) * (SUM_THREADS / 32) + wid) * 3;
+            double *o = p.partial + (((long long)walker_y * p.ntiles + tile_x) * SUM_CW + wid) * 3;
             o[0] = a0; o[1] = a1; o[2] = a2;
         }
     }
 }
 
-// Persistent CTAs (one grid of #SM x resident-CTAs) pull the non-empty tiles queued by empty_tile_kernel: the heavy kernel
-// is never launched on the >90 % of the band that a sparse system leaves empty, and tiles of very different cost balance
-// dynamically.
+// ------------------------------------------------------------------------------------------------------------------
+// Consumer warp: owns 32 * BPT consecutive bins of every tile the CTA handles (a thread owns BPT consecutive (+f, -f) pairs;
+// accumulators and bin frequencies live in the warp's own shared-memory columns).  It waits for the next pass, walks its bins
+// along each of the pass's cubic pieces, releases the slot, and reads out after a tile's last pass.  Consumer warps never wait
+// for one another: a warp with less work in a tile runs ahead, up to SUM_RING passes, into the following tiles.
+// ------------------------------------------------------------------------------------------------------------------
 template <bool WRITE_H, bool LIKE, int BPT>
-__global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
-    extern __shared__ __align__(16) unsigned char smraw[];
-    __shared__ unsigned long long s_q[2]; // double-buffered queue items: the next one is fetched while the current tile runs
-    const unsigned int nq = p.qctl[0];
-    const unsigned long long none = ~0ull;
-    if (threadIdx.x == 0) {
-        const unsigned int it = atomicAdd(&p.qctl[1], 1u);
-        s_q[0] = it < nq ? p.queue[it] : none;
-    }
-    __syncthreads();
-    int staged_walker = -1;
-    for (int cur = 0;; cur ^= 1) {
-        const unsigned long long q = s_q[cur];
-        if (q == none) return;
-        unsigned long long qn = none;
-        if (threadIdx.x == 0) { // in flight during the tile; consumed just before the barrier below
-            const unsigned int it = atomicAdd(&p.qctl[1], 1u);
-            if (it < nq) qn = p.queue[it];
+__device__ __forceinline__ void sum_consumer(const SumParams &p, SumShared &sh, const SubEntry *ring, double *acc, double *sF) {
+    constexpr int TILE = SUM_CT * BPT;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const long long jend = p.j_lo + p.j_cnt; // exclusive
+    for (int it = 0;; it++) {
+        const int slot = it % SUM_RING;
+        mbar_wait(&sh.full[slot], (it / SUM_RING) & 1);
+        const int4 hd = sh.hdr[slot];
+        if (hd.w & PASS_QUIT) return;
+        const int tile_x = hd.x, walker_y = hd.y, nsw = hd.z;
+        const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * TILE;
+        const long long jt1 = (jt0 + TILE < jend ? jt0 + TILE : jend) - 1;  // inclusive
+        const long long j0 = jt0 + (long long)tid * BPT;                     // this thread's first bin
+        int nb = (int)(jt1 - j0 + 1);                                        // its number of valid bins
+        nb = nb < 0 ? 0 : (nb > BPT ? BPT : nb);
+        if (hd.w & PASS_FIRST) {
+            if (LIKE) { // the read-out's data lines: start them towards L2 now (a third of them come from DRAM)
+                const int lb0 = wid * (32 * BPT) + lane * BPT; // BPT consecutive bins of the warp's read-out range per lane
+                if (jt0 + lb0 <= jt1) {
+                    const long long j = jt0 + lb0;
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + j));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + p.n_data + j));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + j));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + p.n_data + j));
+                }
+            }
+#pragma unroll
+            for (int i = 0; i < 4 * BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
+#pragma unroll
+            for (int b = 0; b < BPT; b++) {
+                const long long jj = j0 + b;
+                sF[b * SUM_CT + tid] = (b < nb) ? (p.g.fpos ? p.g.fpos[jj] : rmul((double)(int)jj, p.g.val)) : 0.0;
+            }
         }
-        mode_sum_tile<WRITE_H, LIKE, BPT>(p, (int)(q & 0xffffffffu), (int)(q >> 32), smraw, staged_walker);
-        if (threadIdx.x == 0) s_q[cur ^ 1] = qn;
-        __syncthreads(); // every warp has left the tile (shared memory is reused) and sees the next item
+        if (nb > 0) {
+            // ---- evaluate: every thread walks its BPT consecutive bins along each listed cubic piece ----
+            const SubEntry *sub = ring + slot * SUM_SUBCAP;
+            const int tb0 = tid * BPT;
+            for (int si = 0; si < nsw; si++) {
+                const SubEntry &S = sub[si];
+                const int s_ = S.s, e_ = S.e;
+                const int bl = s_ - tb0 > 0 ? s_ - tb0 : 0;
+                const int bh = e_ - tb0 < nb - 1 ? e_ - tb0 : nb - 1;
+                if (bl > bh) continue;
+                const unsigned int smask = S.fmask;
+                const int side = S.flags & SE_SIDE;
+                const double sdir = (S.flags & SE_FALL) ? -1.0 : 1.0;
+                const double c1 = S.c1;
+                const double d2 = 2.0 * S.c2, d3 = 3.0 * S.c3;
+                const double *pF = sF + tid + bl * SUM_CT;
+                int id0 = side * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE;       // direct term -> this side
+                int im0 = (1 - side) * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE; // mirrored -m term -> other side
+                // The thread's first bin goes through the out-of-line cold solve; after that the bins are taken two at a
+                // time: roots by second-order extrapolation from the last solved bin + ONE Newton step (two independent
+                // chains; a bin that misses the tolerance or the bracket falls back to the cold solve), then both bins are
+                // evaluated in straight-line code.  (In the first pair the first bin's extrapolation step is zero.)
+                double fb = flip_sign(pF[0], smask);
+                double xb = solve_slow(c1, S.c2, S.c3, fb - S.c0, S.xlo, S.xhi, S.tol, sdir);
+                double rb = fast_rcp(fma(xb, fma(d3, xb, d2), c1));
+                for (int b = bl; b <= bh; b += 2) {
+                    const bool two = b < bh;
+                    double xx[2], ff[2];
+                    {
+                        const double c0 = S.c0, c2 = S.c2, c3 = S.c3, xlo = S.xlo, xhi = S.xhi, tol = S.tol;
+                        const double f1 = flip_sign(pF[0], smask);
+                        const double f2 = two ? flip_sign(pF[SUM_CT], smask) : f1;
+                        const double kap = fma(2.0 * d3, xb, d2) * rb; // fddot/fdot at the solved bin
+                        const double dl1 = (f1 - fb) * rb, dl2 = (f2 - fb) * rb;
+                        double x1 = fma(dl1, fma(-0.5 * kap, dl1, 1.0), xb), x2 = fma(dl2, fma(-0.5 * kap, dl2, 1.0), xb);
+                        const double g1 = x1 * fma(x1, fma(x1, c3, c2), c1) - (f1 - c0);
+                        const double g2 = x2 * fma(x2, fma(x2, c3, c2), c1) - (f2 - c0);
+                        double r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1)), r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
+                        const double dx1 = g1 * r1, dx2 = g2 * r2;
+                        x1 -= dx1; x2 -= dx2;
+                        if (!(fabs(dx1) <= tol && x1 >= xlo && x1 <= xhi)) {
+                            x1 = solve_slow(c1, c2, c3, f1 - c0, xlo, xhi, tol, sdir);
+                            r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1));
+                        }
+                        if (two && !(fabs(dx2) <= tol && x2 >= xlo && x2 <= xhi)) {
+                            x2 = solve_slow(c1, c2, c3, f2 - c0, xlo, xhi, tol, sdir);
+                            r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
+                        }
+                        xx[0] = x1; xx[1] = x2; ff[0] = f1; ff[1] = f2;
+                        xb = two ? x2 : x1; fb = f2; rb = two ? r2 : r1;
+                    }
+                    if (two) {
+                        eval_sub<2, BPT>(xx, ff, c1, d2, d3, S, p.k13_few, acc, id0, im0);
+                    } else {
+                        const double x1[1] = {xx[0]}, f1[1] = {ff[0]};
+                        eval_sub<1, BPT>(x1, f1, c1, d2, d3, S, p.k13_few, acc, id0, im0);
+                    }
+                    pF += 2 * SUM_CT;
+                    id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
+                }
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&sh.empty[slot]); // the warp is done with this pass's sub-entries
+        if (hd.w & PASS_LAST) {
+            sum_readout<WRITE_H, LIKE, BPT>(p, tile_x, walker_y, jt0, jt1, acc);
+            __syncwarp(); // the warp's accumulator columns are cleared again by the next tile's first pass
+        }
     }
 }
 
-// Small launches (a few hundred tiles: one bin-sharded slice of a single long waveform, or a single short waveform) fit in
-// about one wave of CTAs; there the hardware's breadth-first placement of a plain (tile, walker) grid balances the SMs
-// better than queue order (measured on the 8-GPU bin-sharded configs[3] slices: 8.6 vs 13.1 ms), so they keep a direct grid.
-template <bool WRITE_H, bool LIKE, int BPT>
-__global__ void __launch_bounds__(SUM_THREADS, SUM_MINB) mode_sum_direct_kernel(SumParams p) {
+// Persistent CTAs (one grid of #SM x resident CTAs) work through the non-empty tiles queued by empty_tile_kernel: the heavy
+// kernel is never launched on the > 90 % of the band that a sparse system leaves empty, and tiles of very different cost
+// balance dynamically.  PERSISTENT = false: a plain (tile, walker) grid for launches of about one wave (a bin-sharded slice of
+// a single long waveform, a single short waveform), where the hardware's breadth-first CTA placement balances the SMs better
+// than queue order (measured on the 8-GPU bin-sharded configs[3] slices).
+template <bool WRITE_H, bool LIKE, int BPT, bool PERSISTENT>
+__global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    int staged_walker = -1;
-    mode_sum_tile<WRITE_H, LIKE, BPT>(p, (int)blockIdx.x, (int)blockIdx.y, smraw, staged_walker);
+    __shared__ SumShared sh;
+    // dynamic smem: accumulators [4][BPT][ACC_STRIDE] | bin frequencies [BPT][SUM_CT] | sub-entry ring | fill entries | knots (t, f_phi, f_r)[L]
+    double *acc = reinterpret_cast<double *>(smraw);
+    double *sF = acc + 4 * BPT * ACC_STRIDE;
+    SubEntry *ring = reinterpret_cast<SubEntry *>(sF + BPT * SUM_CT);
+    FillEntry *ent = reinterpret_cast<FillEntry *>(ring + SUM_RING * SUM_SUBCAP);
+    double *sK = reinterpret_cast<double *>(ent + SUM_ECAP);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < SUM_RING; i++) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], SUM_CW); }
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    }
+    __syncthreads(); // the only CTA-wide barrier: from here on the warps synchronise through the ring's mbarriers alone
+    if (threadIdx.x >= SUM_CT) sum_producer<LIKE, BPT, PERSISTENT>(p, sh, ring, ent, sK);
+    else sum_consumer<WRITE_H, LIKE, BPT>(p, sh, ring, acc, sF);
 }
 
 // deterministic second stage: one CTA per walker
@@ -1926,8 +1995,8 @@ static size_t spline_smem_bytes(int L, bool tiled) {
 }
 
 static size_t sum_smem_bytes(int L, int bpt = SUM_BPT) {
-    return sizeof(double) * 4 * bpt * ACC_STRIDE + sizeof(SubEntry) * SUM_SUBCAP + sizeof(FillEntry) * SUM_ECAP +
-           sizeof(double) * bpt * SUM_THREADS + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
+    return sizeof(double) * 4 * bpt * ACC_STRIDE + sizeof(double) * bpt * SUM_CT + sizeof(SubEntry) * SUM_RING * SUM_SUBCAP +
+           sizeof(FillEntry) * SUM_ECAP + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
 
 static int ensure_bytes(emrifd_handle *h, void **ptr, int64_t *cap, int64_t need, bool pinned_host = false) {
@@ -2034,16 +2103,10 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     SET_ATTR(group_index_kernel, big);
     SET_ATTR(mode_select_kernel, SEL_CAP * 10);
 #define SET_SMEM(W_, L_) \
-    SET_ATTR((mode_sum_kernel<W_, L_, SUM_BPT>), big); SET_ATTR((mode_sum_kernel<W_, L_, SUM_BPT_WIDE>), big); \
-    SET_ATTR((mode_sum_direct_kernel<W_, L_, SUM_BPT>), big); SET_ATTR((mode_sum_direct_kernel<W_, L_, SUM_BPT_WIDE>), big);
+    SET_ATTR((mode_sum_kernel<W_, L_, SUM_BPT, true>), big); SET_ATTR((mode_sum_kernel<W_, L_, SUM_BPT, false>), big);
     SET_SMEM(true, false) SET_SMEM(true, true) SET_SMEM(false, true)
 #undef SET_SMEM
 #undef SET_ATTR
-    {
-        const char *fb = getenv("EMRIFD_BPT");
-        h->force_bpt = fb ? atoi(fb) : 0;
-        if (h->force_bpt != SUM_BPT && h->force_bpt != SUM_BPT_WIDE) h->force_bpt = 0;
-    }
     if (!ok || cudaGetLastError() != cudaSuccess) { emrifd_destroy(h); return EMRIFD_ERR_CUDA; }
     *out = h;
     return 0;
@@ -2053,7 +2116,7 @@ int emrifd_destroy(emrifd_handle_t *h) {
     if (!h) return 0;
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
-    cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_queue); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd); cudaFree(h->d_tiledd_w);
+    cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_queue); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd);
     cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq); cudaFree(h->d_gmem); cudaFree(h->d_goff);
     if (h->h_ws) cudaFreeHost(h->h_ws);
     for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
@@ -2166,8 +2229,7 @@ int emrifd_batch_segment(emrifd_handle_t *h, const emrifd_walker_t *walkers, int
 static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const double *t, const double *coeff,
                          const int32_t *m_arr, const int32_t *n_arr, const double *ylm, const emrifd_branch_t *branches,
                          int64_t N, double val, const double *fpos, int flags, int64_t j_lo, int64_t j_cnt,
-                         double *hp, double *hc, double *like_out, int64_t tile_first = 0, int64_t tile_stride = 1,
-                         int bpt_req = 0) {
+                         double *hp, double *hc, double *like_out, int64_t tile_first = 0, int64_t tile_stride = 1) {
     const bool write_h = hp && hc, like = like_out != nullptr;
     if (!write_h && !like) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum: nothing to compute (no output requested)");
     if (like && !h->d_data) return set_err(h, EMRIFD_ERR_NO_DATA, "likelihood requested before emrifd_set_data");
@@ -2184,11 +2246,8 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     p.include_minus_m = (flags & EMRIFD_INCLUDE_MINUS_M) != 0; p.mask_positive = mask_pos;
     p.hp = (double2 *)hp; p.hc = (double2 *)hc;
     p.dw = (const double2 *)h->d_data; p.wf = h->d_wfac; p.n_data = h->n_data;
-    // bins per thread: always the base variant (4 bins, 1024-bin tiles, three CTAs per SM), so that a walker's result does not depend
-    // on which batch it is evaluated in; the wide variant is an explicit A/B choice (EMRIFD_BPT=6)
-    int bpt = bpt_req ? bpt_req : h->force_bpt;
-    if (!bpt) bpt = SUM_BPT;
-    const int64_t tile_bins = (int64_t)SUM_THREADS * bpt;
+    // one tile shape for every launch, so that a walker's result does not depend on which batch it is evaluated in
+    const int64_t tile_bins = SUM_TILE;
     const int64_t ntiles_all = (j_cnt + tile_bins - 1) / tile_bins;
     if (tile_stride < 1 || tile_first < 0) return set_err(h, EMRIFD_ERR_INVALID, "batch_sum: bad tile_first / tile_stride");
     if (tile_first >= ntiles_all) { // this rank owns no tile: all sums are zero
@@ -2198,7 +2257,7 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     const int64_t ntiles = (ntiles_all - tile_first + tile_stride - 1) / tile_stride; // tiles of this launch
     p.tile_first = tile_first; p.tile_stride = tile_stride;
     if (like) {
-        int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * 3 * ntiles * (SUM_THREADS / 32) * B);
+        int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * 3 * ntiles * SUM_CW * B);
         if (rc) return rc;
         p.partial = h->d_partial;
     }
@@ -2223,19 +2282,19 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
         CUDA_TRY(h, cudaGetLastError());
         p.leader = h->d_leader; p.gcount = h->d_gcount; p.gq = h->d_gq; p.wstatus = h->d_wstatus; p.k13_few = h->k13_few;
     }
-    const int cpw = (Kmax * MAXBR + SUM_THREADS - 1) / SUM_THREADS;
+    const int cpw = (Kmax * MAXBR + SUM_CHUNK - 1) / SUM_CHUNK;
     {
         int rc = ensure_bytes(h, (void **)&h->d_chunk, &h->chunk_cap, (int64_t)sizeof(long long) * 2 * cpw * B);
         if (rc) return rc;
         dim3 cgrid((unsigned)cpw, (unsigned)B);
-        chunk_range_kernel<<<cgrid, SUM_THREADS, 0, h->stream>>>(h->d_walkers, branches, h->d_leader, h->d_gcount, (N - 1) / 2, h->d_chunk, cpw);
+        chunk_range_kernel<<<cgrid, SUM_CHUNK, 0, h->stream>>>(h->d_walkers, branches, h->d_leader, h->d_gcount, (N - 1) / 2, h->d_chunk, cpw);
         h->launches++;
         p.chunk_rng = h->d_chunk; p.cpw = cpw;
         // per-tile sum |d~|^2 table of the injected data: usable when this launch's tiles coincide with the table's
         // (a truncated last tile is sent through the per-bin path by the kernels, see tile_truncated)
-        p.tile_dd = (like && (j_lo % tile_bins) == 0) ? (bpt == SUM_BPT ? h->d_tiledd : h->d_tiledd_w) : nullptr;
+        p.tile_dd = (like && (j_lo % tile_bins) == 0) ? h->d_tiledd : nullptr;
     }
-    const size_t smem = sum_smem_bytes(Lmax, bpt);
+    const size_t smem = sum_smem_bytes(Lmax);
     if ((int64_t)smem > h->max_dyn_smem) return set_err(h, EMRIFD_ERR_TOO_MANY_KNOTS, "trajectory too long for the shared-memory staging of the mode-sum kernel");
     dim3 grid((unsigned)ntiles, (unsigned)B);
     int ev = -1;
@@ -2250,34 +2309,27 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
         p.queue = (unsigned long long *)h->d_queue + 2;
         CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, 16, h->stream));
     }
-    // dispatch on (WRITE_H, LIKE, bins per thread)
-#define SUM_DISPATCH(KERNEL, GRID, SMEM)                                                                              \
-    do {                                                                                                              \
-        if (bpt == SUM_BPT) {                                                                                         \
-            if (write_h && like) KERNEL<true, true, SUM_BPT><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);              \
-            else if (write_h) KERNEL<true, false, SUM_BPT><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);                \
-            else KERNEL<false, true, SUM_BPT><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);                             \
-        } else {                                                                                                      \
-            if (write_h && like) KERNEL<true, true, SUM_BPT_WIDE><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);         \
-            else if (write_h) KERNEL<true, false, SUM_BPT_WIDE><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);           \
-            else KERNEL<false, true, SUM_BPT_WIDE><<<GRID, SUM_THREADS, SMEM, h->stream>>>(p);                        \
-        }                                                                                                             \
+    // dispatch on (WRITE_H, LIKE)
+#define SUM_DISPATCH(KERNEL, THREADS, GRID, SMEM, ...)                                                   \
+    do {                                                                                                 \
+        if (write_h && like) KERNEL<true, true, SUM_BPT, ##__VA_ARGS__><<<GRID, THREADS, SMEM, h->stream>>>(p);  \
+        else if (write_h) KERNEL<true, false, SUM_BPT, ##__VA_ARGS__><<<GRID, THREADS, SMEM, h->stream>>>(p);    \
+        else KERNEL<false, true, SUM_BPT, ##__VA_ARGS__><<<GRID, THREADS, SMEM, h->stream>>>(p);                 \
     } while (0)
-    SUM_DISPATCH(empty_tile_kernel, grid, 0);
+    SUM_DISPATCH(empty_tile_kernel, EMPTY_THREADS, grid, 0);
     h->launches++;
     int per_sm = 0;
-    if (bpt == SUM_BPT) cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, true, SUM_BPT>, SUM_THREADS, smem);
-    else cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, true, SUM_BPT_WIDE>, SUM_THREADS, smem);
+    cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, true, SUM_BPT, true>, SUM_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
     int64_t pgrid = (int64_t)h->num_sms * per_sm;
-    if (ntiles * B <= 4 * pgrid) SUM_DISPATCH(mode_sum_direct_kernel, grid, smem); // about one wave: direct grid
-    else SUM_DISPATCH(mode_sum_kernel, (unsigned)pgrid, smem);
+    if (ntiles * B <= 4 * pgrid) SUM_DISPATCH(mode_sum_kernel, SUM_THREADS, grid, smem, false); // about one wave: direct grid
+    else SUM_DISPATCH(mode_sum_kernel, SUM_THREADS, (unsigned)pgrid, smem, true);
 #undef SUM_DISPATCH
     if (ev >= 0) cudaEventRecord(h->ev_b[ev], h->stream);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     if (like) {
-        like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, ntiles * (SUM_THREADS / 32), like_out, h->d_wstatus);
+        like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, ntiles * SUM_CW, like_out, h->d_wstatus);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -2295,10 +2347,7 @@ int emrifd_batch_sum(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t
     if ((rc = check_grid(h, N, val, fpos))) return rc;
     cudaSetDevice(h->device);
     if ((rc = upload_walkers(h, walkers, B))) return rc;
-    // a slice that does not start on a wide-tile boundary keeps the base tiles (slice starts are aligned to emrifd_tile_bins())
-    const int bpt_req = (j_lo % ((int64_t)SUM_THREADS * SUM_BPT_WIDE) == 0) ? 0 : SUM_BPT;
-    return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, j_lo, j_cnt, hp, hc, like_out, 0, 1,
-                         bpt_req);
+    return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, j_lo, j_cnt, hp, hc, like_out);
 }
 
 int emrifd_tile_bins(void) { return SUM_TILE; }
@@ -2317,7 +2366,7 @@ int emrifd_batch_sum_cyclic(emrifd_handle_t *h, const emrifd_walker_t *walkers, 
     cudaSetDevice(h->device);
     if ((rc = upload_walkers(h, walkers, B))) return rc;
     return batch_sum_dev(h, B, Lmax, Kmax, t, coeff, m_arr, n_arr, ylm, branches, N, val, fpos, flags, 0, (N + 1) / 2, hp, hc, like_out,
-                         tile_first, tile_stride, SUM_BPT); // ownership is defined on emrifd_tile_bins() = base tiles
+                         tile_first, tile_stride); // ownership is defined on tiles of emrifd_tile_bins() bins
 }
 
 int emrifd_fd_waveform_batch(emrifd_handle_t *h, const emrifd_walker_t *walkers, int64_t B,
@@ -2357,14 +2406,12 @@ int emrifd_set_data(emrifd_handle_t *h, const double *d_whitened, const double *
     if (!h || !d_whitened || !noise_factor || n <= 0) return set_err(h, EMRIFD_ERR_INVALID, "set_data: bad argument");
     h->d_data = d_whitened; h->d_wfac = noise_factor; h->n_data = n;
     cudaSetDevice(h->device);
-    const int tile = SUM_THREADS * SUM_BPT, tile_w = SUM_THREADS * SUM_BPT_WIDE;
-    const int64_t nt = (n + tile - 1) / tile, nt_w = (n + tile_w - 1) / tile_w;
+    const int tile = SUM_TILE;
+    const int64_t nt = (n + tile - 1) / tile;
     int rc = ensure_bytes(h, (void **)&h->d_tiledd, &h->tiledd_cap, (int64_t)sizeof(double) * nt);
     if (rc) return rc;
-    if ((rc = ensure_bytes(h, (void **)&h->d_tiledd_w, &h->tiledd_w_cap, (int64_t)sizeof(double) * nt_w))) return rc;
     tile_dd_kernel<<<(unsigned)nt, 256, 0, h->stream>>>((const double2 *)d_whitened, n, tile, h->d_tiledd);
-    tile_dd_kernel<<<(unsigned)nt_w, 256, 0, h->stream>>>((const double2 *)d_whitened, n, tile_w, h->d_tiledd_w);
-    h->launches += 2;
+    h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }

@@ -46,8 +46,8 @@ def bin_work_histogram(branches, m_arr, N):
 
 def balanced_bin_slices(work, world, base_cost=0.02, align=1024):
     """Cut [0, len(work)) into ``world`` contiguous slices of equal cost; every bin costs ``base_cost``
-    (store / data read) plus its evaluations.  Slice starts are multiples of ``align`` (the mode-sum kernel's tile
-    size: tiles then coincide with the precomputed per-tile sum|d~|^2 table, so empty tiles stay on the fast path).
+    (store / data read) plus its evaluations.  Slice starts are multiples of ``align`` (pass the mode-sum kernel's tile
+    size ``emrifd_tile_bins()``: tiles then coincide with the precomputed per-tile sum|d~|^2 table, so empty tiles stay on the fast path).
     Returns [(j_lo, j_cnt)] * world."""
     cost = np.asarray(work, dtype=np.float64) + base_cost
     c = np.concatenate([[0.0], np.cumsum(cost)])
@@ -159,7 +159,7 @@ def gpu_bin_sharded_loglike(db, N, val=0.0, fpos_dev=None, include_minus_m=True,
                                        db.branches.data_ptr(), None))
     if slices is None:
         work = bin_work_histogram(db.branches_host(), pb.m, N)
-        slices = balanced_bin_slices(work, world)
+        slices = balanced_bin_slices(work, world, align=int(h.lib.emrifd_tile_bins()))
 
     def partial(j_lo, j_cnt):
         out = torch.zeros((pb.B, 3), dtype=torch.float64, device=h.torch_device)
