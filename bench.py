@@ -397,6 +397,7 @@ def main():
     # work counters, averaged over the rotating batches: per-(l,m,n) evaluations (SURVEY's unit), MBE, and the stationary
     # points the kernel actually solves (one per (m, n) group and bin)
     evals = mbe = gevals = 0
+    solves_per_batch = []
     for pb, db in zip(pbs, dbs):
         nev = torch.zeros((B, 2), dtype=torch.int64, device=dev)
         h.check(h.lib.emrifd_batch_segment(h.h, pb.walkers.ctypes.data, B, db.t.data_ptr(), db.coeff.data_ptr(), db.m.data_ptr(),
@@ -404,7 +405,8 @@ def main():
         e_, m_ = [int(x) for x in nev.sum(dim=0).cpu().numpy()]
         evals += e_ / NBATCH
         mbe += m_ / NBATCH
-        gevals += int(engine.group_evaluations(db).sum()) / NBATCH
+        solves_per_batch.append(int(engine.group_evaluations(db).sum()))
+        gevals += solves_per_batch[-1] / NBATCH
 
     gfl = C.c_double()
     h.check(h.lib.emrifd_bench_fp64_fma(h.h, 4096, C.byref(gfl)))
@@ -487,6 +489,7 @@ def main():
         "roofline": binding,
         "roofline_other_roof": other,
         "work": {"evals_per_walker": evals / B, "group_evals_per_walker": gevals / B, "mbe_per_walker": mbe / B,
+                 "solves_per_batch": solves_per_batch,
                  "modes_per_walker": float(np.mean([pb.n_modes for pb in pbs])) / B, "knots_per_walker": float(np.mean([pb.n_knots for pb in pbs])) / B},
     }
     line.update(extras)

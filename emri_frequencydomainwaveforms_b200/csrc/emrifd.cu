@@ -4,12 +4,18 @@
 //   spline_build_kernel   A3  batched not-a-knot cubic spline (shared tridiagonal factorisation in smem,
 //                             one RHS per thread, coalesced quad stores)
 //   segment_kernel        A4  per-mode monotone-branch segmentation + bit-exact bin ranges
+//   group_index / group_combine  one stationary point per (m, n) group: combined amplitude quads
+//   piece_build_kernel    per (group branch, spline segment): combined cubic of f_mn, phase constants, amplitude quads and a
+//                             verified degree-5 inverse interpolant x(f) -- the "piece table" the mode sum reads through the TMA
 //   empty_tile_kernel     A5-A7 pass 1: tiles no harmonic touches are zero-filled (a store stream at the HBM write rate),
 //                             the others are queued
-//   mode_sum_kernel       A5-A7 (+A11 fused) pass 2, persistent CTAs fed by the tile queue (mode_sum_direct_kernel: plain grid
-//                             for small launches): bin-owner stationary-phase sum, a thread owns 4 or 6 consecutive (+f,-f)
-//                             bin pairs, no atomics, h+/hx split + scale + rotation fused into the store, optional fused
-//                             |d - h|^2 / <d|h> / <h|h> reduction (like_finalize_kernel adds the partials in a fixed order)
+//   mode_sum_kernel       A5-A7 (+A11 fused) pass 2, one warp-specialised CTA per SM fed by the tile queue (PERSISTENT = false:
+//                             plain grid for small launches): a producer warp scans the walker's cached records and streams
+//                             (header + TMA-copied piece) sub-entries through an mbarrier ring; 19 consumer warps own two
+//                             adjacent (+f,-f) bin pairs per thread with all accumulators in registers: root = interpolant + one
+//                             Newton step, SPA factor, phase in cycles, no atomics, no CTA barrier; h+/hx split + scale +
+//                             rotation fused into the store, optional fused |d - h|^2 / <d|h> / <h|h> reduction
+//                             (like_finalize_kernel adds the per-warp partials in a fixed order)
 //   inner_product / loglike kernels  A10/A11 on materialised arrays
 //   ylm / synth_amplitude / mode_select / compact_* kernels  the producers right before the path
 //
@@ -29,25 +35,31 @@
 #include "k13_tables.h"
 
 #define MAXBR EMRIFD_MAX_BRANCHES
-// mode-sum CTA: SUM_CW consumer warps (bin owners: they evaluate and read out) + one producer warp (record scan, sub-entry fill)
+// mode-sum CTA: SUM_CW consumer warps (bin owners: they evaluate and read out) + one producer warp (record scan, sub-entry fill).
+// One CTA per SM: 20 warps = 5 per SM sub-partition at 96 registers (5 x 32 x 96 = 15 360 of the sub-partition's 16 384
+// registers): the evaluation loop keeps its eight accumulators and both bins' temporaries in registers without spilling.
+// Measured on the bench batch (kernel ms): 19 + 1 warps @ 96 regs 3.55 | 23 + 1 @ 80 (spills) 3.74 | 2 CTAs x (11 + 1) @ 80 3.92 |
+// 27 + 1 @ 72 4.12 | 31 + 1 @ 64 4.30.
 #ifndef SUM_CW
-#define SUM_CW 11
+#define SUM_CW 19
 #endif
 #define SUM_CT (SUM_CW * 32)      /* consumer threads */
 #define SUM_THREADS (SUM_CT + 32) /* + the producer warp */
 #ifndef SUM_BPT
-#define SUM_BPT 4 /* consecutive bins per consumer thread */
+#define SUM_BPT 2 /* consecutive bins per consumer thread: one pair, evaluated together in straight-line code */
 #endif
-#ifndef SUM_MINB
-#define SUM_MINB 2 /* resident CTAs per SM the register allocation is tuned for (2 x 384 threads x 80 registers: 22 consumer warps per SM) */
+#ifndef SUM_MAXNREG
+#define SUM_MAXNREG 96
 #endif
 #ifndef SUM_RING
 #define SUM_RING 4 /* passes (of up to SUM_SUBCAP sub-entries) in flight between the producer warp and the consumer warps */
 #endif
+#ifndef SUM_RCAP
+#define SUM_RCAP 512 /* group records (4 per (m, n) group) the producer warp caches in shared memory per walker */
+#endif
 #define SUM_CHUNK 256 /* group records per chunk of the work-list (chunk_range_kernel's hull granularity) */
-#define SUM_BOUNDS __launch_bounds__(SUM_THREADS, SUM_MINB)
+#define SUM_BOUNDS __maxnreg__(SUM_MAXNREG)
 #define SUM_TILE (SUM_CT * SUM_BPT) /* bins per tile: the tile size every API-visible quantity refers to (emrifd_tile_bins) */
-#define ACC_STRIDE (SUM_CT + 4) /* row stride of the smem accumulators: conflict-free own-slot and transposed access */
 #define SEG_THREADS 128
 #define SMEM_PER_KNOT 3 /* doubles staged per knot by the mode sum: t, f_phi, f_r */
 
@@ -86,6 +98,7 @@ struct emrifd_handle {
     int *d_goff; int64_t goff_cap;
     int *d_gcount; int64_t gcount_cap;
     double *d_gq; int64_t gq_cap;
+    void *d_pieces; int64_t pieces_cap; // piece table of the batch being summed
     int64_t tot_modes, tot_teuk; // packed sizes of the batch validated last (sum K, sum L*K)
     int k13_few;
     // kernel timing
@@ -549,6 +562,8 @@ struct SumParams {
     const double *gq;           // walker block at 16 * teuk_off: [L][G][16] combined amplitude quads
     const int *wstatus;         // [B] per-walker status (0 = ok): failed walkers give zeros / a NaN likelihood, the rest of the batch is unaffected
     int k13_few;                // 1: FastEMRIWaveforms-compatible K_1/3 evaluation (emrifd_set_k13_mode)
+    const struct Piece *pieces; // piece table (piece_build_kernel): row (mode_off * MAXBR + group record), lstride entries per row
+    int lstride;
 };
 
 
@@ -868,31 +883,49 @@ __global__ void __launch_bounds__(GRP_THREADS) group_combine_kernel(GroupParams 
 #define SE_SIDE 1   /* bins are at -f: the direct term lands in the -f accumulators, the mirrored -m term in the +f ones */
 #define SE_MIRROR 2 /* m > 0 and include_minus_m: add the mirrored term */
 #define SE_FALL 4   /* falling branch: G is conjugated (and mu_hi carries the extra quarter turn) */
-struct __align__(16) SubEntry {
-    double c0, c1, c2, c3;  // f_mn(t_j + x) = c0 + c1 x + c2 x^2 + c3 x^3
-    double xlo, xhi;        // slackened root bracket
-    double tol, tj;         // Newton tolerance, knot time
-    double mu_hi, mu_lo;    // (m Phi_phi + n Phi_r)(t_j) / 2pi mod 1 as a double-double; -1/4 on falling branches
-    double p1, p2, p3;      // -(1/2pi) x (m Phi_phi + n Phi_r) cubic remainder, in cycles
-    double pad;
-    int s, e;               // tile-local bin range (inclusive)
-    unsigned int fmask;     // 0 / 0x80000000: sign mask applied to the bin frequency
-    int flags;
-    double4 amp[4];         // quads of Re Cp, Im Cp, Re Cm, Im Cm of (segment, group)
+// One monotone cubic piece of one group's f_mn(t): a (branch, spline segment) pair with every per-segment constant combined
+// once per batch by piece_build_kernel -- the evaluation loop neither searches segments nor recombines (m, n) with the track
+// quads, and gets its root from the piece's inverse interpolant x(f) plus one Newton step.
+#define PIECE_DEG 5
+struct __align__(16) Piece {
+    double c0, c1, c2, c3;       // f_mn(t_j + x) = c0 + c1 x + c2 x^2 + c3 x^3
+    double d2, d3, fmid, finv;   // 2 c2, 3 c3; interpolant variable u = (f - fmid) finv in [-1, 1] over the piece
+    double q0, q1, q2, q3;       // x(u) ~ q0 + u (q1 + u (... + u q5)): degree-5 interpolant through the Chebyshev points of the piece
+    double q4, q5, tol, tj;      // tol: largest Newton step after which the root is good to 1e-7 s (< 0: no usable interpolant,
+                                 // every root goes through the bracketed solver); knot time
+    double xlo, xhi, mu_hi, mu_lo; // slackened root bracket; (m Phi_phi + n Phi_r)(t_j) / 2pi mod 1 as a double-double (-1/4 on falling branches)
+    double p1, p2, p3, pad;      // -(1/2pi) x (m Phi_phi + n Phi_r) cubic remainder, in cycles
+    double4 amp[4];              // quads of Re Cp, Im Cp, Re Cm, Im Cm of (segment, group)
 };
-// overlapping work-list record of the current fill round (written and read by the fill warp only)
+// A piece restricted to the current tile (one entry of a pass): the 16-byte header is written by the producer warp, the body is
+// copied from the piece table by the TMA (cp.async.bulk) straight into the ring slot.
+struct __align__(16) SubEntry {
+    int s, e;           // tile-local bin range (inclusive)
+    unsigned int fmask; // 0 / 0x80000000: sign mask applied to the bin frequency
+    int flags;
+    Piece P;
+};
+// overlapping work-list record of the current fill round (written and read by the producer warp only)
 struct __align__(16) FillEntry {
-    double xa, xb, dm, dn;
-    int ja, jb, dir, g;
+    double dm, dn;
+    int ja, jb, dir, r; // r: group record (group * MAXBR + branch) -> row of the piece table
     int s[2], e[2];     // tile-local bin range per side (+f, -f); empty if s > e
     int jlo[2], jhi[2]; // spline segments those bins fall in
     int mirror, off;    // off: index of its first sub-entry in the round's list
     int nsub, pad;
 };
+// group record as the producer warp caches it per walker
+struct __align__(16) RecC {
+    long long start, end;
+    int ja, jb, dir, mirror;
+    double dm, dn;
+    int lo, hi;         // hull of the positive bins it touches (through +f or -f)
+    int pad0, pad1;
+};
 #ifndef SUM_SUBCAP
-#define SUM_SUBCAP 32 /* sub-entries evaluated per pass */
+#define SUM_SUBCAP 32 /* sub-entries per pass */
 #endif
-#define SUM_ECAP 32   /* work-list records per fill round: one per lane of the fill warp */
+#define SUM_ECAP 32   /* work-list records per fill round: one per lane of the producer warp */
 
 __device__ __noinline__ double2 spa_fix(double fdot, double fddot, double s, double u, int few) {
     // rare path of the SPA factor: X = 1/u < 1024 (late inspiral, turnover neighbourhood); returns R/sqrt|fdot|.
@@ -937,16 +970,18 @@ __device__ __noinline__ double2 spa_fix(double fdot, double fddot, double s, dou
     return make_double2(re, im);
 }
 
-// ---- evaluation of W (1 or 2) bins of one sub-entry in straight-line code: the W independent dependency chains
-//      (SPA factor, phase, sincos, amplitude Horner) interleave in the instruction stream (ILP without more warps) ----
-template <int W, int BPT>
-__device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)[W], const double c1, const double d2,
-                                         const double d3, const SubEntry &S, const int few, double *__restrict__ acc,
-                                         const int id0, const int im0) {
+// ---- evaluation of the W bins of one sub-entry in straight-line code: the W independent dependency chains (SPA factor,
+//      phase, sincos, amplitude Horner) interleave in the instruction stream (ILP without more warps).  The accumulators
+//      are registers: ad_* receive the direct term, ao_* the mirrored -m term; a bin with in[i] == false is computed (as a
+//      copy of its neighbour) but not accumulated ----
+template <int W>
+__device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)[W], const bool (&in)[W], const Piece &S,
+                                         const int fl, const int few, double (&ad_r)[W], double (&ad_i)[W], double (&ao_r)[W],
+                                         double (&ao_i)[W]) {
     double er[W], ei[W];
-    const int fl = S.flags;
     {
         double re[W], im[W], s[W], uu[W], fd[W], fdd[W], sn[W], cs[W];
+        const double c1 = S.c1, d2 = S.d2, d3 = S.d3;
         const double tj = S.tj, mu_hi = S.mu_hi, mu_lo = S.mu_lo, p1 = S.p1, p2 = S.p2, p3 = S.p3;
 #pragma unroll
         for (int i = 0; i < W; i++) {
@@ -988,9 +1023,10 @@ __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)
             const double xi = x[i];
             const double cr = fma(xi, fma(xi, fma(xi, qa.w, qa.z), qa.y), qa.x);
             const double ci = fma(xi, fma(xi, fma(xi, qb.w, qb.z), qb.y), qb.x);
-            const int id = id0 + i * ACC_STRIDE;
-            acc[id] = fma(cr, er[i], fma(-ci, ei[i], acc[id]));
-            acc[id + BPT * ACC_STRIDE] = fma(cr, ei[i], fma(ci, er[i], acc[id + BPT * ACC_STRIDE]));
+            if (in[i]) {
+                ad_r[i] = fma(cr, er[i], fma(-ci, ei[i], ad_r[i]));
+                ad_i[i] = fma(cr, ei[i], fma(ci, er[i], ad_i[i]));
+            }
         }
     }
     if (fl & SE_MIRROR) {
@@ -1000,9 +1036,10 @@ __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)
             const double xi = x[i];
             const double cr = fma(xi, fma(xi, fma(xi, qc.w, qc.z), qc.y), qc.x);
             const double ci = fma(xi, fma(xi, fma(xi, qd.w, qd.z), qd.y), qd.x);
-            const int im_ = im0 + i * ACC_STRIDE;
-            acc[im_] = fma(cr, er[i], fma(ci, ei[i], acc[im_]));
-            acc[im_ + BPT * ACC_STRIDE] = fma(ci, er[i], fma(-cr, ei[i], acc[im_ + BPT * ACC_STRIDE]));
+            if (in[i]) {
+                ao_r[i] = fma(cr, er[i], fma(ci, ei[i], ao_r[i]));
+                ao_i[i] = fma(ci, er[i], fma(-cr, ei[i], ao_i[i]));
+            }
         }
     }
 }
@@ -1126,9 +1163,141 @@ __device__ __forceinline__ double knot_F(const double *sK, int j, double dm, dou
     return radd(rmul(dm, sK[3 * j + 1]), rmul(dn, sK[3 * j + 2]));
 }
 
-// Producer warp, step 1: lane i < gcount turns overlapping record s_list[i] into a FillEntry (tile-local bin ranges and the
-// spline segments they fall in, per side) and the warp numbers the sub-entries of the round (exclusive scan).  Returns their total.
-__device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *marr, const int *narr, int include_minus_m,
+// ==========================================================================================
+// Piece table: one Piece per (group record, spline segment) of every walker, built once per batch.  Row r = group * MAXBR +
+// branch of walker w starts at ((mode_off * MAXBR + r) * lstride); entry j of a row is the piece on segment j (valid for
+// ja <= j <= jb of a non-empty branch).  The inverse interpolant is fitted over the piece's whole x-range (the segment, cut
+// at the branch ends) and VERIFIED here; where it is not good enough (turnover neighbourhoods: 0.3 % of the evaluations of
+// the bench workload) tol < 0 sends the evaluation through the bracketed solver.
+// ==========================================================================================
+struct PieceParams {
+    const emrifd_walker_t *w;
+    const double *t, *coeff;
+    const int *m, *n;
+    const emrifd_branch_t *br;
+    const int *leader, *gcount;
+    const double *gq;
+    Piece *pieces;
+    int lstride;
+};
+#define PIECE_THREADS 128
+__global__ void __launch_bounds__(PIECE_THREADS) piece_build_kernel(PieceParams p) {
+    const emrifd_walker_t wd = p.w[blockIdx.y];
+    const int G = p.gcount[blockIdx.y], L = wd.L, K = wd.K, R = 2 * K + 4;
+    const int nseg = L - 1;
+    const long long tot = (long long)G * MAXBR * nseg;
+    const double *coeff = p.coeff + wd.coeff_off;
+    const double *gq = p.gq + 16 * wd.teuk_off;
+    const double *tk = p.t + wd.knot_off;
+    for (long long idx = (long long)blockIdx.x * PIECE_THREADS + threadIdx.x; idx < tot; idx += (long long)gridDim.x * PIECE_THREADS) {
+        const int r = (int)(idx / nseg), j = (int)(idx - (long long)r * nseg);
+        const int gi = r / MAXBR, lead = p.leader[wd.mode_off + gi];
+        const emrifd_branch_t *b = p.br + (wd.mode_off + lead) * MAXBR + (r % MAXBR);
+        if (b->end < b->start) continue;
+        const int ja = b->ja, jb = b->jb, dir = b->dir;
+        if (j < ja || j > jb) continue;
+        const double dm = (double)p.m[wd.mode_off + lead], dn = (double)p.n[wd.mode_off + lead];
+        const double4 qf = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K) * 4);     // f_phi quad
+        const double4 qr = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 1) * 4); // f_r
+        const double4 qP = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 2) * 4); // Phi_phi
+        const double4 qR = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 3) * 4); // Phi_r
+        const double4 *ga = reinterpret_cast<const double4 *>(gq + ((long long)j * G + gi) * 16);
+        Piece S;
+        S.amp[0] = ga[0]; S.amp[1] = ga[1]; S.amp[2] = ga[2]; S.amp[3] = ga[3];
+        const double tj = tk[j], hj = tk[j + 1] - tj;
+        S.c0 = radd(rmul(dm, qf.x), rmul(dn, qr.x));
+        S.c1 = fma(dm, qf.y, dn * qr.y);
+        S.c2 = fma(dm, qf.z, dn * qr.z);
+        S.c3 = fma(dm, qf.w, dn * qr.w);
+        S.d2 = 2.0 * S.c2; S.d3 = 3.0 * S.c3;
+        const double xl0 = (j == ja) ? b->xa : 0.0, xh0 = (j == jb) ? b->xb : hj;
+        S.xlo = xl0 - 1e-5 * hj; S.xhi = xh0 + 1e-5 * hj;
+        S.tj = tj;
+        { // ---- inverse interpolant x(f) over [xl0, xh0]: the consumers' root = interpolant + ONE Newton step ----
+            const double sdir = dir > 0 ? 1.0 : -1.0;
+            const double c0 = S.c0, c1 = S.c1, c2 = S.c2, c3 = S.c3;
+            const double xm = 0.5 * (xl0 + xh0), xr = 0.5 * (xh0 - xl0);
+            const double fa = c0 + xl0 * fma(xl0, fma(xl0, c3, c2), c1), fb = c0 + xh0 * fma(xh0, fma(xh0, c3, c2), c1);
+            S.fmid = 0.5 * (fa + fb);
+            const double fh = 0.5 * (fb - fa);
+            S.finv = fh != 0.0 ? 1.0 / fh : 0.0;
+            if (!(fabs(S.finv) < 1e300)) S.finv = 0.0;
+            // curvature bound K = max |fddot / (2 fdot)| over the piece: one Newton step of size d leaves an error ~ K d^2
+            double Kc = 0.0;
+            bool bad = !(xr > 0.0) || S.finv == 0.0;
+#pragma unroll
+            for (int q = 0; q < 3; q++) {
+                const double xq = q == 0 ? xl0 : (q == 1 ? xh0 : xm);
+                const double fd = fma(xq, fma(S.d3, xq, S.d2), c1), fdd = fma(2.0 * S.d3, xq, S.d2);
+                if (!(fd * sdir > 0.0)) bad = true;
+                Kc = fmax(Kc, fabs(fdd / (2.0 * fd)));
+            }
+            double tol = Kc > 0.0 ? sqrt(1e-7 / Kc) : hj;
+            if (!(tol <= hj)) tol = hj;
+            double q[PIECE_DEG + 1];
+#pragma unroll
+            for (int d = 0; d <= PIECE_DEG; d++) q[d] = 0.0;
+            q[0] = xm;
+            if (!bad) {
+                double uk[PIECE_DEG + 1], a[PIECE_DEG + 1];
+#pragma unroll
+                for (int k = 0; k <= PIECE_DEG; k++) {
+                    const double xk = fma(xr, cospi((2 * k + 1) / (2.0 * (PIECE_DEG + 1))), xm);
+                    a[k] = xk;
+                    uk[k] = (c0 + xk * fma(xk, fma(xk, c3, c2), c1) - S.fmid) * S.finv;
+                }
+#pragma unroll
+                for (int jj = 1; jj <= PIECE_DEG; jj++) // Newton divided differences in u
+#pragma unroll
+                    for (int k = PIECE_DEG; k >= jj; k--) a[k] = (a[k] - a[k - 1]) / (uk[k] - uk[k - jj]);
+                q[0] = a[PIECE_DEG]; // monomial coefficients, built by Horner on the Newton form
+#pragma unroll
+                for (int k = PIECE_DEG - 1; k >= 0; k--) {
+#pragma unroll
+                    for (int d = PIECE_DEG; d >= 1; d--) q[d] = q[d - 1] - uk[k] * q[d];
+                    q[0] = a[k] - uk[k] * q[0];
+                }
+                // verify between the nodes (Chebyshev extrema and the midpoints between them, ends included)
+                double err = 0.0;
+#pragma unroll
+                for (int k = 0; k <= 2 * (PIECE_DEG + 1); k++) {
+                    const double xt = fma(xr, cospi(k / (2.0 * (PIECE_DEG + 1))), xm);
+                    const double ut = (c0 + xt * fma(xt, fma(xt, c3, c2), c1) - S.fmid) * S.finv;
+                    double xq = q[PIECE_DEG];
+#pragma unroll
+                    for (int d = PIECE_DEG - 1; d >= 0; d--) xq = fma(xq, ut, q[d]);
+                    err = fmax(err, fabs(xq - xt));
+                }
+                if (!(err <= 0.25 * tol)) bad = true;
+            }
+            S.q0 = q[0]; S.q1 = q[1]; S.q2 = q[2]; S.q3 = q[3]; S.q4 = q[4]; S.q5 = q[5];
+            S.tol = bad ? -1.0 : tol;
+        }
+        double u[4]; // Phi/(2 pi) mod 1 as double-doubles (hi, lo) for Phi_phi, Phi_r
+#pragma unroll
+        for (int q = 0; q < 2; q++) {
+            const double ph = q == 0 ? qP.x : qR.x;
+            double a = ph * EMRIFD_INV2PI_HI;
+            double er = fma(ph, EMRIFD_INV2PI_HI, -a);
+            a -= rint(a);
+            er = fma(ph, EMRIFD_INV2PI_LO, er);
+            const double hi2 = a + er;
+            u[2 * q] = hi2; u[2 * q + 1] = er - (hi2 - a);
+        }
+        S.mu_hi = fma(dm, u[0], dn * u[2]) - (dir < 0 ? 0.25 : 0.0);
+        S.mu_lo = fma(dm, u[1], dn * u[3]);
+        S.p1 = -EMRIFD_INV2PI_HI * fma(dm, qP.y, dn * qR.y);
+        S.p2 = -EMRIFD_INV2PI_HI * fma(dm, qP.z, dn * qR.z);
+        S.p3 = -EMRIFD_INV2PI_HI * fma(dm, qP.w, dn * qR.w);
+        S.pad = 0.0;
+        p.pieces[(wd.mode_off * MAXBR + r) * (long long)p.lstride + j] = S;
+    }
+}
+
+// Producer warp, step 1: lane i < gcount turns overlapping group record s_list[i] into a FillEntry (tile-local bin ranges and the
+// spline segments they fall in, per side) and the warp numbers the sub-entries of the round (exclusive scan).  Returns their
+// total.  rc: the walker's cached records (shared memory) or NULL (read the branch records from global memory).
+__device__ __noinline__ int fill_entries(const RecC *rc, const emrifd_branch_t *br, const int *marr, const int *narr, int include_minus_m,
                                          long long zero, const int *s_list, const int *s_rec, int gcount, long long jt0,
                                          long long jt1, Grid g, const double *sK, FillEntry *ent) {
     // (br, marr, narr: this walker's blocks.  Scalars by value: a reference to the kernel parameters would force a
@@ -1136,19 +1305,26 @@ __device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *m
     const int lane = threadIdx.x & 31;
     int nsub = 0;
     if (lane < gcount) {
-        const int gi = s_list[lane] / MAXBR, rec = s_rec[lane], k = rec / MAXBR;
-        const emrifd_branch_t b = br[rec];
-        const int mi = marr[k], ni = narr[k];
+        const int r = s_list[lane];
         FillEntry e;
-        e.xa = b.xa; e.xb = b.xb; e.dm = (double)mi; e.dn = (double)ni;
-        e.ja = b.ja; e.jb = b.jb; e.dir = b.dir; e.g = gi;
-        e.mirror = (mi > 0) && include_minus_m; e.pad = 0;
+        long long bstart, bend;
+        if (rc) {
+            const RecC c = rc[r];
+            bstart = c.start; bend = c.end; e.ja = c.ja; e.jb = c.jb; e.dir = c.dir; e.mirror = c.mirror; e.dm = c.dm; e.dn = c.dn;
+        } else {
+            const int rec = s_rec[lane], k = rec / MAXBR;
+            const emrifd_branch_t b = br[rec];
+            const int mi = marr[k];
+            bstart = b.start; bend = b.end; e.ja = b.ja; e.jb = b.jb; e.dir = b.dir;
+            e.mirror = (mi > 0) && include_minus_m; e.dm = (double)mi; e.dn = (double)narr[k];
+        }
+        e.r = r; e.pad = 0;
         // tile-local covered ranges: +f bins have full-grid index zero + jt0 + lb, -f bins zero - jt0 - lb
         const long long ntile = jt1 - jt0 + 1;
-        long long lo = b.start - (zero + jt0), hi = b.end - (zero + jt0);
+        long long lo = bstart - (zero + jt0), hi = bend - (zero + jt0);
         e.s[0] = (int)(lo < 0 ? 0 : (lo > ntile ? ntile : lo));
         e.e[0] = (int)(hi > ntile - 1 ? ntile - 1 : (hi < -1 ? -1 : hi));
-        lo = (zero - jt0) - b.end; hi = (zero - jt0) - b.start;
+        lo = (zero - jt0) - bend; hi = (zero - jt0) - bstart;
         e.s[1] = (int)(lo < 0 ? 0 : (lo > ntile ? ntile : lo));
         if (jt0 == 0 && e.s[1] == 0) e.s[1] = 1; // f = 0 is handled on the + side
         e.e[1] = (int)(hi > ntile - 1 ? ntile - 1 : (hi < -1 ? -1 : hi));
@@ -1160,11 +1336,11 @@ __device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *m
             { // segment of the side's first bin: largest j whose knot frequency is not beyond f (binary search) ...
                 const double fb = tile_binf(g, jt0, e.s[sd]);
                 const double f = sd == 0 ? fb : -fb;
-                int l2 = b.ja, h2 = b.jb;
+                int l2 = e.ja, h2 = e.jb;
                 while (l2 < h2) {
                     const int mid = (l2 + h2 + 1) >> 1;
                     const double Fk = knot_F(sK, mid, e.dm, e.dn);
-                    if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) l2 = mid; else h2 = mid - 1;
+                    if (e.dir > 0 ? (Fk <= f) : (Fk >= f)) l2 = mid; else h2 = mid - 1;
                 }
                 jj2[0] = l2;
             }
@@ -1172,8 +1348,8 @@ __device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *m
                 const double fb = tile_binf(g, jt0, e.e[sd]);
                 const double f = sd == 0 ? fb : -fb;
                 int l2 = jj2[0];
-                while (l2 < b.jb) { const double Fk = knot_F(sK, l2 + 1, e.dm, e.dn); if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) l2++; else break; }
-                while (l2 > b.ja) { const double Fk = knot_F(sK, l2, e.dm, e.dn); if (b.dir > 0 ? (Fk <= f) : (Fk >= f)) break; l2--; }
+                while (l2 < e.jb) { const double Fk = knot_F(sK, l2 + 1, e.dm, e.dn); if (e.dir > 0 ? (Fk <= f) : (Fk >= f)) l2++; else break; }
+                while (l2 > e.ja) { const double Fk = knot_F(sK, l2, e.dm, e.dn); if (e.dir > 0 ? (Fk <= f) : (Fk >= f)) break; l2--; }
                 jj2[1] = l2;
             }
             e.jlo[sd] = jj2[0] < jj2[1] ? jj2[0] : jj2[1];
@@ -1192,31 +1368,48 @@ __device__ __noinline__ int fill_entries(const emrifd_branch_t *br, const int *m
     return __shfl_sync(0xffffffffu, incl, 31);
 }
 
-// Producer warp, step 2: lane t < nsw builds sub-entry w0 + t of the round (its record found from the entries' offsets) in `sub`.
-__device__ __noinline__ void fill_subs(const double *coeff, const double *gq, int K, int G, int gcount, int w0, int nsw, Grid g,
-                                       long long jt0, const double *sK, const FillEntry *ent, SubEntry *sub) {
-    // (coeff, gq: this walker's blocks)
+// ---- mbarrier / TMA helpers (CTA-local producer/consumer hand-off of the sub-entry ring) ----
+__device__ __forceinline__ unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
+__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(unsigned long long *bar, unsigned bytes) {
+    asm volatile("mbarrier.expect_tx.relaxed.cta.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    do {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    } while (!ok);
+}
+// global -> shared bulk copy by the TMA; completion is counted in bytes on `bar`
+__device__ __forceinline__ void tma_copy(void *dst_smem, const void *src_global, unsigned bytes, unsigned long long *bar) {
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
+                 ::"r"(smem_u32(dst_smem)), "l"(src_global), "r"(bytes), "r"(smem_u32(bar)) : "memory");
+}
+
+// Producer warp, step 2: lane t < nsw builds sub-entry w0 + t of the round in `sub`: finds its (record, side, segment) from the
+// entries' offsets, the tile-local bins that fall on that segment (the 16-byte header), and has the TMA copy the piece itself.
+__device__ __noinline__ void fill_subs(const Piece *pieces, int lstride, int gcount, int w0, int nsw, Grid g, long long jt0,
+                                       const double *sK, const FillEntry *ent, SubEntry *sub, unsigned long long *full) {
+    // (pieces: this walker's block of the piece table)
     const int t = threadIdx.x & 31;
     if (t >= nsw) return;
     const int idx = w0 + t;
     int ei = 0;
     while (ei < gcount - 1 && idx >= ent[ei].off + ent[ei].nsub) ei++;
     const FillEntry e = ent[ei];
-    const int R = 2 * K + 4;
     const int loc = idx - e.off;
     const int n0 = e.jhi[0] >= e.jlo[0] ? e.jhi[0] - e.jlo[0] + 1 : 0;
     const int sd = loc >= n0 ? 1 : 0;
     const int j = e.jlo[sd] + (sd ? loc - n0 : loc);
+    tma_copy(&sub[t].P, pieces + ((long long)e.r * lstride + j), (unsigned)sizeof(Piece), full);
     const bool fwd = (e.dir > 0) == (sd == 0); // bin index and segment index grow together
     const double sg = sd == 0 ? 1.0 : -1.0;
-    SubEntry S;
-    // ---- per-segment constants (global loads first: they overlap the boundary searches) ----
-    const double4 qf = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K) * 4);     // f_phi quad
-    const double4 qr = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 1) * 4); // f_r
-    const double4 qP = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 2) * 4); // Phi_phi
-    const double4 qR = *reinterpret_cast<const double4 *>(coeff + ((long long)j * R + 2 * K + 3) * 4); // Phi_r
-    const double4 *ga = reinterpret_cast<const double4 *>(gq + ((long long)j * G + e.g) * 16);
-    S.amp[0] = ga[0]; S.amp[1] = ga[1]; S.amp[2] = ga[2]; S.amp[3] = ga[3];
     // ---- bins of this side that fall on segment j: P(lb, jj) = "bin lb lies on a segment >= jj" is monotone in lb ----
     int bnd[2]; // first bin with P(., j) [fwd] / first bin without P(., j + 1) [!fwd]; then the bin after the last one
 #pragma unroll
@@ -1234,60 +1427,24 @@ __device__ __noinline__ void fill_subs(const double *coeff, const double *gq, in
         }
         bnd[w] = lo;
     }
-    S.s = bnd[0]; S.e = bnd[1] - 1;
-    const double dm = e.dm, dn = e.dn;
-    const double tj = sK[3 * j], hj = sK[3 * (j + 1)] - tj;
-    S.c0 = radd(rmul(dm, qf.x), rmul(dn, qr.x));
-    S.c1 = fma(dm, qf.y, dn * qr.y);
-    S.c2 = fma(dm, qf.z, dn * qr.z);
-    S.c3 = fma(dm, qf.w, dn * qr.w);
-    const double xl0 = (j == e.ja) ? e.xa : 0.0, xh0 = (j == e.jb) ? e.xb : hj;
-    S.xlo = xl0 - 1e-5 * hj; S.xhi = xh0 + 1e-5 * hj;
-    S.tol = 1e-6 * hj; // post-step error ~ tol^2 |c2/c1| + 1e-6 tol: far below 1e-4 s
-    S.tj = tj;
-    double u[4]; // Phi/(2 pi) mod 1 as double-doubles (hi, lo) for Phi_phi, Phi_r
-#pragma unroll
-    for (int q = 0; q < 2; q++) {
-        const double ph = q == 0 ? qP.x : qR.x;
-        double a = ph * EMRIFD_INV2PI_HI;
-        double er = fma(ph, EMRIFD_INV2PI_HI, -a);
-        a -= rint(a);
-        er = fma(ph, EMRIFD_INV2PI_LO, er);
-        const double hi2 = a + er;
-        u[2 * q] = hi2; u[2 * q + 1] = er - (hi2 - a);
-    }
-    S.mu_hi = fma(dm, u[0], dn * u[2]) - (e.dir < 0 ? 0.25 : 0.0);
-    S.mu_lo = fma(dm, u[1], dn * u[3]);
-    S.p1 = -EMRIFD_INV2PI_HI * fma(dm, qP.y, dn * qR.y);
-    S.p2 = -EMRIFD_INV2PI_HI * fma(dm, qP.z, dn * qR.z);
-    S.p3 = -EMRIFD_INV2PI_HI * fma(dm, qP.w, dn * qR.w);
-    S.pad = 0.0;
-    S.fmask = sd == 0 ? 0u : 0x80000000u;
-    S.flags = (sd ? SE_SIDE : 0) | (e.mirror ? SE_MIRROR : 0) | (e.dir < 0 ? SE_FALL : 0);
-    sub[t] = S;
+    int4 hdr;
+    hdr.x = bnd[0]; hdr.y = bnd[1] - 1;
+    hdr.z = sd == 0 ? 0 : (int)0x80000000u;
+    hdr.w = (sd ? SE_SIDE : 0) | (e.mirror ? SE_MIRROR : 0) | (e.dir < 0 ? SE_FALL : 0);
+    *reinterpret_cast<int4 *>(&sub[t]) = hdr;
 }
 
-// ---- mbarrier helpers (CTA-local producer/consumer hand-off of the sub-entry ring) ----
-__device__ __forceinline__ unsigned smem_u32(const void *ptr) { return (unsigned)__cvta_generic_to_shared(ptr); }
-__device__ __forceinline__ void mbar_init(unsigned long long *bar, int count) {
-    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(unsigned long long *bar) {
-    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned parity) {
-    unsigned ok;
-    do {
-        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
-                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
-    } while (!ok);
-}
-
+#ifdef SUM_STATS
+__device__ unsigned long long g_stats[16]; // debug build only: 0 tiles, 1 passes, 2 sub-entries, 3 (warp, sub-entry) visits, 4 pair evaluations, 5 bins accumulated, 6 robust pair solves, 7 empty passes
+#define STAT_ADD(i, v) atomicAdd(&g_stats[i], (unsigned long long)(v))
+#else
+#define STAT_ADD(i, v) do { } while (0)
+#endif
 #define PASS_FIRST 1 /* first pass of its tile: the consumers clear their accumulators and compute their bin frequencies */
 #define PASS_LAST 2  /* last pass of its tile: the consumers read out after evaluating it */
 #define PASS_QUIT 4  /* no more tiles */
 struct SumShared { // static shared memory of the mode-sum CTA
-    unsigned long long full[SUM_RING], empty[SUM_RING]; // mbarriers: pass published / pass released by all consumer warps
+    unsigned long long full[SUM_RING], empty[SUM_RING]; // mbarriers: pass published and its pieces landed / pass released by all consumer warps
     int4 hdr[SUM_RING];                                 // (tile, walker, sub-entries in the pass, PASS_* flags)
     int list[64], rec[64];                              // producer: overlapping group records waiting for a fill round
 };
@@ -1295,13 +1452,14 @@ struct SumShared { // static shared memory of the mode-sum CTA
 // ------------------------------------------------------------------------------------------------------------------
 // Producer warp.  For every tile it owns (persistent launch: pulled from the queue empty_tile_kernel filled; direct launch: the
 // CTA's own tile) it scans the walker's group records in order, turns the overlapping ones into sub-entries (fill_entries /
-// fill_subs, 32 per pass) and publishes the passes through the ring.  It runs ahead of the consumers by up to SUM_RING passes --
-// across tile boundaries -- so the dependent global loads of the fill (record -> branch -> coefficient quads) never stall them.
-// A pass is published one step late (when the next one has been built, or the tile ends), so that the last pass of a tile
-// can carry PASS_LAST.
+// fill_subs, 32 per pass: a header each, the piece bodies by TMA) and publishes the passes through the ring.  A walker's
+// knots and group records are cached in shared memory when the walker changes (the queue hands out a walker's tiles
+// consecutively), so a tile costs no dependent global load.  The producer runs ahead of the consumers by up to SUM_RING passes
+// -- across tile boundaries.  A pass is published one step late (when the next one has been built, or the tile ends), so that
+// the last pass of a tile can carry PASS_LAST.
 // ------------------------------------------------------------------------------------------------------------------
 template <bool LIKE, int BPT, bool PERSISTENT>
-__device__ __forceinline__ void sum_producer(const SumParams &p, SumShared &sh, SubEntry *ring, FillEntry *ent, double *sK) {
+__device__ __forceinline__ void sum_producer(const SumParams &p, SumShared &sh, SubEntry *ring, FillEntry *ent, RecC *sR, double *sK) {
     constexpr int TILE = SUM_CT * BPT;
     const int lane = threadIdx.x & 31;
     const long long zero = p.g.zero;
@@ -1318,53 +1476,98 @@ __device__ __forceinline__ void sum_producer(const SumParams &p, SumShared &sh, 
     } else {
         q = ((unsigned long long)blockIdx.y << 32) | blockIdx.x;
     }
+    // per-walker state, reloaded only when the walker changes
+    emrifd_walker_t wd;
+    memset(&wd, 0, sizeof(wd));
+    int G = 0, nrec = 0, wbad = 0;
+    bool cached = false; // the walker's group records are in shared memory
     while (q != none) {
         if (PERSISTENT) { // the next item: in flight during this tile
             if (lane == 0) { const unsigned int i1 = atomicAdd(&p.qctl[1], 1u); qn = i1 < nq ? p.queue[i1] : none; }
         }
         const int tile_x = (int)(q & 0xffffffffu), walker_y = (int)(q >> 32);
-        const emrifd_walker_t wd = p.w[walker_y];
-        const int G = p.gcount[walker_y];
-        const int nrec = G * MAXBR;
         const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * TILE;
         const long long jt1 = (jt0 + TILE < jend ? jt0 + TILE : jend) - 1; // inclusive
         const long long pos_lo = zero + jt0, pos_hi = zero + jt1, neg_lo = zero - jt1, neg_hi = zero - jt0;
-        const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
-        bool any = false;
-        for (int ch = 0; ch * SUM_CHUNK < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
-        if (p.wstatus[walker_y]) any = false; // failed walker: zeros (and a NaN likelihood from like_finalize_kernel)
+        if (!PERSISTENT) { // one tile per CTA: look at the chunk hulls before staging anything
+            const int nrec_ = p.gcount[walker_y] * MAXBR;
+            const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
+            bool any_ = false;
+            for (int ch = 0; ch * SUM_CHUNK < nrec_; ch++) any_ |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
+            if (p.wstatus[walker_y]) any_ = false;
+            if (!any_ && !(LIKE && (p.no_empty || tile_truncated(p, jt0, TILE)))) break; // empty_tile_kernel has dealt with this tile
+        }
+        if (staged_walker != walker_y) {
+            staged_walker = walker_y;
+            wd = p.w[walker_y];
+            G = p.gcount[walker_y];
+            nrec = G * MAXBR;
+            wbad = p.wstatus[walker_y]; // failed walker: zeros (and a NaN likelihood from like_finalize_kernel)
+            const emrifd_branch_t *br_ = p.br + wd.mode_off * MAXBR;
+            const int *leader_ = p.leader + wd.mode_off;
+            const double *coeff_ = p.coeff + wd.coeff_off;
+            // knots (time, f_phi, f_r)
+            const double *t = p.t + wd.knot_off;
+            const int R = 2 * wd.K + 4;
+            for (int i = lane; i < wd.L; i += 32) {
+                sK[3 * i] = t[i];
+                sK[3 * i + 1] = coeff_[((long long)i * R + 2 * wd.K) * 4];
+                sK[3 * i + 2] = coeff_[((long long)i * R + 2 * wd.K + 1) * 4];
+            }
+            // group records (a one-tile CTA reads the few it needs straight from global memory instead)
+            cached = PERSISTENT && nrec <= SUM_RCAP;
+            for (int r = lane; cached && r < nrec; r += 32) {
+                const int lead = leader_[r / MAXBR];
+                const emrifd_branch_t b = br_[lead * MAXBR + (r % MAXBR)];
+                const int mi = p.m[wd.mode_off + lead];
+                RecC c;
+                c.start = b.start; c.end = b.end; c.ja = b.ja; c.jb = b.jb; c.dir = b.dir;
+                c.mirror = (mi > 0) && p.include_minus_m; c.dm = (double)mi; c.dn = (double)p.n[wd.mode_off + lead];
+                long long lo = 0x7fffffffLL, hi = -1;
+                if (b.end >= b.start) {
+                    if (b.end >= zero) { lo = (b.start > zero ? b.start : zero) - zero; hi = b.end - zero; }
+                    if (b.start <= zero) {
+                        const long long a_ = zero - (b.end < zero ? b.end : zero), c_ = zero - b.start;
+                        lo = a_ < lo ? a_ : lo; hi = c_ > hi ? c_ : hi;
+                    }
+                }
+                c.lo = (int)lo; c.hi = (int)hi; c.pad0 = c.pad1 = 0;
+                sR[r] = c;
+            }
+            __syncwarp();
+        }
         const bool per_bin = LIKE && (p.no_empty || tile_truncated(p, jt0, TILE));
+        bool any = !wbad;
+        if (any && !cached) { // the chunk hulls tell whether anything touches the tile
+            const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
+            any = false;
+            for (int ch = 0; ch * SUM_CHUNK < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
+        }
         if (any || per_bin) { // (else: direct-grid launch on a tile empty_tile_kernel has dealt with)
             const emrifd_branch_t *br = p.br + wd.mode_off * MAXBR;
             const int *leader = p.leader + wd.mode_off;
-            const double *coeff = p.coeff + wd.coeff_off;
-            const double *gq = p.gq + 16 * wd.teuk_off;
-            if (any && staged_walker != walker_y) { // knots (time, f_phi, f_r) of this walker: stay staged across its tiles
-                staged_walker = walker_y;
-                const double *t = p.t + wd.knot_off;
-                const int R = 2 * wd.K + 4;
-                for (int i = lane; i < wd.L; i += 32) {
-                    sK[3 * i] = t[i];
-                    sK[3 * i + 1] = coeff[((long long)i * R + 2 * wd.K) * 4];
-                    sK[3 * i + 2] = coeff[((long long)i * R + 2 * wd.K + 1) * 4];
-                }
-                __syncwarp();
-            }
+            const Piece *pieces = p.pieces + wd.mode_off * MAXBR * (long long)p.lstride;
+            if (lane == 0) STAT_ADD(0, 1);
             int pflags = PASS_FIRST; // flags of the next pass built for this tile
             int count = 0;           // overlapping records waiting in sh.list
             // a fill round: the first (up to) 32 waiting records, one per lane, become sub-entries; passes of SUM_SUBCAP go out
             auto fill_round = [&]() {
                 const int gcount = count < 32 ? count : 32;
-                const int tot = fill_entries(br, p.m + wd.mode_off, p.n + wd.mode_off, p.include_minus_m, zero, sh.list, sh.rec, gcount,
-                                             jt0, jt1, p.g, sK, ent);
+                const int tot = fill_entries(cached ? sR : nullptr, br, p.m + wd.mode_off, p.n + wd.mode_off, p.include_minus_m, zero,
+                                             sh.list, sh.rec, gcount, jt0, jt1, p.g, sK, ent);
                 for (int w0 = 0; w0 < tot; w0 += SUM_SUBCAP) {
                     const int nsw = tot - w0 < SUM_SUBCAP ? tot - w0 : SUM_SUBCAP;
                     if (pending >= 0) { if (lane == 0) mbar_arrive(&sh.full[pending]); pending = -1; }
                     const int slot = it % SUM_RING;
                     mbar_wait(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
                     it++;
-                    fill_subs(coeff, gq, wd.K, G, gcount, w0, nsw, p.g, jt0, sK, ent, ring + slot * SUM_SUBCAP);
-                    if (lane == 0) sh.hdr[slot] = make_int4(tile_x, walker_y, nsw, pflags);
+                    if (lane == 0) {
+                        mbar_expect_tx(&sh.full[slot], (unsigned)(nsw * sizeof(Piece)));
+                        sh.hdr[slot] = make_int4(tile_x, walker_y, nsw, pflags);
+                        STAT_ADD(1, 1); STAT_ADD(2, nsw);
+                    }
+                    __syncwarp();
+                    fill_subs(pieces, p.lstride, gcount, w0, nsw, p.g, jt0, sK, ent, ring + slot * SUM_SUBCAP, &sh.full[slot]);
                     pflags = 0;
                     __syncwarp();
                     pending = slot;
@@ -1378,34 +1581,45 @@ __device__ __forceinline__ void sum_producer(const SumParams &p, SumShared &sh, 
                 __syncwarp();
                 count = left;
             };
-            for (int base = 0; any && base < nrec; base += 32) {
-                const int ch = base / SUM_CHUNK;
-                if (crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0) { base = (ch + 1) * SUM_CHUNK - 32; continue; } // chunk outside the tile
-                // ---- ordered compaction of the group records that overlap the tile ----
-                const int r = base + lane;
-                bool pred = false;
-                int rec = 0;
-                if (r < nrec) {
-                    rec = leader[r / MAXBR] * MAXBR + (r % MAXBR);
-                    const long long s0 = br[rec].start, e0 = br[rec].end;
-                    pred = (e0 >= s0) && ((s0 <= pos_hi && e0 >= pos_lo) || (s0 <= neg_hi && e0 >= neg_lo));
+            if (cached) { // ordered compaction of the group records that overlap the tile, from the shared-memory table
+                const int t0 = (int)jt0, t1 = (int)jt1;
+                for (int base = 0; any && base < nrec; base += 32) {
+                    const int r = base + lane;
+                    bool pred = false;
+                    if (r < nrec) pred = !(sR[r].lo > t1 || sR[r].hi < t0);
+                    const unsigned bal = __ballot_sync(0xffffffffu, pred);
+                    if (pred) { const int pos = count + __popc(bal & ((1u << lane) - 1)); sh.list[pos] = r; sh.rec[pos] = 0; }
+                    count += __popc(bal);
+                    __syncwarp();
+                    if (count >= 32) fill_round();
                 }
-                const unsigned bal = __ballot_sync(0xffffffffu, pred);
-                if (pred) { const int pos = count + __popc(bal & ((1u << lane) - 1)); sh.list[pos] = r; sh.rec[pos] = rec; }
-                count += __popc(bal);
-                __syncwarp();
-                if (count >= 32) fill_round();
+            } else {
+                const long long *crng = p.chunk_rng + (long long)walker_y * p.cpw * 2;
+                for (int base = 0; any && base < nrec; base += 32) {
+                    const int ch = base / SUM_CHUNK;
+                    if (crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0) { base = (ch + 1) * SUM_CHUNK - 32; continue; } // chunk outside the tile
+                    const int r = base + lane;
+                    bool pred = false;
+                    int rec = 0;
+                    if (r < nrec) {
+                        rec = leader[r / MAXBR] * MAXBR + (r % MAXBR);
+                        const long long s0 = br[rec].start, e0 = br[rec].end;
+                        pred = (e0 >= s0) && ((s0 <= pos_hi && e0 >= pos_lo) || (s0 <= neg_hi && e0 >= neg_lo));
+                    }
+                    const unsigned bal = __ballot_sync(0xffffffffu, pred);
+                    if (pred) { const int pos = count + __popc(bal & ((1u << lane) - 1)); sh.list[pos] = r; sh.rec[pos] = rec; }
+                    count += __popc(bal);
+                    __syncwarp();
+                    if (count >= 32) fill_round();
+                }
             }
             if (count > 0) fill_round();
             // ---- end of the tile: its last pass carries PASS_LAST (a tile without sub-entries gets an empty pass) ----
-            if (pending < 0 || (pflags & PASS_FIRST)) {
-                if (pending >= 0) { if (lane == 0) mbar_arrive(&sh.full[pending]); pending = -1; }
+            if (pending < 0) {
                 const int slot = it % SUM_RING;
                 mbar_wait(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
                 it++;
-                if (lane == 0) sh.hdr[slot] = make_int4(tile_x, walker_y, 0, PASS_FIRST | PASS_LAST);
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sh.full[slot]);
+                if (lane == 0) { sh.hdr[slot] = make_int4(tile_x, walker_y, 0, PASS_FIRST | PASS_LAST); STAT_ADD(7, 1); mbar_arrive(&sh.full[slot]); }
             } else {
                 if (lane == 0) { sh.hdr[pending].w |= PASS_LAST; mbar_arrive(&sh.full[pending]); }
                 pending = -1;
@@ -1421,69 +1635,60 @@ __device__ __forceinline__ void sum_producer(const SumParams &p, SumShared &sh, 
 }
 
 // ---- A6/A7: S = -flip(W); h+ = (S + conj flip S)/2; hx = i (S - conj flip S)/2; scale; rotate ----
-// Warp-local transposed read-out: a warp owns 32*BPT consecutive bins (its lanes' bins); in iteration i lane l
-// finalises bin 32*i + l of them, so the warp stores 512 contiguous bytes per array and reads the data stream the
-// same way.  Only __syncwarp is needed.  The data loads of a group of iterations are issued together, ahead of the
-// stores (which could alias them for all the compiler knows), so their latencies overlap.
-template <bool WRITE_H, bool LIKE, int BPT>
-__device__ __forceinline__ void sum_readout(const SumParams &p, const int tile_x, const int walker_y, const long long jt0,
-                                            const long long jt1, const double *acc) {
+// Straight from the accumulator registers: a thread finalises its own two adjacent bins (32 contiguous bytes per array,
+// a warp covers 1 KB); the data loads of both bins are issued together, ahead of the stores.
+template <bool WRITE_H, bool LIKE>
+__device__ __forceinline__ void sum_readout(const SumParams &p, const int tile_x, const int walker_y, const long long j0,
+                                            const int nb, const double (&wp_r)[2], const double (&wp_i)[2],
+                                            const double (&wm_r)[2], const double (&wm_i)[2]) {
     const int lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
     const emrifd_walker_t *wp = p.w + walker_y;
     const double sc = wp->scale, c2 = wp->cos2psi, s2 = wp->sin2psi;
     const long long out_off = wp->out_off;
     const long long zero = p.g.zero;
     double a0 = 0, a1 = 0, a2 = 0;
-    const int ntile = (int)(jt1 - jt0 + 1);
-    constexpr int RG = BPT % 3 == 0 ? 3 : (BPT % 2 == 0 ? 2 : 1); // read-out group
+    double2 d0[2], d1[2];
+    double w0[2], w1[2];
+    if (LIKE) {
 #pragma unroll
-    for (int i0 = 0; i0 < BPT; i0 += RG) {
-        double2 d0[RG], d1[RG];
-        double w0[RG], w1[RG];
-        if (LIKE) {
-#pragma unroll
-            for (int ii = 0; ii < RG; ii++) {
-                const int lb = wid * (32 * BPT) + (i0 + ii) * 32 + lane;
-                const long long j = jt0 + (lb < ntile ? lb : 0);
-                d0[ii] = p.dw[j]; d1[ii] = p.dw[p.n_data + j];
-                w0[ii] = p.wf[j]; w1[ii] = p.wf[p.n_data + j];
-            }
+        for (int b = 0; b < 2; b++) {
+            const long long j = j0 + (b < nb ? b : 0);
+            const long long jj = nb > 0 ? j : 0;
+            d0[b] = p.dw[jj]; d1[b] = p.dw[p.n_data + jj];
+            w0[b] = p.wf[jj]; w1[b] = p.wf[p.n_data + jj];
         }
+    }
 #pragma unroll
-        for (int ii = 0; ii < RG; ii++) {
-            const int lb = wid * (32 * BPT) + (i0 + ii) * 32 + lane;
-            if (lb >= ntile) continue;
-            const long long j = jt0 + lb;
-            const int own = lb / BPT, bb = lb % BPT;
-            const double *ap = acc + bb * ACC_STRIDE + own;
-            double wpr = ap[0], wpi = ap[BPT * ACC_STRIDE], wmr = ap[2 * BPT * ACC_STRIDE], wmi = ap[3 * BPT * ACC_STRIDE];
-            if (j == 0) { wpr += wmr; wpi += wmi; wmr = wpr; wmi = wpi; }
-            const double pr_ = 0.5 * (-wmr - wpr), pi_ = 0.5 * (-wmi + wpi);
-            const double xr_ = 0.5 * (wmi + wpi), xi_ = 0.5 * (-wmr + wpr);
-            const double hpr = sc * (c2 * pr_ - s2 * xr_), hpi = sc * (c2 * pi_ - s2 * xi_);
-            const double hxr = sc * (s2 * pr_ + c2 * xr_), hxi = sc * (s2 * pi_ + c2 * xi_);
-            if (WRITE_H) {
-                if (p.mask_positive) {
-                    const long long o = out_off + (j - p.j_lo);
-                    p.hp[o] = make_double2(hpr, hpi);
-                    p.hc[o] = make_double2(hxr, hxi);
-                } else {
-                    const long long o = out_off + zero;
-                    p.hp[o + j] = make_double2(hpr, hpi);
-                    p.hc[o + j] = make_double2(hxr, hxi);
-                    if (j > 0) { // Hermitian mirror: h(-f) = conj h(f)
-                        p.hp[o - j] = make_double2(hpr, -hpi);
-                        p.hc[o - j] = make_double2(hxr, -hxi);
-                    }
+    for (int b = 0; b < 2; b++) {
+        if (b >= nb) continue;
+        const long long j = j0 + b;
+        double wpr = wp_r[b], wpi = wp_i[b], wmr = wm_r[b], wmi = wm_i[b];
+        if (j == 0) { wpr += wmr; wpi += wmi; wmr = wpr; wmi = wpi; }
+        const double pr_ = 0.5 * (-wmr - wpr), pi_ = 0.5 * (-wmi + wpi);
+        const double xr_ = 0.5 * (wmi + wpi), xi_ = 0.5 * (-wmr + wpr);
+        const double hpr = sc * (c2 * pr_ - s2 * xr_), hpi = sc * (c2 * pi_ - s2 * xi_);
+        const double hxr = sc * (s2 * pr_ + c2 * xr_), hxi = sc * (s2 * pi_ + c2 * xi_);
+        if (WRITE_H) {
+            if (p.mask_positive) {
+                const long long o = out_off + (j - p.j_lo);
+                p.hp[o] = make_double2(hpr, hpi);
+                p.hc[o] = make_double2(hxr, hxi);
+            } else {
+                const long long o = out_off + zero;
+                p.hp[o + j] = make_double2(hpr, hpi);
+                p.hc[o + j] = make_double2(hxr, hxi);
+                if (j > 0) { // Hermitian mirror: h(-f) = conj h(f)
+                    p.hp[o - j] = make_double2(hpr, -hpi);
+                    p.hc[o - j] = make_double2(hxr, -hxi);
                 }
             }
-            if (LIKE) {
-                const double h0r = hpr * w0[ii], h0i = hpi * w0[ii], h1r = hxr * w1[ii], h1i = hxi * w1[ii];
-                const double r0 = d0[ii].x - h0r, q0 = d0[ii].y - h0i, r1 = d1[ii].x - h1r, q1 = d1[ii].y - h1i;
-                a0 += r0 * r0 + q0 * q0 + r1 * r1 + q1 * q1;
-                a1 += d0[ii].x * h0r + d0[ii].y * h0i + d1[ii].x * h1r + d1[ii].y * h1i;
-                a2 += h0r * h0r + h0i * h0i + h1r * h1r + h1i * h1i;
-            }
+        }
+        if (LIKE) {
+            const double h0r = hpr * w0[b], h0i = hpi * w0[b], h1r = hxr * w1[b], h1i = hxi * w1[b];
+            const double r0 = d0[b].x - h0r, q0 = d0[b].y - h0i, r1 = d1[b].x - h1r, q1 = d1[b].y - h1i;
+            a0 += r0 * r0 + q0 * q0 + r1 * r1 + q1 * q1;
+            a1 += d0[b].x * h0r + d0[b].y * h0i + d1[b].x * h1r + d1[b].y * h1i;
+            a2 += h0r * h0r + h0i * h0i + h1r * h1r + h1i * h1i;
         }
     }
     if (LIKE) { // per-warp partial sums; like_finalize_kernel adds them in a fixed order
@@ -1501,113 +1706,104 @@ __device__ __forceinline__ void sum_readout(const SumParams &p, const int tile_x
 }
 
 // ------------------------------------------------------------------------------------------------------------------
-// Consumer warp: owns 32 * BPT consecutive bins of every tile the CTA handles (a thread owns BPT consecutive (+f, -f) pairs;
-// accumulators and bin frequencies live in the warp's own shared-memory columns).  It waits for the next pass, walks its bins
-// along each of the pass's cubic pieces, releases the slot, and reads out after a tile's last pass.  Consumer warps never wait
-// for one another: a warp with less work in a tile runs ahead, up to SUM_RING passes, into the following tiles.
+// Consumer warp: owns 64 consecutive bins of every tile the CTA handles; a thread owns two adjacent (+f, -f) bin pairs whose
+// four complex accumulators W(+-f) live in registers for the whole tile.  It waits for the next pass, evaluates its two bins
+// on each of the pass's cubic pieces that covers them -- root from the piece's inverse interpolant + one Newton step (no state
+// carried from bin to bin, both bins in straight-line code), SPA factor, phase, amplitude -- releases the slot, and reads out
+// after a tile's last pass.  Consumer warps never wait for one another: a warp with less work in a tile runs ahead, up to
+// SUM_RING passes, into the following tiles.
 // ------------------------------------------------------------------------------------------------------------------
-template <bool WRITE_H, bool LIKE, int BPT>
-__device__ __forceinline__ void sum_consumer(const SumParams &p, SumShared &sh, const SubEntry *ring, double *acc, double *sF) {
-    constexpr int TILE = SUM_CT * BPT;
-    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+template <bool WRITE_H, bool LIKE>
+__device__ __forceinline__ void sum_consumer(const SumParams &p, SumShared &sh, const SubEntry *ring) {
+    constexpr int TILE = SUM_CT * 2;
+    const int tid = threadIdx.x, lane = tid & 31;
     const long long jend = p.j_lo + p.j_cnt; // exclusive
+    double fb[2] = {0.0, 0.0};               // this thread's two bin frequencies
+    double wp_r[2] = {0.0, 0.0}, wp_i[2] = {0.0, 0.0}, wm_r[2] = {0.0, 0.0}, wm_i[2] = {0.0, 0.0}; // W(+f), W(-f)
     for (int it = 0;; it++) {
         const int slot = it % SUM_RING;
         mbar_wait(&sh.full[slot], (it / SUM_RING) & 1);
         const int4 hd = sh.hdr[slot];
         if (hd.w & PASS_QUIT) return;
-        const int tile_x = hd.x, walker_y = hd.y, nsw = hd.z;
-        const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * TILE;
-        const long long jt1 = (jt0 + TILE < jend ? jt0 + TILE : jend) - 1;  // inclusive
-        const long long j0 = jt0 + (long long)tid * BPT;                     // this thread's first bin
-        int nb = (int)(jt1 - j0 + 1);                                        // its number of valid bins
-        nb = nb < 0 ? 0 : (nb > BPT ? BPT : nb);
-        if (hd.w & PASS_FIRST) {
-            if (LIKE) { // the read-out's data lines: start them towards L2 now (a third of them come from DRAM)
-                const int lb0 = wid * (32 * BPT) + lane * BPT; // BPT consecutive bins of the warp's read-out range per lane
-                if (jt0 + lb0 <= jt1) {
-                    const long long j = jt0 + lb0;
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + j));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + p.n_data + j));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + j));
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + p.n_data + j));
+        const int nsw = hd.z;
+        int nb;
+        {
+            const long long jt0 = p.j_lo + (p.tile_first + (long long)hd.x * p.tile_stride) * TILE;
+            const long long jt1 = (jt0 + TILE < jend ? jt0 + TILE : jend) - 1; // inclusive
+            const long long j0 = jt0 + 2 * tid;                                 // this thread's first bin
+            nb = (int)(jt1 - j0 + 1);                                           // its number of valid bins
+            nb = nb < 0 ? 0 : (nb > 2 ? 2 : nb);
+            if (hd.w & PASS_FIRST) {
+                if (LIKE && nb > 0) { // the read-out's data lines: start them towards L2 now (a third of them come from DRAM)
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + j0));
+                    asm volatile("prefetch.global.L2 [%0];" ::"l"(p.dw + p.n_data + j0));
+                    if ((lane & 1) == 0) {
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + j0));
+                        asm volatile("prefetch.global.L2 [%0];" ::"l"(p.wf + p.n_data + j0));
+                    }
                 }
-            }
 #pragma unroll
-            for (int i = 0; i < 4 * BPT; i++) acc[i * ACC_STRIDE + tid] = 0.0;
-#pragma unroll
-            for (int b = 0; b < BPT; b++) {
-                const long long jj = j0 + b;
-                sF[b * SUM_CT + tid] = (b < nb) ? (p.g.fpos ? p.g.fpos[jj] : rmul((double)(int)jj, p.g.val)) : 0.0;
+                for (int b = 0; b < 2; b++) {
+                    wp_r[b] = wp_i[b] = wm_r[b] = wm_i[b] = 0.0;
+                    const long long jj = j0 + b;
+                    fb[b] = (b < nb) ? (p.g.fpos ? p.g.fpos[jj] : rmul((double)(int)jj, p.g.val)) : 0.0;
+                }
             }
         }
         if (nb > 0) {
-            // ---- evaluate: every thread walks its BPT consecutive bins along each listed cubic piece ----
             const SubEntry *sub = ring + slot * SUM_SUBCAP;
-            const int tb0 = tid * BPT;
+            const int tb0 = 2 * tid;
             for (int si = 0; si < nsw; si++) {
-                const SubEntry &S = sub[si];
-                const int s_ = S.s, e_ = S.e;
-                const int bl = s_ - tb0 > 0 ? s_ - tb0 : 0;
-                const int bh = e_ - tb0 < nb - 1 ? e_ - tb0 : nb - 1;
-                if (bl > bh) continue;
-                const unsigned int smask = S.fmask;
-                const int side = S.flags & SE_SIDE;
-                const double sdir = (S.flags & SE_FALL) ? -1.0 : 1.0;
-                const double c1 = S.c1;
-                const double d2 = 2.0 * S.c2, d3 = 3.0 * S.c3;
-                const double *pF = sF + tid + bl * SUM_CT;
-                int id0 = side * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE;       // direct term -> this side
-                int im0 = (1 - side) * 2 * BPT * ACC_STRIDE + tid + bl * ACC_STRIDE; // mirrored -m term -> other side
-                // The thread's first bin goes through the out-of-line cold solve; after that the bins are taken two at a
-                // time: roots by second-order extrapolation from the last solved bin + ONE Newton step (two independent
-                // chains; a bin that misses the tolerance or the bracket falls back to the cold solve), then both bins are
-                // evaluated in straight-line code.  (In the first pair the first bin's extrapolation step is zero.)
-                double fb = flip_sign(pF[0], smask);
-                double xb = solve_slow(c1, S.c2, S.c3, fb - S.c0, S.xlo, S.xhi, S.tol, sdir);
-                double rb = fast_rcp(fma(xb, fma(d3, xb, d2), c1));
-                for (int b = bl; b <= bh; b += 2) {
-                    const bool two = b < bh;
-                    double xx[2], ff[2];
-                    {
-                        const double c0 = S.c0, c2 = S.c2, c3 = S.c3, xlo = S.xlo, xhi = S.xhi, tol = S.tol;
-                        const double f1 = flip_sign(pF[0], smask);
-                        const double f2 = two ? flip_sign(pF[SUM_CT], smask) : f1;
-                        const double kap = fma(2.0 * d3, xb, d2) * rb; // fddot/fdot at the solved bin
-                        const double dl1 = (f1 - fb) * rb, dl2 = (f2 - fb) * rb;
-                        double x1 = fma(dl1, fma(-0.5 * kap, dl1, 1.0), xb), x2 = fma(dl2, fma(-0.5 * kap, dl2, 1.0), xb);
-                        const double g1 = x1 * fma(x1, fma(x1, c3, c2), c1) - (f1 - c0);
-                        const double g2 = x2 * fma(x2, fma(x2, c3, c2), c1) - (f2 - c0);
-                        double r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1)), r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
-                        const double dx1 = g1 * r1, dx2 = g2 * r2;
-                        x1 -= dx1; x2 -= dx2;
-                        if (!(fabs(dx1) <= tol && x1 >= xlo && x1 <= xhi)) {
-                            x1 = solve_slow(c1, c2, c3, f1 - c0, xlo, xhi, tol, sdir);
-                            r1 = fast_rcp(fma(x1, fma(d3, x1, d2), c1));
-                        }
-                        if (two && !(fabs(dx2) <= tol && x2 >= xlo && x2 <= xhi)) {
-                            x2 = solve_slow(c1, c2, c3, f2 - c0, xlo, xhi, tol, sdir);
-                            r2 = fast_rcp(fma(x2, fma(d3, x2, d2), c1));
-                        }
-                        xx[0] = x1; xx[1] = x2; ff[0] = f1; ff[1] = f2;
-                        xb = two ? x2 : x1; fb = f2; rb = two ? r2 : r1;
+                const SubEntry &E = sub[si];
+                const Piece &S = E.P;
+                const int lo = E.s - tb0, hi = E.e - tb0;
+                bool in[2];
+                in[0] = lo <= 0 && hi >= 0;
+                in[1] = lo <= 1 && hi >= 1 && nb > 1;
+#ifdef SUM_STATS
+                if (lane == 0) STAT_ADD(3, 1);
+#endif
+                if (!(in[0] || in[1])) continue;
+                STAT_ADD(4, 1); STAT_ADD(5, (int)in[0] + (int)in[1]);
+                const unsigned int smask = E.fmask;
+                const int fl = E.flags;
+                double f[2], x[2];
+                // a bin outside the piece is evaluated as a copy of its neighbour (and not accumulated)
+                f[0] = flip_sign(in[0] ? fb[0] : fb[1], smask);
+                f[1] = flip_sign(in[1] ? fb[1] : fb[0], smask);
+                bool ok;
+                {
+                    const double c0 = S.c0, c1 = S.c1, c2 = S.c2, c3 = S.c3, d2 = S.d2, d3 = S.d3, tol = S.tol;
+                    const double fmid = S.fmid, finv = S.finv, q0 = S.q0, q1 = S.q1, q2 = S.q2, q3 = S.q3, q4 = S.q4, q5 = S.q5;
+                    double dx[2];
+#pragma unroll
+                    for (int i = 0; i < 2; i++) {
+                        const double u = (f[i] - fmid) * finv;
+                        const double x0 = fma(u, fma(u, fma(u, fma(u, fma(u, q5, q4), q3), q2), q1), q0);
+                        const double g0 = x0 * fma(x0, fma(x0, c3, c2), c1) - (f[i] - c0);
+                        dx[i] = g0 * fast_rcp(fma(x0, fma(d3, x0, d2), c1));
+                        x[i] = x0 - dx[i];
                     }
-                    if (two) {
-                        eval_sub<2, BPT>(xx, ff, c1, d2, d3, S, p.k13_few, acc, id0, im0);
-                    } else {
-                        const double x1[1] = {xx[0]}, f1[1] = {ff[0]};
-                        eval_sub<1, BPT>(x1, f1, c1, d2, d3, S, p.k13_few, acc, id0, im0);
-                    }
-                    pF += 2 * SUM_CT;
-                    id0 += 2 * ACC_STRIDE; im0 += 2 * ACC_STRIDE;
+                    ok = fabs(dx[0]) <= tol && fabs(dx[1]) <= tol; // (tol < 0: the piece has no usable interpolant)
                 }
+                if (!ok) { // turnover neighbourhood, or an interpolant that missed: bracketed solver
+                    STAT_ADD(6, 1);
+                    const double sdir = (fl & SE_FALL) ? -1.0 : 1.0;
+                    const double xlo = S.xlo, xhi = S.xhi, tolr = 1e-6 * (xhi - xlo);
+                    x[0] = solve_slow(S.c1, S.c2, S.c3, f[0] - S.c0, xlo, xhi, tolr, sdir);
+                    x[1] = in[0] && in[1] ? solve_slow(S.c1, S.c2, S.c3, f[1] - S.c0, xlo, xhi, tolr, sdir) : x[0];
+                }
+                if (fl & SE_SIDE) eval_sub<2>(x, f, in, S, fl, p.k13_few, wm_r, wm_i, wp_r, wp_i); // bins at -f: direct -> W(-f)
+                else eval_sub<2>(x, f, in, S, fl, p.k13_few, wp_r, wp_i, wm_r, wm_i);
             }
         }
         __syncwarp();
         if (lane == 0) mbar_arrive(&sh.empty[slot]); // the warp is done with this pass's sub-entries
         if (hd.w & PASS_LAST) {
-            sum_readout<WRITE_H, LIKE, BPT>(p, tile_x, walker_y, jt0, jt1, acc);
-            __syncwarp(); // the warp's accumulator columns are cleared again by the next tile's first pass
+            int tile_x = hd.x;
+            asm volatile("" : "+r"(tile_x)); // recompute the tile geometry here rather than keep it live through the evaluation
+            const long long jt0 = p.j_lo + (p.tile_first + (long long)tile_x * p.tile_stride) * TILE;
+            sum_readout<WRITE_H, LIKE>(p, tile_x, hd.y, jt0 + 2 * tid, nb, wp_r, wp_i, wm_r, wm_i);
         }
     }
 }
@@ -1619,21 +1815,21 @@ __device__ __forceinline__ void sum_consumer(const SumParams &p, SumShared &sh, 
 // than queue order (measured on the 8-GPU bin-sharded configs[3] slices).
 template <bool WRITE_H, bool LIKE, int BPT, bool PERSISTENT>
 __global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
+    static_assert(BPT == 2, "a consumer thread owns one pair of bins");
     extern __shared__ __align__(16) unsigned char smraw[];
     __shared__ SumShared sh;
-    // dynamic smem: accumulators [4][BPT][ACC_STRIDE] | bin frequencies [BPT][SUM_CT] | sub-entry ring | fill entries | knots (t, f_phi, f_r)[L]
-    double *acc = reinterpret_cast<double *>(smraw);
-    double *sF = acc + 4 * BPT * ACC_STRIDE;
-    SubEntry *ring = reinterpret_cast<SubEntry *>(sF + BPT * SUM_CT);
+    // dynamic smem: sub-entry ring | fill entries | group records [SUM_RCAP] | knots (t, f_phi, f_r)[L]
+    SubEntry *ring = reinterpret_cast<SubEntry *>(smraw);
     FillEntry *ent = reinterpret_cast<FillEntry *>(ring + SUM_RING * SUM_SUBCAP);
-    double *sK = reinterpret_cast<double *>(ent + SUM_ECAP);
+    RecC *sR = reinterpret_cast<RecC *>(ent + SUM_ECAP);
+    double *sK = reinterpret_cast<double *>(sR + SUM_RCAP);
     if (threadIdx.x == 0) {
         for (int i = 0; i < SUM_RING; i++) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], SUM_CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads(); // the only CTA-wide barrier: from here on the warps synchronise through the ring's mbarriers alone
-    if (threadIdx.x >= SUM_CT) sum_producer<LIKE, BPT, PERSISTENT>(p, sh, ring, ent, sK);
-    else sum_consumer<WRITE_H, LIKE, BPT>(p, sh, ring, acc, sF);
+    if (threadIdx.x >= SUM_CT) sum_producer<LIKE, BPT, PERSISTENT>(p, sh, ring, ent, sR, sK);
+    else sum_consumer<WRITE_H, LIKE>(p, sh, ring);
 }
 
 // deterministic second stage: one CTA per walker
@@ -1994,9 +2190,9 @@ static size_t spline_smem_bytes(int L, bool tiled) {
     return sizeof(double) * (size_t)L * (5 + (tiled ? 2 * SPL_ROWS : 0));
 }
 
-static size_t sum_smem_bytes(int L, int bpt = SUM_BPT) {
-    return sizeof(double) * 4 * bpt * ACC_STRIDE + sizeof(double) * bpt * SUM_CT + sizeof(SubEntry) * SUM_RING * SUM_SUBCAP +
-           sizeof(FillEntry) * SUM_ECAP + sizeof(double) * SMEM_PER_KNOT * (size_t)L;
+static size_t sum_smem_bytes(int L) {
+    return sizeof(SubEntry) * SUM_RING * SUM_SUBCAP + sizeof(FillEntry) * SUM_ECAP + sizeof(RecC) * SUM_RCAP +
+           sizeof(double) * SMEM_PER_KNOT * (size_t)L;
 }
 
 static int ensure_bytes(emrifd_handle *h, void **ptr, int64_t *cap, int64_t need, bool pinned_host = false) {
@@ -2117,7 +2313,7 @@ int emrifd_destroy(emrifd_handle_t *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_queue); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd);
-    cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq); cudaFree(h->d_gmem); cudaFree(h->d_goff);
+    cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq); cudaFree(h->d_gmem); cudaFree(h->d_goff); cudaFree(h->d_pieces);
     if (h->h_ws) cudaFreeHost(h->h_ws);
     for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
     for (int i = 0; i < 64; i++) { if (h->ev_a[i]) cudaEventDestroy(h->ev_a[i]); if (h->ev_b[i]) cudaEventDestroy(h->ev_b[i]); }
@@ -2281,6 +2477,17 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
         h->launches += 2;
         CUDA_TRY(h, cudaGetLastError());
         p.leader = h->d_leader; p.gcount = h->d_gcount; p.gq = h->d_gq; p.wstatus = h->d_wstatus; p.k13_few = h->k13_few;
+        // piece table: every (group record, segment) with its constants and inverse interpolant, once per batch
+        if ((rc = ensure_bytes(h, &h->d_pieces, &h->pieces_cap, (int64_t)sizeof(Piece) * h->tot_modes * MAXBR * Lmax))) return rc;
+        PieceParams pp;
+        pp.w = h->d_walkers; pp.t = t; pp.coeff = coeff; pp.m = m_arr; pp.n = n_arr; pp.br = branches;
+        pp.leader = h->d_leader; pp.gcount = h->d_gcount; pp.gq = h->d_gq; pp.pieces = (Piece *)h->d_pieces; pp.lstride = Lmax;
+        int64_t npc = ((int64_t)Kmax * MAXBR * Lmax + PIECE_THREADS - 1) / PIECE_THREADS;
+        npc = npc < 1 ? 1 : (npc > 4096 ? 4096 : npc);
+        piece_build_kernel<<<dim3((unsigned)npc, (unsigned)B), PIECE_THREADS, 0, h->stream>>>(pp);
+        h->launches++;
+        CUDA_TRY(h, cudaGetLastError());
+        p.pieces = (const Piece *)h->d_pieces; p.lstride = Lmax;
     }
     const int cpw = (Kmax * MAXBR + SUM_CHUNK - 1) / SUM_CHUNK;
     {
@@ -2635,6 +2842,16 @@ int emrifd_bench_fp64_fma(emrifd_handle_t *h, int iters, double *gflops) {
     *gflops = flops / (best * 1e-3) * 1e-9;
     return 0;
 }
+
+#ifdef SUM_STATS
+int emrifd_debug_stats(uint64_t *out) { // debug build only: read and clear the counters
+    unsigned long long z[16] = {0};
+    cudaDeviceSynchronize();
+    cudaMemcpyFromSymbol(out, g_stats, sizeof(z));
+    cudaMemcpyToSymbol(g_stats, z, sizeof(z));
+    return 0;
+}
+#endif
 
 int emrifd_sum_kernel_time(emrifd_handle_t *h, int enable, double *ms, int64_t *launches) {
     if (!h) return EMRIFD_ERR_INVALID;
