@@ -35,7 +35,8 @@ SYMBOLS = [
     "emrifd_loglike", "emrifd_loglike_batch_host", "emrifd_bench_fp64_fma", "emrifd_launch_count",
     "emrifd_sum_kernel_time", "emrifd_mode_select", "emrifd_ylm_batch", "emrifd_mode_compact_count",
     "emrifd_mode_compact_gather", "emrifd_tile_bins", "emrifd_batch_sum_cyclic",
-    "emrifd_synth_amplitude", "emrifd_walker_status", "emrifd_walker_status_dev", "emrifd_set_k13_mode"]
+    "emrifd_synth_amplitude", "emrifd_walker_status", "emrifd_walker_status_dev", "emrifd_set_k13_mode",
+    "emrifd_window_taps", "emrifd_band_energy", "emrifd_band_convolve"]
 
 _lib = None
 
@@ -82,6 +83,9 @@ def load():
     lib.emrifd_synth_amplitude.argtypes = [vp, vp, vp, i64, vp, vp, vp, vp, i64, i32, i32, vp]
     lib.emrifd_mode_compact_count.argtypes = [vp, vp, i64, i64, vp, vp]
     lib.emrifd_mode_compact_gather.argtypes = [vp, vp, i64, vp, i64, i64, vp, vp, vp, vp, vp, vp, vp, vp, vp]
+    lib.emrifd_window_taps.argtypes = [vp, vp, i64, i32, vp]
+    lib.emrifd_band_energy.argtypes = [vp, vp, i64, i32, vp]
+    lib.emrifd_band_convolve.argtypes = [vp, vp, i32, vp, i64, i64, i64, i64, vp]
     lib.emrifd_bench_fp64_fma.argtypes = [vp, i32, C.POINTER(dbl)]
     lib.emrifd_launch_count.argtypes = [vp]
     lib.emrifd_launch_count.restype = i64

@@ -1004,9 +1004,14 @@ __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)
             const double cyc = ((p0 - mu_hi) + (e0 - mu_lo)) + poly;
             sincos_cycles(cyc, sn[i], cs[i]);
         }
+        bool slow = false; // one branch for all W bins: the rare path is taken by the whole group
 #pragma unroll
-        for (int i = 0; i < W; i++)
-            if (!(uu[i] <= 0.0009765625)) { const double2 g = spa_fix(fd[i], fdd[i], s[i], uu[i], few); re[i] = g.x; im[i] = g.y; }
+        for (int i = 0; i < W; i++) slow |= !(uu[i] <= 0.0009765625);
+        if (slow) {
+#pragma unroll
+            for (int i = 0; i < W; i++)
+                if (!(uu[i] <= 0.0009765625)) { const double2 g = spa_fix(fd[i], fdd[i], s[i], uu[i], few); re[i] = g.x; im[i] = g.y; }
+        }
         const unsigned int cmask = (fl & SE_FALL) ? 0x80000000u : 0u;
 #pragma unroll
         for (int i = 0; i < W; i++) { // E = R~ / sqrt|fdot| e^{i phase}  (R conjugated on falling branches)
@@ -1748,6 +1753,7 @@ __device__ __forceinline__ void sum_consumer(const SumParams &p, SumShared &sh, 
                     const long long jj = j0 + b;
                     fb[b] = (b < nb) ? (p.g.fpos ? p.g.fpos[jj] : rmul((double)(int)jj, p.g.val)) : 0.0;
                 }
+                if (nb == 1) fb[1] = fb[0]; // truncated tile: the missing second bin shadows the first
             }
         }
         if (nb > 0) {
@@ -1768,9 +1774,10 @@ __device__ __forceinline__ void sum_consumer(const SumParams &p, SumShared &sh, 
                 const unsigned int smask = E.fmask;
                 const int fl = E.flags;
                 double f[2], x[2];
-                // a bin outside the piece is evaluated as a copy of its neighbour (and not accumulated)
-                f[0] = flip_sign(in[0] ? fb[0] : fb[1], smask);
-                f[1] = flip_sign(in[1] ? fb[1] : fb[0], smask);
+                // (a bin just outside the piece is evaluated all the same -- one bin beyond the piece's end is still a perfectly
+                //  regular point of its cubic and interpolant -- and not accumulated)
+                f[0] = flip_sign(fb[0], smask);
+                f[1] = flip_sign(fb[1], smask);
                 bool ok;
                 {
                     const double c0 = S.c0, c1 = S.c1, c2 = S.c2, c3 = S.c3, d2 = S.d2, d3 = S.d3, tol = S.tol;
@@ -1791,7 +1798,7 @@ __device__ __forceinline__ void sum_consumer(const SumParams &p, SumShared &sh, 
                     const double sdir = (fl & SE_FALL) ? -1.0 : 1.0;
                     const double xlo = S.xlo, xhi = S.xhi, tolr = 1e-6 * (xhi - xlo);
                     x[0] = solve_slow(S.c1, S.c2, S.c3, f[0] - S.c0, xlo, xhi, tolr, sdir);
-                    x[1] = in[0] && in[1] ? solve_slow(S.c1, S.c2, S.c3, f[1] - S.c0, xlo, xhi, tolr, sdir) : x[0];
+                    x[1] = solve_slow(S.c1, S.c2, S.c3, f[1] - S.c0, xlo, xhi, tolr, sdir);
                 }
                 if (fl & SE_SIDE) eval_sub<2>(x, f, in, S, fl, p.k13_few, wm_r, wm_i, wp_r, wp_i); // bins at -f: direct -> W(-f)
                 else eval_sub<2>(x, f, in, S, fl, p.k13_few, wp_r, wp_i, wm_r, wm_i);
@@ -2170,6 +2177,120 @@ __global__ void __launch_bounds__(256) synth_amplitude_kernel(const double *__re
 }
 
 // FP64 FMA peak micro-benchmark: 8 independent chains per thread
+// ==========================================================================================
+// FD window convolution (FDutils.py:35-47,66-101).  The reference convolves the FD channels with the
+// conjugated DFT of a time-domain window: out[k] = (1/N) sum_i a[i] b[(k - i) mod N], a = conj(fft(window)).  For the windows the
+// scripts use (hann, blackman, hamming, nuttall, ...: check_mode_by_mode.py:43,269) the DFT is concentrated in a few taps
+// around i = 0 (mod N), so the convolution is a banded stencil: window_taps_kernel evaluates the 2H + 1 central taps of the
+// window's DFT directly (and sum w^2, from which Parseval gives the energy left outside the band = the truncation bound), and
+// band_convolve_kernel applies them: one read and one write of the signal, no FFT.
+// ==========================================================================================
+#define WIN_THREADS 256
+// taps W_j = sum_n w[n] e^{-2 pi i j n / N} for j = 0..H (a real window: W_{-j} = conj W_j) as per-block partial sums, plus sum w^2
+// in row H + 1.  grid (chunks, H + 2).  The phase j n / N is reduced exactly in integers before the sincos.
+__global__ void __launch_bounds__(WIN_THREADS) window_taps_kernel(const double *__restrict__ w, long long N, int H,
+                                                                  double *__restrict__ partial) {
+    __shared__ double s[2][WIN_THREADS / 32];
+    const int j = blockIdx.y;
+    double re = 0.0, im = 0.0;
+    for (long long n = (long long)blockIdx.x * WIN_THREADS + threadIdx.x; n < N; n += (long long)gridDim.x * WIN_THREADS) {
+        const double wn = w[n];
+        if (j > H) { re = fma(wn, wn, re); continue; }
+        const long long r = ((long long)j * n) % N;
+        double sn, cs;
+        sincos_cycles((double)r / (double)N, sn, cs);
+        re = fma(wn, cs, re); im = fma(-wn, sn, im);
+    }
+    for (int o = 16; o > 0; o >>= 1) { re += __shfl_down_sync(0xffffffffu, re, o); im += __shfl_down_sync(0xffffffffu, im, o); }
+    if ((threadIdx.x & 31) == 0) { s[0][threadIdx.x >> 5] = re; s[1][threadIdx.x >> 5] = im; }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double t0 = 0, t1 = 0;
+        for (int q = 0; q < WIN_THREADS / 32; q++) { t0 += s[0][q]; t1 += s[1][q]; }
+        double *o = partial + ((long long)j * gridDim.x + blockIdx.x) * 2;
+        o[0] = t0; o[1] = t1;
+    }
+}
+// fixed-order sum of the partials: taps[j] (complex) for j = 0..H, taps[H + 1] = (sum w^2, 0)
+__global__ void window_taps_final_kernel(const double *__restrict__ partial, int nchunk, double *__restrict__ taps) {
+    __shared__ double s[2][256];
+    const double *pp = partial + (long long)blockIdx.x * nchunk * 2;
+    double a = 0, b = 0;
+    for (int i = threadIdx.x; i < nchunk; i += 256) { a += pp[2 * i]; b += pp[2 * i + 1]; }
+    s[0][threadIdx.x] = a; s[1][threadIdx.x] = b;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) { s[0][threadIdx.x] += s[0][threadIdx.x + o]; s[1][threadIdx.x] += s[1][threadIdx.x + o]; }
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) { taps[2 * blockIdx.x] = s[0][0]; taps[2 * blockIdx.x + 1] = s[1][0]; }
+}
+// out[c] = sum over blocks of partial[block][c] (fixed order), c = blockIdx.x < ncol
+__global__ void inner_strided_sum_kernel(const double *__restrict__ partial, int nblk, int ncol, double *__restrict__ out) {
+    __shared__ double s[256];
+    double a = 0;
+    for (int i = threadIdx.x; i < nblk; i += 256) a += partial[(long long)i * ncol + blockIdx.x];
+    s[threadIdx.x] = a;
+    __syncthreads();
+    for (int o = 128; o > 0; o >>= 1) {
+        if ((int)threadIdx.x < o) s[threadIdx.x] += s[threadIdx.x + o];
+        __syncthreads();
+    }
+    if (threadIdx.x == 0) out[blockIdx.x] = s[0];
+}
+// energy of a full-length DFT array split by circular distance from index 0: band[h] = sum over min(i, N - i) == h of |a_i|^2 for
+// h = 0..H, band[H + 1] = everything farther out (one pass; per-block partials [H + 2])
+__global__ void __launch_bounds__(WIN_THREADS) band_energy_kernel(const double2 *__restrict__ a, long long N, int H,
+                                                                  double *__restrict__ partial) {
+    extern __shared__ double sb[]; // [H + 2]
+    for (int i = threadIdx.x; i < H + 2; i += WIN_THREADS) sb[i] = 0.0;
+    __syncthreads();
+    double far = 0.0;
+    for (long long i = (long long)blockIdx.x * WIN_THREADS + threadIdx.x; i < N; i += (long long)gridDim.x * WIN_THREADS) {
+        const double2 v = a[i];
+        const double e = v.x * v.x + v.y * v.y;
+        const long long d = i < N - i ? i : N - i;
+        if (d <= H) atomicAdd(&sb[(int)d], e); else far += e;
+    }
+    for (int o = 16; o > 0; o >>= 1) far += __shfl_down_sync(0xffffffffu, far, o);
+    if ((threadIdx.x & 31) == 0) atomicAdd(&sb[H + 1], far);
+    __syncthreads();
+    for (int i = threadIdx.x; i < H + 2; i += WIN_THREADS) partial[(long long)blockIdx.x * (H + 2) + i] = sb[i];
+}
+// out[c][k - out_lo] = (1/N) sum_{i = -H..H} taps[i + H] b[c][(k - i) mod N] for k in [out_lo, out_lo + out_n): the signal slice
+// (with its circular halo) is staged in shared memory once; grid (tiles of 1024 outputs, channels)
+#define CONV_TILE 1024
+__global__ void __launch_bounds__(WIN_THREADS) band_convolve_kernel(const double2 *__restrict__ taps, int H, const double2 *__restrict__ b,
+                                                                    long long N, long long out_lo, long long out_n,
+                                                                    double2 *__restrict__ out) {
+    extern __shared__ double2 sc[]; // signal [CONV_TILE + 2 H] | taps [2 H + 1]
+    double2 *st = sc + CONV_TILE + 2 * H;
+    const double2 *bc = b + (long long)blockIdx.y * N;
+    const long long k0 = out_lo + (long long)blockIdx.x * CONV_TILE; // first output of the tile
+    for (int i = threadIdx.x; i < CONV_TILE + 2 * H; i += WIN_THREADS) {
+        long long src = (k0 - H + i) % N;  // b index k0 - H + i, wrapped
+        if (src < 0) src += N;
+        sc[i] = bc[src];
+    }
+    for (int i = threadIdx.x; i < 2 * H + 1; i += WIN_THREADS) st[i] = taps[i];
+    __syncthreads();
+    const double inv = 1.0 / (double)N;
+#pragma unroll
+    for (int q = 0; q < CONV_TILE / WIN_THREADS; q++) {
+        const int lk = q * WIN_THREADS + threadIdx.x;
+        const long long k = k0 + lk;
+        if (k >= out_lo + out_n) continue;
+        double re = 0.0, im = 0.0;
+        // b[k - i] sits at sc[lk + H - i]; i runs over -H..H in a fixed order
+        for (int i = -H; i <= H; i++) {
+            const double2 a = st[i + H], v = sc[lk + H - i];
+            re = fma(a.x, v.x, fma(-a.y, v.y, re));
+            im = fma(a.x, v.y, fma(a.y, v.x, im));
+        }
+        out[(long long)blockIdx.y * out_n + (k - out_lo)] = make_double2(re * inv, im * inv);
+    }
+}
+
 __global__ void __launch_bounds__(256) fma_bench_kernel(double *out, int iters, double a, double b) {
     double x0 = threadIdx.x, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
     for (int i = 0; i < iters; i++) {
@@ -2812,6 +2933,55 @@ int emrifd_mode_compact_gather(emrifd_handle_t *h, const emrifd_walker_t *walker
     compact_gather_kernel<<<dim3((unsigned)(Lmax + 1), (unsigned)B), 256, 0, h->stream>>>(
         h->d_walkers, Lmax, (int)M, (int)Mneg, (const double2 *)teuk_full, keep_idx, m_basis, n_basis, neg_pos,
         (const double2 *)ylm_full, (double2 *)teuk_out, m_out, n_out, (double2 *)ylm_out);
+    h->launches++;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int emrifd_window_taps(emrifd_handle_t *h, const double *window, int64_t N, int H, double *taps) {
+    if (!h || !window || !taps || N < 2 || H < 0 || H > EMRIFD_WINDOW_MAX_TAPS || 2 * (int64_t)H + 1 > N)
+        return set_err(h, EMRIFD_ERR_INVALID, "window_taps: bad argument (0 <= H <= EMRIFD_WINDOW_MAX_TAPS, 2 H + 1 <= N)");
+    cudaSetDevice(h->device);
+    int64_t nchunk = (N + WIN_THREADS * 16 - 1) / (WIN_THREADS * 16);
+    const int64_t cap = (int64_t)h->num_sms * 8 / (H + 2) + 1;
+    if (nchunk > cap) nchunk = cap;
+    if (nchunk < 1) nchunk = 1;
+    int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * 2 * nchunk * (H + 2));
+    if (rc) return rc;
+    window_taps_kernel<<<dim3((unsigned)nchunk, (unsigned)(H + 2)), WIN_THREADS, 0, h->stream>>>(window, N, H, h->d_partial);
+    window_taps_final_kernel<<<(unsigned)(H + 2), 256, 0, h->stream>>>(h->d_partial, (int)nchunk, taps);
+    h->launches += 2;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int emrifd_band_energy(emrifd_handle_t *h, const double *a, int64_t N, int H, double *energy) {
+    if (!h || !a || !energy || N < 2 || H < 0 || H > EMRIFD_WINDOW_MAX_TAPS || 2 * (int64_t)H + 1 > N)
+        return set_err(h, EMRIFD_ERR_INVALID, "band_energy: bad argument");
+    cudaSetDevice(h->device);
+    int64_t nb = (N + WIN_THREADS * 16 - 1) / (WIN_THREADS * 16);
+    if (nb > (int64_t)h->num_sms * 4) nb = (int64_t)h->num_sms * 4;
+    if (nb < 1) nb = 1;
+    int rc = ensure_bytes(h, (void **)&h->d_partial, &h->partial_cap, (int64_t)sizeof(double) * (nb * (H + 2) + 2 * (H + 2)));
+    if (rc) return rc;
+    band_energy_kernel<<<(unsigned)nb, WIN_THREADS, sizeof(double) * (H + 2), h->stream>>>((const double2 *)a, N, H, h->d_partial);
+    // fixed-order sum over the blocks: reuse the taps finaliser on a transposed view is not possible (layout [block][H + 2]), so
+    // one small kernel launch per call would be needed; the table is tiny -- sum it with the generic strided finaliser below
+    inner_strided_sum_kernel<<<(unsigned)(H + 2), 256, 0, h->stream>>>(h->d_partial, (int)nb, H + 2, energy);
+    h->launches += 2;
+    CUDA_TRY(h, cudaGetLastError());
+    return 0;
+}
+
+int emrifd_band_convolve(emrifd_handle_t *h, const double *taps, int H, const double *signal, int64_t nch, int64_t N,
+                         int64_t out_lo, int64_t out_n, double *out) {
+    if (!h || !taps || !signal || !out || nch <= 0 || nch > 65535 || N < 2 || H < 0 || H > EMRIFD_WINDOW_MAX_TAPS || 2 * (int64_t)H + 1 > N ||
+        out_lo < 0 || out_n <= 0 || out_lo + out_n > N)
+        return set_err(h, EMRIFD_ERR_INVALID, "band_convolve: bad argument");
+    cudaSetDevice(h->device);
+    const size_t smem = sizeof(double2) * (size_t)(CONV_TILE + 4 * H + 1);
+    dim3 grid((unsigned)((out_n + CONV_TILE - 1) / CONV_TILE), (unsigned)nch);
+    band_convolve_kernel<<<grid, WIN_THREADS, smem, h->stream>>>((const double2 *)taps, H, (const double2 *)signal, N, out_lo, out_n, (double2 *)out);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     return 0;

@@ -217,6 +217,26 @@ int emrifd_synth_amplitude(emrifd_handle_t *h, const double *p, const double *e,
 /* ---- measurement helpers (bench.py roofline denominators) ----------------------------------- */
 /* FP64 FMA throughput micro-benchmark: returns achieved GFLOP/s in *gflops. sync. */
 int emrifd_bench_fp64_fma(emrifd_handle_t *h, int iters, double *gflops);
+/* ---- section 8f rank 2: FD window convolution (FDutils.py:35-47 get_convolution, :66-101 get_fd_windowed) --------------
+ * The reference evaluates convolve(hstack((a[1:], a)), b, 'valid') / len(b) with a = conj(fft(window)), i.e. the circular
+ * convolution out[k] = (1/N) sum_i a[i] b[(k - i) mod N].  The DFT of the windows the scripts use (scipy.signal.windows hann,
+ * blackman, hamming, nuttall, blackmanharris: check_mode_by_mode.py:43,269; emri_pe.py:261) is concentrated in a few taps around
+ * i = 0 (mod N), so the product path applies a banded stencil of 2 H + 1 taps and reports the truncation bound
+ * (energy of the dropped taps, by Parseval); lengths N need not be powers of two (the 1-yr grid is 3 155 815).
+ *
+ * emrifd_window_taps: taps[2 (H + 2)] doubles (device) <- W_j = sum_n window[n] e^{-2 pi i j n / N} for j = 0..H as (re, im)
+ *   pairs (a REAL time-domain window: W_{-j} = conj W_j), then (sum_n window[n]^2, 0) in slot H + 1.  By Parseval the energy of
+ *   the taps outside the band is N sum w^2 - (|W_0|^2 + 2 sum_{j=1..H} |W_j|^2).
+ * emrifd_band_energy: for a window given in the frequency domain (window_in_fd=True): energy[H + 2] doubles (device) <-
+ *   sum of |a_i|^2 over circular distance min(i, N - i) == h for h = 0..H, and everything farther out in slot H + 1.
+ * emrifd_band_convolve: out[nch][out_n] complex <- (1/N) sum_{i = -H..H} taps[i + H] signal[c][(k - i) mod N] for
+ *   k = out_lo .. out_lo + out_n - 1; taps [2 H + 1] complex in the order i = -H..H (device).  Signal and output must not alias. */
+#define EMRIFD_WINDOW_MAX_TAPS 256
+int emrifd_window_taps(emrifd_handle_t *h, const double *window, int64_t N, int H, double *taps);
+int emrifd_band_energy(emrifd_handle_t *h, const double *a, int64_t N, int H, double *energy);
+int emrifd_band_convolve(emrifd_handle_t *h, const double *taps, int H, const double *signal, int64_t nch, int64_t N,
+                         int64_t out_lo, int64_t out_n, double *out);
+
 /* number of kernels this handle has launched since creation (bench.py "gpu_launches") */
 int64_t emrifd_launch_count(emrifd_handle_t *h);
 /* CUDA-event time (ms) accumulated by the dominant kernel (mode-sum) since the last reset, and launches */

@@ -381,8 +381,9 @@ def test_full_size_one_year_grid(generator, oracle_quad, torch_cuda):
 
 
 def test_fd_window_convolution(torch_cuda):
-    """FDutils.get_convolution / get_fd_windowed (the step after the path when window_flag=1): FFT evaluation
-    == the reference's direct 'valid' convolution, and == DFT(window * IDFT(signal)) (FDutils.py:83-85)."""
+    """FDutils.get_convolution / get_fd_windowed (the step after the path when window_flag=1): the exact evaluation (rtol=0)
+    == the reference's direct 'valid' convolution to rounding, the default (banded kernel, certified bound 1e-7) to 1e-7;
+    == DFT(window * IDFT(signal)) (FDutils.py:83-85).  The banded kernel itself: tests/test_gpu_round2.py."""
     from scipy.signal import convolve
     from emri_frequencydomainwaveforms_b200.fdutils import get_convolution, get_fd_windowed, get_fd_waveform_fromFD
     rng = np.random.default_rng(8)
@@ -394,9 +395,11 @@ def test_fd_window_convolution(torch_cuda):
     assert np.max(np.abs(got - ref)) <= 1e-13 * np.max(np.abs(ref))
     window = np.hanning(n)
     sig = [np.fft.fftshift(a), np.fft.fftshift(b)]
-    out = get_fd_windowed(sig, window)
+    out = get_fd_windowed(sig, window, rtol=0)
     ref0 = convolve(np.hstack((np.conj(np.fft.fft(window))[1:], np.conj(np.fft.fft(window)))), sig[0], mode="valid") / n
     assert np.max(np.abs(out[0].cpu().numpy() - ref0)) <= 1e-12 * np.max(np.abs(ref0))
+    out7 = get_fd_windowed(sig, window)
+    assert np.linalg.norm(out7[0].cpu().numpy() - ref0) <= 1.5e-7 * np.linalg.norm(np.fft.fft(window)) * np.linalg.norm(sig[0]) / n
     assert get_fd_windowed(sig, None)[1] is sig[1]
 
     class Gen:                                                             # a generator returning [h+, hx] on the two-sided grid
@@ -406,7 +409,7 @@ def test_fd_window_convolution(torch_cuda):
     freq = np.fft.fftshift(np.fft.fftfreq(n, 10.0))
     ad = get_fd_waveform_fromFD(Gen(), freq >= 0.0, 10.0, window=window)
     ch = ad()
-    assert ch[0].shape[0] == (n + 1) // 2 and np.max(np.abs(ch[0].cpu().numpy() - ref0[freq >= 0.0])) <= 1e-12 * np.max(np.abs(ref0))
+    assert ch[0].shape[0] == (n + 1) // 2 and np.max(np.abs(ch[0].cpu().numpy() - ref0[freq >= 0.0])) <= 1e-6 * np.max(np.abs(ref0))
 
 
 def test_cyclic_tile_sharding_sums_to_full_likelihood(generator, torch_cuda):

@@ -220,3 +220,64 @@ def test_cell26_golden_through_the_cuda_path(torch_cuda):
         ip = np.vdot(W_ref[sup], W_gpu[sup])
         nrm = np.sqrt(np.vdot(W_ref[sup], W_ref[sup]).real * np.vdot(W_gpu[sup], W_gpu[sup]).real)
         assert 1.0 - ip.real / nrm <= 1e-8 and abs(ip.imag) / nrm <= 1e-5, (name, ip / nrm)
+
+
+def test_fd_window_banded_kernel(torch_cuda):
+    """SURVEY 8f rank 2 as a hand-written kernel (FDutils.py:35-47,66-101): the conjugated DFT of a Hann-type window is a narrow
+    band, so get_fd_windowed applies it as a banded stencil (emrifd_window_taps: direct DFT of the central taps + Parseval bound;
+    emrifd_band_convolve).  (1) small N, forced band: against the reference's verbatim convolve(hstack((a[1:], a)), b, 'valid')/len(b)
+    within the certified bound; (2) the 1-yr grid length N = 3 155 815 with the scripts' windows at the default bound: against the
+    exact FFT evaluation, the measured error below the certified one; (3) window_in_fd=True; (4) f >= 0 output range."""
+    torch = torch_cuda
+    from scipy.signal import convolve
+    from scipy.signal.windows import hann, blackman, blackmanharris, hamming, nuttall
+    from emri_frequencydomainwaveforms_b200 import fdutils
+    rng = np.random.default_rng(12)
+    # (1) verbatim reference at a size the O(N^2) direct sum finishes
+    n = 1025
+    window = hann(n)
+    sig = [rng.normal(size=n) + 1j * rng.normal(size=n) for _ in range(2)]
+    band = fdutils.window_band(window, rtol=5e-3)
+    assert band is not None and band[1] <= 16 and band[2] <= 5e-3
+    out = fdutils.get_fd_windowed(sig, window, rtol=5e-3)
+    cw = np.conj(np.fft.fft(window))
+    for c in range(2):
+        ref = convolve(np.hstack((cw[1:], cw)), sig[c], mode="valid") / n                 # FDutils.py:47 verbatim
+        scale = np.sqrt(np.sum(np.abs(cw) ** 2)) * np.sqrt(np.sum(np.abs(sig[c]) ** 2)) / n
+        assert np.max(np.abs(out[c].cpu().numpy() - ref)) <= 1.01 * band[2] * scale
+    # the band is symmetric and its centre tap is sum(window)
+    taps = band[0].cpu().numpy()
+    assert abs(taps[band[1]] - window.sum()) <= 1e-12 * window.sum() and np.allclose(taps, np.conj(taps[::-1]), rtol=0, atol=1e-9)
+    # (2) full 1-yr grid length (odd, not a power of two)
+    N = 3155815
+    s = torch.complex(torch.randn(2, N, dtype=torch.float64, device="cuda"), torch.randn(2, N, dtype=torch.float64, device="cuda"))
+    for ww in (hann, blackman, blackmanharris, hamming, nuttall):
+        w = torch.as_tensor(ww(N)).cuda()
+        band = fdutils.window_band(w)
+        assert band is not None and band[1] <= 16, (ww.__name__, band)
+        got = fdutils.get_fd_windowed([s[0], s[1]], w)
+        cwd = torch.conj(torch.fft.fft(w.to(torch.complex128)))
+        for c in range(2):
+            exact = fdutils._fft_convolution(cwd, s[c])
+            rel = (torch.linalg.vector_norm(got[c] - exact) / torch.linalg.vector_norm(exact)).item()
+            assert rel <= max(band[2], 3e-8) * 1.5 and rel <= 2e-7, (ww.__name__, rel, band[1:])
+    # (3) the same window handed over in the frequency domain
+    w = torch.as_tensor(hann(N)).cuda()
+    fw = torch.fft.fft(w.to(torch.complex128))
+    g_td = fdutils.get_fd_windowed([s[0], s[1]], w)
+    g_fd = fdutils.get_fd_windowed([s[0], s[1]], fw, window_in_fd=True)
+    assert (torch.linalg.vector_norm(g_td[0] - g_fd[0]) / torch.linalg.vector_norm(g_td[0])).item() <= 1e-7
+    # (4) f >= 0 half only == slice of the full result; circular wrap at both ends of the array
+    lo, cnt = (N - 1) // 2, (N + 1) // 2
+    half = fdutils.get_fd_windowed([s[0], s[1]], w, out_lo=lo, out_n=cnt)
+    assert torch.equal(half[1], g_td[1][lo:]) and half[0].shape[0] == cnt
+    exact = fdutils._fft_convolution(torch.conj(fw), s[0])
+    for k in (0, 1, N - 1):
+        assert abs((g_td[0][k] - exact[k]).item()) <= 1e-6 * abs(exact[k].item()) + 1e-9
+    # get_convolution routes a band-limited first argument through the same kernel, anything else through the exact path
+    a_bl = torch.conj(fw)
+    assert (torch.linalg.vector_norm(fdutils.get_convolution(a_bl, s[0]) - exact) / torch.linalg.vector_norm(exact)).item() <= 2e-7
+    a_gen = torch.complex(torch.randn(4097, dtype=torch.float64, device="cuda"), torch.randn(4097, dtype=torch.float64, device="cuda"))
+    b_gen = torch.complex(torch.randn(4097, dtype=torch.float64, device="cuda"), torch.randn(4097, dtype=torch.float64, device="cuda"))
+    ref = fdutils._fft_convolution(a_gen, b_gen)
+    assert torch.allclose(fdutils.get_convolution(a_gen, b_gen), ref, rtol=1e-12, atol=1e-12)

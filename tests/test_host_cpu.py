@@ -284,3 +284,31 @@ def test_reference_likelihood_adopts_the_plugin():
     assert (c["T"], c["dt"], c["eps"]) == (0.5, 15.0, 1e-2)
     df = f_arr[1] - f_arr[0]
     assert np.allclose(np.asarray(like.noise_factor), np.sqrt(df / 4.0))                                # likelihood.py:218-220
+
+
+def test_window_band_host_logic():
+    """fdutils._choose_band (host side of the banded FD-window kernel): the chosen half-width meets the requested bound, the
+    Cauchy-Schwarz error bound holds for the truncated circular convolution (numpy restatement of FDutils.py:35-47 as the DFT
+    identity), and bounds below the certifiable floor are refused (-> exact FFT evaluation)."""
+    from scipy.signal.windows import hann
+    from emri_frequencydomainwaveforms_b200.fdutils import _choose_band
+    n = 4001
+    rng = np.random.default_rng(3)
+    w = hann(n)
+    W = np.fft.fft(w)
+    p2 = np.abs(W) ** 2
+    Hm = 128
+    e_band = p2[0] + 2.0 * np.concatenate([[0.0], np.cumsum(p2[1:Hm + 1])])
+    e_tot = n * np.sum(w * w)                                   # Parseval, as the device path computes it
+    assert abs(e_tot - p2.sum()) <= 1e-12 * e_tot
+    H, bound = _choose_band(e_band, e_tot, 1e-3)
+    assert 1 <= H <= 8 and bound <= 1e-3
+    assert _choose_band(e_band, e_tot, 1e-9) is None and _choose_band(e_band, e_tot, 0.0) is None
+    a = np.conj(W)
+    b = rng.normal(size=n) + 1j * rng.normal(size=n)
+    exact = np.fft.ifft(np.fft.fft(a) * np.fft.fft(b)) / n      # == convolve(hstack((a[1:], a)), b, 'valid') / n
+    at = np.zeros_like(a)
+    idx = np.arange(-H, H + 1) % n
+    at[idx] = a[idx]
+    trunc = np.fft.ifft(np.fft.fft(at) * np.fft.fft(b)) / n
+    assert np.max(np.abs(trunc - exact)) <= bound * np.sqrt(e_tot) * np.linalg.norm(b) / n
