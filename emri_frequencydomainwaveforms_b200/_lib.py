@@ -36,7 +36,7 @@ SYMBOLS = [
     "emrifd_sum_kernel_time", "emrifd_mode_select", "emrifd_ylm_batch", "emrifd_mode_compact_count",
     "emrifd_mode_compact_gather", "emrifd_tile_bins", "emrifd_batch_sum_cyclic",
     "emrifd_synth_amplitude", "emrifd_walker_status", "emrifd_walker_status_dev", "emrifd_set_k13_mode",
-    "emrifd_window_taps", "emrifd_band_energy", "emrifd_band_convolve"]
+    "emrifd_window_taps", "emrifd_band_energy", "emrifd_band_convolve", "emrifd_sum_kernel_times"]
 
 _lib = None
 
@@ -90,6 +90,7 @@ def load():
     lib.emrifd_launch_count.argtypes = [vp]
     lib.emrifd_launch_count.restype = i64
     lib.emrifd_sum_kernel_time.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(i64)]
+    lib.emrifd_sum_kernel_times.argtypes = [vp, i32, C.POINTER(dbl), C.POINTER(dbl), C.POINTER(i64)]
     assert lib.emrifd_sizeof_branch() == BRANCH_DTYPE.itemsize
     assert lib.emrifd_sizeof_walker() == WALKER_DTYPE.itemsize
     _lib = lib

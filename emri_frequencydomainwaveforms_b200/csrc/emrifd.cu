@@ -103,9 +103,9 @@ struct emrifd_handle {
     int k13_few;
     // kernel timing
     int timing;
-    cudaEvent_t ev_a[64], ev_b[64];
+    cudaEvent_t ev_a[64], ev_b[64], ev_m[64]; // before empty_tile_kernel, after mode_sum_kernel, between the two
     int ev_n;
-    double sum_ms;
+    double sum_ms, sum_ms_main;
     int64_t sum_launches;
 };
 
@@ -642,6 +642,35 @@ __device__ __forceinline__ void sincos_cycles(double c, double &sn, double &cs) 
     cs = ((qi + 1) & 2) ? -b : b;
 }
 
+// the same for W arguments at once, the W pairs of Horner chains advanced together (2 W independent dependency chains)
+template <int W>
+__device__ __forceinline__ void sincos_cycles_n(const double (&c)[W], double (&sn)[W], double (&cs)[W]) {
+    double r[W], r2[W], ps[W], pc[W];
+    int qi[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const double q = rint(4.0 * c[i]);
+        qi[i] = (int)q;
+        r[i] = fma(-0.25, q, c[i]);
+        r2[i] = r[i] * r[i];
+        ps[i] = c_sin[7]; pc[i] = c_cos[8];
+    }
+#pragma unroll
+    for (int k = 6; k >= 0; k--) {
+#pragma unroll
+        for (int i = 0; i < W; i++) { ps[i] = fma(ps[i], r2[i], c_sin[k]); pc[i] = fma(pc[i], r2[i], c_cos[k + 1]); }
+    }
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        ps[i] *= r[i];
+        pc[i] = fma(pc[i], r2[i], c_cos[0]);
+        const bool swap = qi[i] & 1;
+        const double a = swap ? pc[i] : ps[i], b = swap ? ps[i] : pc[i];
+        sn[i] = (qi[i] & 2) ? -a : a;
+        cs[i] = ((qi[i] + 1) & 2) ? -b : b;
+    }
+}
+
 // robust bracketed Newton (rare path: cold-start failures, turnover neighbourhood)
 __device__ __noinline__ double solve_bracketed(double c1, double c2, double c3, double delta, double xl, double xh,
                                                double sdir, double hj) {
@@ -980,7 +1009,7 @@ __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)
                                          double (&ao_i)[W]) {
     double er[W], ei[W];
     {
-        double re[W], im[W], s[W], uu[W], fd[W], fdd[W], sn[W], cs[W];
+        double re[W], im[W], s[W], uu[W], fd[W], fdd[W], sn[W], cs[W], cyc[W];
         const double c1 = S.c1, d2 = S.d2, d3 = S.d3;
         const double tj = S.tj, mu_hi = S.mu_hi, mu_lo = S.mu_lo, p1 = S.p1, p2 = S.p2, p3 = S.p3;
 #pragma unroll
@@ -1001,9 +1030,9 @@ __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)
             const double e0 = fma(fi, tj, -p0);
             p0 -= rint_fast(p0);
             const double poly = fma(fi, xi, xi * fma(xi, fma(xi, p3, p2), p1));
-            const double cyc = ((p0 - mu_hi) + (e0 - mu_lo)) + poly;
-            sincos_cycles(cyc, sn[i], cs[i]);
+            cyc[i] = ((p0 - mu_hi) + (e0 - mu_lo)) + poly;
         }
+        sincos_cycles_n<W>(cyc, sn, cs);
         bool slow = false; // one branch for all W bins: the rare path is taken by the whole group
 #pragma unroll
         for (int i = 0; i < W; i++) slow |= !(uu[i] <= 0.0009765625);
@@ -2405,7 +2434,8 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaMemset(h->d_status, 0, sizeof(int));
     bool ok = true; // every set-up call is checked: a handle is either fully usable or not created
     for (int i = 0; i < 4; i++) ok &= cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming) == cudaSuccess;
-    for (int i = 0; i < 64; i++) ok &= cudaEventCreate(&h->ev_a[i]) == cudaSuccess && cudaEventCreate(&h->ev_b[i]) == cudaSuccess;
+    for (int i = 0; i < 64; i++)
+        ok &= cudaEventCreate(&h->ev_a[i]) == cudaSuccess && cudaEventCreate(&h->ev_b[i]) == cudaSuccess && cudaEventCreate(&h->ev_m[i]) == cudaSuccess;
     int optin = 0;
     ok &= cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess;
     const int big = optin - 4096; // static smem of the kernels (< 4 KB) comes out of the same budget
@@ -2437,7 +2467,7 @@ int emrifd_destroy(emrifd_handle_t *h) {
     cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq); cudaFree(h->d_gmem); cudaFree(h->d_goff); cudaFree(h->d_pieces);
     if (h->h_ws) cudaFreeHost(h->h_ws);
     for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
-    for (int i = 0; i < 64; i++) { if (h->ev_a[i]) cudaEventDestroy(h->ev_a[i]); if (h->ev_b[i]) cudaEventDestroy(h->ev_b[i]); }
+    for (int i = 0; i < 64; i++) { if (h->ev_a[i]) cudaEventDestroy(h->ev_a[i]); if (h->ev_b[i]) cudaEventDestroy(h->ev_b[i]); if (h->ev_m[i]) cudaEventDestroy(h->ev_m[i]); }
     cudaGetLastError();
     delete h;
     return 0;
@@ -2646,6 +2676,7 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     } while (0)
     SUM_DISPATCH(empty_tile_kernel, EMPTY_THREADS, grid, 0);
     h->launches++;
+    if (ev >= 0) cudaEventRecord(h->ev_m[ev], h->stream);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, true, SUM_BPT, true>, SUM_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
@@ -3023,20 +3054,27 @@ int emrifd_debug_stats(uint64_t *out) { // debug build only: read and clear the 
 }
 #endif
 
-int emrifd_sum_kernel_time(emrifd_handle_t *h, int enable, double *ms, int64_t *launches) {
+int emrifd_sum_kernel_times(emrifd_handle_t *h, int enable, double *ms_pair, double *ms_mode_sum, int64_t *launches) {
     if (!h) return EMRIFD_ERR_INVALID;
     cudaSetDevice(h->device);
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (int i = 0; i < h->ev_n; i++) {
-        float e = 0;
-        if (cudaEventElapsedTime(&e, h->ev_a[i], h->ev_b[i]) == cudaSuccess) { h->sum_ms += e; h->sum_launches++; }
+        float e = 0, m = 0;
+        if (cudaEventElapsedTime(&e, h->ev_a[i], h->ev_b[i]) == cudaSuccess && cudaEventElapsedTime(&m, h->ev_m[i], h->ev_b[i]) == cudaSuccess) {
+            h->sum_ms += e; h->sum_ms_main += m; h->sum_launches++;
+        }
     }
     h->ev_n = 0;
-    if (ms) *ms = h->sum_ms;
+    if (ms_pair) *ms_pair = h->sum_ms;
+    if (ms_mode_sum) *ms_mode_sum = h->sum_ms_main;
     if (launches) *launches = h->sum_launches;
-    if (ms || launches) { h->sum_ms = 0; h->sum_launches = 0; }
+    if (ms_pair || ms_mode_sum || launches) { h->sum_ms = 0; h->sum_ms_main = 0; h->sum_launches = 0; }
     h->timing = enable;
     return 0;
+}
+
+int emrifd_sum_kernel_time(emrifd_handle_t *h, int enable, double *ms, int64_t *launches) {
+    return emrifd_sum_kernel_times(h, enable, ms, nullptr, launches);
 }
 
 } // extern "C"
