@@ -7,8 +7,8 @@ check_mode_by_mode.py:125-136,194-213), T = 1 yr, dt = 10 s, eps = 1e-2, N = 3 1
 of a batch is a DISTINCT draw and NBATCH pre-built batches rotate across the steps (NBATCH x B draws per GPU).
 One *step* = one pass of the hot path over a batch of B walkers per GPU: spline build -> segmentation -> (m, n) grouping ->
 SPA mode sum writing h+(f), hx(f) on f >= 0 (32 B/bin) fused with the PSD-weighted <d|h>, <h|h>, |d-h|^2 reductions against
-an injected signal; with more than one GPU the step ends with the all_gather of the B log-likelihoods (the one collective
-walker sharding needs).  `value` = walkers (waveform + likelihood) per second with the packed sparse inputs resident in HBM;
+an injected signal; with more than one GPU every step issues the all_gather of its B log-likelihoods (the one collective
+walker sharding needs; asynchronous, overlapping the next step's kernels, drained before the timed region closes).  `value` = walkers (waveform + likelihood) per second with the packed sparse inputs resident in HBM;
 `e2e` = the same through the host-buffer C-ABI call (H2D of the sparse inputs and D2H of the likelihoods inside the timed
 region).  Extra keys measured in the same run: `cfg1` (BASELINE configs[0] system, sparse support, HBM-bound), `cfg4_binsharded`
 (BASELINE configs[3]: one 4-yr all-mode waveform, frequency-bin sharded over the N GPUs + NCCL all_reduce, strong scaling)
@@ -166,7 +166,8 @@ def workload_config(batch, workload="plunge"):
             "walkers_per_gpu_per_step": batch, "distinct_draws_per_gpu": batch * NBATCH, "batches_rotating": NBATCH,
             "seed": f"{SEED} + 1000*rank + 17*batch", "T_yr": T_YR, "dt_s": DT, "eps": EPS, "N": grid_len(),
             "l2": "per-step output (B x 50.5 MB) and inputs exceed the 126 MB L2; no explicit flush needed",
-            "parallelism": "walker-sharded; the step ends with the all_gather of the log-likelihoods when N > 1",
+            "parallelism": "walker-sharded; when N > 1 every step issues the NCCL all_gather of its log-likelihoods (asynchronous: it overlaps the next "
+                            "step's kernels; the last one is drained inside the timed region)",
             "data_note": "trajectories / amplitudes from the package's offline stand-in producers (FEW's data files are absent)"}
 
 
@@ -313,11 +314,22 @@ def main():
     ll_all = torch.empty(B * world, dtype=torch.float64, device=dev)
     flags = _lib.INCLUDE_MINUS_M | _lib.MASK_POSITIVE
 
+    pending = [None]
+
     def gather_ll(src):
         """The collective of walker sharding: every rank ends a step with all B x N log-likelihoods (what Eryn's
-        compute_log_like returns to the ensemble move, ensemble.py:1283-1318)."""
+        compute_log_like returns to the ensemble move, ensemble.py:1283-1318).  Issued asynchronously on NCCL's stream so that it
+        overlaps the next step's kernels (steps are independent batches); the previous step's gather is waited for before its
+        buffers are reused, and the last one before the timed region closes (drain_ll)."""
+        if pending[0] is not None:
+            pending[0].wait()
         ll_vec.copy_(src)
-        dist.all_gather_into_tensor(ll_all, ll_vec)
+        pending[0] = dist.all_gather_into_tensor(ll_all, ll_vec, async_op=True)
+
+    def drain_ll():
+        if pending[0] is not None:
+            pending[0].wait()
+            pending[0] = None
 
     def step_device(i):
         pb, db = pbs[i % NBATCH], dbs[i % NBATCH]
@@ -339,6 +351,7 @@ def main():
             flags, hp.data_ptr(), hc.data_ptr(), like_host.ctypes.data))
         if dist is not None:     # host results -> device -> all_gather -> host: what a multi-process sampler would do
             gather_ll(like_host_t[:, 0].to(dev, non_blocking=False))
+            drain_ll()
             ll_all.cpu()
 
     def barrier():
@@ -355,6 +368,8 @@ def main():
         ev0.record()
         for s in range(steps):
             fn(first + s)
+        if dist is not None:
+            drain_ll()           # the last step's all_gather belongs to the timed region
         ev1.record()
         torch.cuda.synchronize()
         wall = time.perf_counter() - t0
@@ -424,6 +439,8 @@ def main():
             extras["multi_gpu_parity"] = leg_parity(h, rank, world, dist, N, n, val, dev)
         h.check(h.lib.emrifd_set_data(h.h, data_w.data_ptr(), wfac.data_ptr(), n))
 
+    if dist is not None:
+        drain_ll()
     if rank != 0:
         if dist is not None:
             dist.destroy_process_group()
