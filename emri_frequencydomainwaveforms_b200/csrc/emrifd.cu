@@ -1786,19 +1786,19 @@ __device__ __forceinline__ void sum_consumer(const SumParams &p, SumShared &sh, 
             }
         }
         if (nb > 0) {
-            const SubEntry *sub = ring + slot * SUM_SUBCAP;
-            const int tb0 = 2 * tid;
-            for (int si = 0; si < nsw; si++) {
-                const SubEntry &E = sub[si];
+            // the thread's bin range as one opaque register pair (kept live instead of being re-derived from %tid every pass)
+            int tb0 = 2 * tid, tb1 = 2 * tid + nb - 1;
+            asm volatile("" : "+r"(tb0), "+r"(tb1));
+            const SubEntry *Ep = ring + slot * SUM_SUBCAP;
+            const SubEntry *const Eend = Ep + nsw;
+            for (; Ep != Eend; ++Ep) {
+                const SubEntry &E = *Ep;
                 const Piece &S = E.P;
-                const int lo = E.s - tb0, hi = E.e - tb0;
+                const int es = E.s, ee = E.e;
+                if (es > tb1 || ee < tb0) continue; // the piece does not touch this thread's bins
                 bool in[2];
-                in[0] = lo <= 0 && hi >= 0;
-                in[1] = lo <= 1 && hi >= 1 && nb > 1;
-#ifdef SUM_STATS
-                if (lane == 0) STAT_ADD(3, 1);
-#endif
-                if (!(in[0] || in[1])) continue;
+                in[0] = es <= tb0;                  // (then ee >= tb0 holds)
+                in[1] = ee > tb0 && nb > 1;         // (then es <= tb0 + 1 holds)
                 STAT_ADD(4, 1); STAT_ADD(5, (int)in[0] + (int)in[1]);
                 const unsigned int smask = E.fmask;
                 const int fl = E.flags;
