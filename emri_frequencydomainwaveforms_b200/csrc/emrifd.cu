@@ -1219,14 +1219,19 @@ __global__ void __launch_bounds__(PIECE_THREADS) piece_build_kernel(PieceParams 
     const emrifd_walker_t wd = p.w[blockIdx.y];
     const int G = p.gcount[blockIdx.y], L = wd.L, K = wd.K, R = 2 * K + 4;
     const int nseg = L - 1;
-    const long long tot = (long long)G * MAXBR * nseg;
+    const long long tot = (long long)G * nseg; // (group, segment) pairs; one thread per (branch slot, group, segment)
     const double *coeff = p.coeff + wd.coeff_off;
     const double *gq = p.gq + 16 * wd.teuk_off;
     const double *tk = p.t + wd.knot_off;
-    for (long long idx = (long long)blockIdx.x * PIECE_THREADS + threadIdx.x; idx < tot; idx += (long long)gridDim.x * PIECE_THREADS) {
-        const int r = (int)(idx / nseg), j = (int)(idx - (long long)r * nseg);
-        const int gi = r / MAXBR, lead = p.leader[wd.mode_off + gi];
-        const emrifd_branch_t *b = p.br + (wd.mode_off + lead) * MAXBR + (r % MAXBR);
+    for (long long idx = (long long)blockIdx.x * PIECE_THREADS + threadIdx.x; idx < tot * MAXBR; idx += (long long)gridDim.x * PIECE_THREADS) {
+        // (group, segment) pairs first, branch slot last: the threads of a warp share the branch slot, and slot 0 -- the only
+        // non-empty one of a monotone harmonic -- keeps whole warps busy while the warps of the empty slots leave at once
+        const int bslot = (int)(idx / tot);
+        const long long gj = idx - (long long)bslot * tot;
+        const int gi = (int)(gj / nseg), j = (int)(gj - (long long)gi * nseg);
+        const int r = gi * MAXBR + bslot;
+        const int lead = p.leader[wd.mode_off + gi];
+        const emrifd_branch_t *b = p.br + (wd.mode_off + lead) * MAXBR + bslot;
         if (b->end < b->start) continue;
         const int ja = b->ja, jb = b->jb, dir = b->dir;
         if (j < ja || j > jb) continue;
@@ -1869,15 +1874,16 @@ __global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
 }
 
 // deterministic second stage: one CTA per walker
-__global__ void __launch_bounds__(256) like_finalize_kernel(const double *__restrict__ partial, long long ntiles,
-                                                            double *__restrict__ out, const int *__restrict__ wstatus) {
-    __shared__ double s[3][256];
+#define FIN_THREADS 1024
+__global__ void __launch_bounds__(FIN_THREADS) like_finalize_kernel(const double *__restrict__ partial, long long ntiles,
+                                                                    double *__restrict__ out, const int *__restrict__ wstatus) {
+    __shared__ double s[3][FIN_THREADS];
     const double *pp = partial + (long long)blockIdx.x * ntiles * 3;
     double a0 = 0, a1 = 0, a2 = 0;
-    for (long long i = threadIdx.x; i < ntiles; i += 256) { a0 += pp[3 * i]; a1 += pp[3 * i + 1]; a2 += pp[3 * i + 2]; }
+    for (long long i = threadIdx.x; i < ntiles; i += FIN_THREADS) { a0 += pp[3 * i]; a1 += pp[3 * i + 1]; a2 += pp[3 * i + 2]; }
     s[0][threadIdx.x] = a0; s[1][threadIdx.x] = a1; s[2][threadIdx.x] = a2;
     __syncthreads();
-    for (int o = 128; o > 0; o >>= 1) {
+    for (int o = FIN_THREADS / 2; o > 0; o >>= 1) {
         if ((int)threadIdx.x < o) {
             s[0][threadIdx.x] += s[0][threadIdx.x + o];
             s[1][threadIdx.x] += s[1][threadIdx.x + o];
@@ -2688,7 +2694,7 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
     if (like) {
-        like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, ntiles * SUM_CW, like_out, h->d_wstatus);
+        like_finalize_kernel<<<(unsigned)B, FIN_THREADS, 0, h->stream>>>(h->d_partial, ntiles * SUM_CW, like_out, h->d_wstatus);
         h->launches++;
         CUDA_TRY(h, cudaGetLastError());
     }
@@ -2804,7 +2810,7 @@ int emrifd_loglike(emrifd_handle_t *h, const double *templates, int64_t B, doubl
     if (rc) return rc;
     dim3 grid((unsigned)nb, (unsigned)B);
     loglike_partial_kernel<<<grid, 256, 0, h->stream>>>((const double2 *)templates, (const double2 *)h->d_data, h->d_wfac, n, h->d_partial);
-    like_finalize_kernel<<<(unsigned)B, 256, 0, h->stream>>>(h->d_partial, nb, out, nullptr);
+    like_finalize_kernel<<<(unsigned)B, FIN_THREADS, 0, h->stream>>>(h->d_partial, nb, out, nullptr);
     h->launches += 2;
     CUDA_TRY(h, cudaGetLastError());
     return 0;
