@@ -94,23 +94,53 @@ def draw_walkers(n_distinct, n_total, seed, T=T_YR, dt=DT, eps=EPS, workload="pl
     return items
 
 
-def bench_batches(rank, B, nbatch=NBATCH):
-    """The NBATCH batches of B distinct draws of `rank` (cached on disk: the reference arm, which runs first on the same box,
-    and the B200 arm draw the very same walkers)."""
-    path = os.path.join(tempfile.gettempdir(), f"emrifd_bench_walkers_r{rank}_B{B}_n{nbatch}_s{SEED}.pkl")
+def _pool_path(g, B, nbatch):
+    return os.path.join(tempfile.gettempdir(), f"emrifd_bench_walkers_r{g}_B{B}_n{nbatch}_s{SEED}.pkl")
+
+
+def draw_pool(g, B, nbatch=NBATCH, wait_s=0.0):
+    """The NBATCH batches of B distinct draws with seed index g (cached on disk: the reference arm, which runs first on the same
+    box, and the B200 arm draw the very same walkers; with several ranks every rank draws its own pool and reads the others').
+    wait_s > 0: another process is drawing this pool right now -- poll for its file before falling back to drawing it here."""
+    path = _pool_path(g, B, nbatch)
+    t0 = time.time()
+    while True:
+        try:
+            with open(path, "rb") as f:
+                return pickle.load(f)
+        except Exception:
+            pass
+        if time.time() - t0 >= wait_s:
+            break
+        time.sleep(0.5)
+    batches = [draw_walkers(B, B, SEED + 1000 * g + 17 * k) for k in range(nbatch)]
     try:
-        with open(path, "rb") as f:
-            return pickle.load(f)
-    except Exception:
-        pass
-    batches = [draw_walkers(B, B, SEED + 1000 * rank + 17 * k) for k in range(nbatch)]
-    try:
-        with open(path + ".tmp", "wb") as f:
+        with open(path + f".tmp{os.getpid()}", "wb") as f:
             pickle.dump(batches, f)
-        os.replace(path + ".tmp", path)
+        os.replace(path + f".tmp{os.getpid()}", path)
     except Exception:
         pass
     return batches
+
+
+def bench_batches(rank, B, nbatch=NBATCH, world=1):
+    """The NBATCH batches of B walkers that `rank` evaluates.  One GPU: pool 0 as drawn.  Several GPUs: the draws of all ranks'
+    pools are dealt out per batch index, heaviest first, each to the least-loaded rank (distributed.balanced_walker_assignment on
+    engine.walker_cost_estimate, the bins swept by a walker's harmonics), so that every rank carries the same work: a random split
+    leaves the heaviest of 8 ranks 13-18 % above the mean, which a synchronous ensemble step pays in full."""
+    own = draw_pool(rank, B, nbatch)
+    if world == 1:
+        return own
+    from emri_frequencydomainwaveforms_b200 import distributed as D, engine
+    pools = [own if g == rank else draw_pool(g, B, nbatch, wait_s=900.0) for g in range(world)]
+    df = 1.0 / (grid_len() * DT)
+    out = []
+    for k in range(nbatch):
+        flat = [(g, w) for g in range(world) for w in range(B)]
+        cost = np.array([engine.walker_cost_estimate(pools[g][k][w], df) for g, w in flat])
+        mine = D.balanced_walker_assignment(cost, world)[rank]
+        out.append([pools[flat[i][0]][k][flat[i][1]] for i in mine])
+    return out
 
 
 def grid_len(T=T_YR, dt=DT):
@@ -164,7 +194,7 @@ def workload_config(batch, workload="plunge"):
                 "FD waveform on f>=0 + PSD-weighted likelihood, T=1 yr, dt=10 s, eps=1e-2, N=3155815")
     return {"workload": desc,
             "walkers_per_gpu_per_step": batch, "distinct_draws_per_gpu": batch * NBATCH, "batches_rotating": NBATCH,
-            "seed": f"{SEED} + 1000*rank + 17*batch", "T_yr": T_YR, "dt_s": DT, "eps": EPS, "N": grid_len(),
+            "seed": f"{SEED} + 1000*pool + 17*batch (N > 1: the pools of all ranks dealt out per batch by estimated cost, equal counts and equal work per rank)", "T_yr": T_YR, "dt_s": DT, "eps": EPS, "N": grid_len(),
             "l2": "per-step output (B x 50.5 MB) and inputs exceed the 126 MB L2; no explicit flush needed",
             "parallelism": "walker-sharded; when N > 1 every step issues the NCCL all_gather of its log-likelihoods (asynchronous: it overlaps the next "
                             "step's kernels; the last one is drained inside the timed region)",
@@ -190,6 +220,7 @@ def run_reference(args, guard):
     """--impl reference: the path's CPU implementation (optimised double port, all host threads) on the same batches."""
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
+        draw_pool(rank, args.batch)      # (rank 0 deals the walkers out of every rank's pool; nothing is timed here)
         return
     # torchrun exports OMP_NUM_THREADS=1 to its workers; this arm is meant to use every host thread it can
     os.environ["OMP_NUM_THREADS"] = str(host_threads())
@@ -200,7 +231,7 @@ def run_reference(args, guard):
     N = grid_len()
     val = 1.0 / (N * DT)
     B = args.batch
-    batches = bench_batches(0, B)
+    batches = bench_batches(0, B, world=max(1, args.gpus))
     data_w, wfac = injected_signal_host(fast, N, val)
 
     def step(i):
@@ -289,7 +320,7 @@ def main():
     if args.workload == "cfg1":
         batches = [draw_walkers(1, B, SEED + 1000 * rank + 17 * k, workload="cfg1") for k in range(NBATCH)]
     else:
-        batches = bench_batches(rank, B)
+        batches = bench_batches(rank, B, world=world)
     pbs = [engine.PackedBatch(items) for items in batches]
     dbs = [engine.DeviceBatch(pb, h) for pb in pbs]
     for pb in pbs:

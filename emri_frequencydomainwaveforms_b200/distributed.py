@@ -62,6 +62,24 @@ def balanced_bin_slices(work, world, base_cost=0.02, align=1024):
     return [(int(edges[r]), int(edges[r + 1] - edges[r])) for r in range(world)]
 
 
+def balanced_walker_assignment(cost, world):
+    """Deal walkers to ``world`` ranks so that every rank carries about the same estimated work AND the same number of walkers
+    (counts differ by at most one): walkers in order of descending cost (ties by index), each to the rank with the least work so
+    far among those that still have room (longest-processing-time rule with a capacity).  Returns a list of index lists, one per
+    rank; deterministic, so every rank computes the same assignment without communication."""
+    cost = np.asarray(cost, dtype=np.float64)
+    n = len(cost)
+    cap = [n // world + (1 if r < n % world else 0) for r in range(world)]
+    order = sorted(range(n), key=lambda i: (-cost[i], i))
+    shares = [[] for _ in range(world)]
+    load = [0.0] * world
+    for i in order:
+        r = min((r for r in range(world) if len(shares[r]) < cap[r]), key=lambda r: (load[r], r))
+        shares[r].append(i)
+        load[r] += cost[i]
+    return shares
+
+
 def gather_walker_results(local, counts, group=None):
     """all_gather ragged per-rank result vectors (torch tensors, same dtype/device) into one tensor."""
     import torch

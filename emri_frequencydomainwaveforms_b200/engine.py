@@ -182,3 +182,15 @@ def run_loglike_host(pb, handle, N, val=0.0, fpos_dev=None, include_minus_m=True
         out.ctypes.data)
     handle.check(rc)
     return out
+
+
+def walker_cost_estimate(item, df):
+    """Host-side estimate of a walker's mode-sum work = stationary points to solve: for every distinct (m, n) of its modes the
+    frequency bins swept by f_mn = m f_phi + n f_r along the trajectory (total variation, so both branches of a turnover count),
+    in bins of width ``df``.  Used to balance walker shards (distributed.balanced_walker_assignment); the exact count comes from the
+    device (group_evaluations) once the work-list exists."""
+    fp, fr = np.asarray(item["f_phi"]), np.asarray(item["f_r"])
+    cost = 0.0
+    for m, n in set(zip(np.asarray(item["m_arr"]).tolist(), np.asarray(item["n_arr"]).tolist())):
+        cost += float(np.sum(np.abs(np.diff(m * fp + n * fr))))
+    return cost / df
