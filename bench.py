@@ -650,8 +650,8 @@ def leg_cfg1(h, rank, world, dist, barrier, N, n, val, B, flags, hp, hc, like, d
             step()
         ev1.record()
         torch.cuda.synchronize()
-        kms, kl = C.c_double(), C.c_int64()
-        h.check(h.lib.emrifd_sum_kernel_time(h.h, 0, C.byref(kms), C.byref(kl)))
+        kms, kmain, kl = C.c_double(), C.c_double(), C.c_int64()
+        h.check(h.lib.emrifd_sum_kernel_times(h.h, 0, C.byref(kms), C.byref(kmain), C.byref(kl)))
         tt = torch.tensor([ev0.elapsed_time(ev1)], dtype=torch.float64, device=dev)
         if dist is not None:
             dist.all_reduce(tt, op=dist.ReduceOp.MAX)
@@ -664,7 +664,8 @@ def leg_cfg1(h, rank, world, dist, barrier, N, n, val, B, flags, hp, hc, like, d
             pass
         hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
         gbs = 32.0 * n * B / (k_ms * 1e-3) / 1e9
-        return {"walkers_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "kernel_ms": k_ms, "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak,
+        return {"walkers_per_s": world * B / (ms * 1e-3), "ms_per_step": ms, "kernel_ms": k_ms, "mode_sum_ms": kmain.value / max(kl.value, 1),
+                "hbm_gbs": gbs, "hbm_frac": gbs / hbm_peak,
                 "hbm_peak": hbm_peak, "algorithmic_bytes_per_launch": 32.0 * n * B, "group_evals_per_walker": float(engine.group_evaluations(db).mean()),
                 "what": "configs[0] system (M=1e6, mu=10, p0=12, e0=0.35, 1 yr, eps=1e-2): waveform on f>=0 + likelihood, "
                         f"{B} walkers/GPU/step; kernel = empty_tile + mode_sum bracket, charged 32 B/bin of h+, hx written"}

@@ -103,7 +103,10 @@ struct emrifd_handle {
     int k13_few;
     // kernel timing
     int timing;
-    cudaEvent_t ev_a[64], ev_b[64], ev_m[64]; // before empty_tile_kernel, after mode_sum_kernel, between the two
+    cudaEvent_t ev_a[64], ev_b[64], ev_m[64], ev_s[64]; // before the tile classification, after the join of the launch pair, around mode_sum_kernel
+    cudaStream_t aux;                         // empty_tile_kernel's stream (forked after the classification, joined before the finalize)
+    cudaEvent_t ev_fork, ev_join;
+    int overlap_mode;                         // EMRIFD_OVERLAP=0: zero-fill after the sum on the same stream (A/B runs); default: underneath it
     int ev_n;
     double sum_ms, sum_ms_main;
     int64_t sum_launches;
@@ -556,6 +559,7 @@ struct SumParams {
     int ntiles;                 // tiles per walker (= ceil(j_cnt / SUM_TILE))
     unsigned long long *queue;  // [B * ntiles] non-empty tiles as (walker << 32 | tile), filled by empty_tile_kernel
     unsigned int *qctl;         // [0] number of queued tiles, [1] next item handed to a persistent mode_sum CTA
+    unsigned char *tile_flag;   // [B * ntiles] 1: the tile has work for mode_sum_kernel, 0: empty (empty_tile_kernel's)
     // (m, n) groups (group_kernel): one stationary point per (group, bin)
     const int *leader;          // [sum K] walker block at mode_off: first member (mode index) of each group
     const int *gcount;          // [B] groups per walker
@@ -1135,39 +1139,104 @@ __device__ __forceinline__ bool tile_truncated(const SumParams &p, long long jt0
     return jt0 + tile_bins > jend && jend != p.n_data;
 }
 
-// Tiles no harmonic touches (most of the band of a non-plunging eps = 1e-2 system): h = 0 is stored and the tile's likelihood
-// term is the precomputed sum |d~|^2.  A kernel of its own because this work is a pure store stream: no shared memory and
-// 8 resident CTAs per SM keep enough stores in flight to approach the HBM write rate, which the resident CTAs of
-// mode_sum_kernel (register- and smem-limited) cannot.  The walker descriptor and the chunk hulls are fetched together
-// (one memory round trip before the stores).  A walker whose status word is set (bad knots, too many branches) has all its
-// tiles treated as empty: zeros in h, NaN in the likelihood (like_finalize_kernel).
-#define EMPTY_THREADS 256
+// Does anything of walker `wy`'s work-list touch tile `tx`?  (chunk hulls; a failed walker has no work.)  `per_bin`: the tile's
+// likelihood term cannot come from the precomputed whole-tile sum |d~|^2 (no table for this slice, or the slice cuts the tile).
+template <bool LIKE, int BPT>
+__device__ __forceinline__ bool tile_has_work(const SumParams &p, int tx, int wy, long long &jt0, long long &jt1) {
+    constexpr int TILE = SUM_CT * BPT;
+    const long long *crng = p.chunk_rng + (long long)wy * p.cpw * 2;
+    const int nrec = p.gcount[wy] * MAXBR;
+    jt0 = p.j_lo + (p.tile_first + (long long)tx * p.tile_stride) * TILE;
+    const long long jend = p.j_lo + p.j_cnt;
+    jt1 = (jt0 + TILE < jend ? jt0 + TILE : jend) - 1;
+    bool any = false;
+    for (int ch = 0; ch * SUM_CHUNK < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
+    if (p.wstatus[wy]) any = false;
+    const bool per_bin = LIKE && (p.no_empty || tile_truncated(p, jt0, TILE));
+    return any || per_bin;
+}
+
+// Pass 1a: one thread per (tile, walker) flags the tiles that have work for mode_sum_kernel; queue_build_kernel then compacts
+// the flagged tiles into the work queue IN ORDER (walker-major, ascending tile: a walker's tiles stay together for the producer
+// warp's per-walker cache, the order is the same from run to run, and the long low-frequency tiles of a many-mode waveform come
+// first instead of landing in the tail: atomically appended queues cost configs[3] 7 %).  A few microseconds each.
+#define CLASSIFY_THREADS 256
+template <bool LIKE, int BPT>
+__global__ void __launch_bounds__(CLASSIFY_THREADS) classify_tiles_kernel(SumParams p) {
+    const int tx = blockIdx.x * CLASSIFY_THREADS + threadIdx.x, wy = blockIdx.y;
+    if (tx >= p.ntiles) return;
+    long long jt0, jt1;
+    p.tile_flag[(long long)wy * p.ntiles + tx] = tile_has_work<LIKE, BPT>(p, tx, wy, jt0, jt1) ? 1 : 0;
+}
+#define QBUILD_THREADS 1024
+__global__ void __launch_bounds__(QBUILD_THREADS) queue_build_kernel(const unsigned char *__restrict__ flag, long long ntot, int ntiles,
+                                                                     unsigned long long *__restrict__ queue, unsigned int *__restrict__ qctl) {
+    __shared__ unsigned int s_warp[QBUILD_THREADS / 32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    // a thread owns a run of flags that is a multiple of 8 long and reads them eight at a time (the flag array is 8-byte aligned
+    // and allocated up to the next multiple of 8; the bytes beyond ntot are masked here)
+    long long per = (ntot + QBUILD_THREADS - 1) / QBUILD_THREADS;
+    per = (per + 7) & ~7LL;
+    const long long lo = (long long)tid * per, hi = lo + per < ntot ? lo + per : ntot;
+    const unsigned long long *f8 = reinterpret_cast<const unsigned long long *>(flag);
+    unsigned int cnt = 0;
+    for (long long t = lo; t < hi; t += 8) {
+        unsigned long long w = f8[t >> 3];
+        if (t + 8 > ntot) w &= (1ull << (8 * (ntot - t))) - 1ull; // bytes past the end
+        cnt += __popcll(w & 0x0101010101010101ull);
+    }
+    unsigned int incl = cnt;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, incl, o); if (lane >= o) incl += u; }
+    if (lane == 31) s_warp[wid] = incl;
+    __syncthreads();
+    if (wid == 0) {
+        unsigned int v = s_warp[lane];
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const unsigned int u = __shfl_up_sync(0xffffffffu, v, o); if (lane >= o) v += u; }
+        s_warp[lane] = v; // inclusive totals of the warps
+    }
+    __syncthreads();
+    unsigned int off = incl - cnt + (wid > 0 ? s_warp[wid - 1] : 0u);
+    if (cnt) {
+        unsigned int wy = (unsigned int)(lo / ntiles), tx = (unsigned int)(lo - (long long)wy * ntiles);
+        for (long long t = lo; t < hi; t += 8) {
+            unsigned long long w = f8[t >> 3];
+            if (t + 8 > ntot) w &= (1ull << (8 * (ntot - t))) - 1ull;
+#pragma unroll
+            for (int c = 0; c < 8; c++) {
+                if ((w >> (8 * c)) & 1ull) queue[off++] = ((unsigned long long)wy << 32) | tx;
+                if (++tx == (unsigned int)ntiles) { tx = 0; wy++; }
+            }
+        }
+    }
+    if (tid == QBUILD_THREADS - 1) qctl[0] = s_warp[QBUILD_THREADS / 32 - 1];
+}
+
+// Pass 1b: tiles no harmonic touches (most of the band of a non-plunging eps = 1e-2 system): h = 0 is stored and the tile's
+// likelihood term is the precomputed sum |d~|^2.  A kernel of its own because this work is a pure store stream, and on a stream
+// of its own: one 128-thread, 32-register CTA per tile slots into the 4 K registers per SM that mode_sum_kernel's CTA leaves
+// free, so the zeros go out underneath the FP64-bound sum (the bench batch's 0.27 ms store stream costs the sum 0.12 ms), and
+// 16 CTAs per SM take the whole machine once the sum is done (the sparse regime: 7 TB/s).  A walker whose status word is set
+// (bad knots, too many branches) has all its tiles treated as empty: zeros in h, NaN in the likelihood (like_finalize_kernel).
+// Measured alternatives: persistent zero-fill CTAs with dynamic tile hand-out stream 30 % slower on their own (4.9 TB/s) and,
+// by keeping the memory system busy during the whole sparse sum, make that latency-bound sum 2.3x slower.
+#define EMPTY_THREADS 128
 template <bool WRITE_H, bool LIKE, int BPT>
-__global__ void __launch_bounds__(EMPTY_THREADS, 8) empty_tile_kernel(SumParams p) {
+__global__ void __launch_bounds__(EMPTY_THREADS, 16) empty_tile_kernel(SumParams p) {
     constexpr int TILE = SUM_CT * BPT;
     const int tid = threadIdx.x;
-    const long long *crng = p.chunk_rng + (long long)blockIdx.y * p.cpw * 2;
-    const long long c_lo = crng[0], c_hi = crng[1];          // first chunk's hull: independent of the descriptor
-    const emrifd_walker_t *wp = p.w + blockIdx.y;
-    const int nrec = p.gcount[blockIdx.y] * MAXBR;
-    const int bad = p.wstatus[blockIdx.y];
-    const long long out_off = wp->out_off;
-    const long long jt0 = p.j_lo + (p.tile_first + (long long)blockIdx.x * p.tile_stride) * TILE;
+    if (p.tile_flag[(long long)blockIdx.y * p.ntiles + blockIdx.x]) return; // mode_sum_kernel's tile
+    const long long out_off = p.w[blockIdx.y].out_off;
+    const long long tglob = p.tile_first + (long long)blockIdx.x * p.tile_stride; // tile index within the slice
+    const long long jt0 = p.j_lo + tglob * TILE;
     const long long jend = p.j_lo + p.j_cnt;
     const long long jt1 = (jt0 + TILE < jend ? jt0 + TILE : jend) - 1;
-    bool any = !(c_lo > jt1 || c_hi < jt0);
-    for (int ch = 1; ch * SUM_CHUNK < nrec; ch++) any |= !(crng[2 * ch] > jt1 || crng[2 * ch + 1] < jt0);
-    if (bad) any = false;
-    const bool per_bin = LIKE && (p.no_empty || tile_truncated(p, jt0, TILE));
-    if (any || per_bin) { // work for mode_sum_kernel's persistent CTAs (processing order does not affect any result)
-        if (tid == 0) p.queue[atomicAdd(&p.qctl[0], 1u)] = ((unsigned long long)blockIdx.y << 32) | blockIdx.x;
-        return;
-    }
     const int ntile_ = (int)(jt1 - jt0 + 1);
     if (WRITE_H) {
         const double2 z = make_double2(0.0, 0.0);
         const long long zero = p.g.zero;
-#pragma unroll 2
+#pragma unroll 4
         for (int lb = tid; lb < ntile_; lb += EMPTY_THREADS) {
             const long long j = jt0 + lb;
             if (p.mask_positive) {
@@ -1181,8 +1250,8 @@ __global__ void __launch_bounds__(EMPTY_THREADS, 8) empty_tile_kernel(SumParams 
         }
     }
     if (LIKE && tid < SUM_CW) { // the partial-sum slots of the tile's consumer warps
-        double *o = p.partial + (((long long)blockIdx.y * gridDim.x + blockIdx.x) * SUM_CW + tid) * 3;
-        o[0] = (tid == 0) ? p.tile_dd[jt0 / TILE] : 0.0; o[1] = 0.0; o[2] = 0.0;
+        double *o = p.partial + (((long long)blockIdx.y * p.ntiles + blockIdx.x) * SUM_CW + tid) * 3;
+        o[0] = (tid == 0) ? p.tile_dd[p.j_lo / TILE + tglob] : 0.0; o[1] = 0.0; o[2] = 0.0; // (tile_dd is used only when j_lo is tile-aligned)
     }
 }
 
@@ -2440,8 +2509,13 @@ int emrifd_create(int device, void *stream, emrifd_handle_t **out) {
     cudaMemset(h->d_status, 0, sizeof(int));
     bool ok = true; // every set-up call is checked: a handle is either fully usable or not created
     for (int i = 0; i < 4; i++) ok &= cudaEventCreateWithFlags(&h->stage_ev[i], cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaStreamCreateWithFlags(&h->aux, cudaStreamNonBlocking) == cudaSuccess;
+    { const char *ov = getenv("EMRIFD_OVERLAP"); h->overlap_mode = ov ? atoi(ov) : 1; }
+    ok &= cudaEventCreateWithFlags(&h->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+    ok &= cudaEventCreateWithFlags(&h->ev_join, cudaEventDisableTiming) == cudaSuccess;
     for (int i = 0; i < 64; i++)
-        ok &= cudaEventCreate(&h->ev_a[i]) == cudaSuccess && cudaEventCreate(&h->ev_b[i]) == cudaSuccess && cudaEventCreate(&h->ev_m[i]) == cudaSuccess;
+        ok &= cudaEventCreate(&h->ev_a[i]) == cudaSuccess && cudaEventCreate(&h->ev_b[i]) == cudaSuccess && cudaEventCreate(&h->ev_m[i]) == cudaSuccess &&
+              cudaEventCreate(&h->ev_s[i]) == cudaSuccess;
     int optin = 0;
     ok &= cudaDeviceGetAttribute(&optin, cudaDevAttrMaxSharedMemoryPerBlockOptin, device) == cudaSuccess;
     const int big = optin - 4096; // static smem of the kernels (< 4 KB) comes out of the same budget
@@ -2473,7 +2547,10 @@ int emrifd_destroy(emrifd_handle_t *h) {
     cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq); cudaFree(h->d_gmem); cudaFree(h->d_goff); cudaFree(h->d_pieces);
     if (h->h_ws) cudaFreeHost(h->h_ws);
     for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
-    for (int i = 0; i < 64; i++) { if (h->ev_a[i]) cudaEventDestroy(h->ev_a[i]); if (h->ev_b[i]) cudaEventDestroy(h->ev_b[i]); if (h->ev_m[i]) cudaEventDestroy(h->ev_m[i]); }
+    for (int i = 0; i < 64; i++) { if (h->ev_a[i]) cudaEventDestroy(h->ev_a[i]); if (h->ev_b[i]) cudaEventDestroy(h->ev_b[i]); if (h->ev_m[i]) cudaEventDestroy(h->ev_m[i]); if (h->ev_s[i]) cudaEventDestroy(h->ev_s[i]); }
+    if (h->aux) { cudaStreamSynchronize(h->aux); cudaStreamDestroy(h->aux); }
+    if (h->ev_fork) cudaEventDestroy(h->ev_fork);
+    if (h->ev_join) cudaEventDestroy(h->ev_join);
     cudaGetLastError();
     delete h;
     return 0;
@@ -2667,29 +2744,53 @@ static int batch_sum_dev(emrifd_handle *h, int64_t B, int Lmax, int Kmax, const 
     p.no_empty = (like && !p.tile_dd) ? 1 : 0;
     p.ntiles = (int)ntiles;
     {
-        int rc = ensure_bytes(h, (void **)&h->d_queue, &h->queue_cap, (int64_t)sizeof(unsigned long long) * ntiles * B + 16);
+        int rc = ensure_bytes(h, (void **)&h->d_queue, &h->queue_cap, (int64_t)(sizeof(unsigned long long) + 1) * ntiles * B + 32);
         if (rc) return rc;
         p.qctl = (unsigned int *)h->d_queue;
         p.queue = (unsigned long long *)h->d_queue + 2;
+        p.tile_flag = (unsigned char *)(p.queue + ntiles * B);
         CUDA_TRY(h, cudaMemsetAsync(h->d_queue, 0, 16, h->stream));
     }
     // dispatch on (WRITE_H, LIKE)
-#define SUM_DISPATCH(KERNEL, THREADS, GRID, SMEM, ...)                                                   \
-    do {                                                                                                 \
-        if (write_h && like) KERNEL<true, true, SUM_BPT, ##__VA_ARGS__><<<GRID, THREADS, SMEM, h->stream>>>(p);  \
-        else if (write_h) KERNEL<true, false, SUM_BPT, ##__VA_ARGS__><<<GRID, THREADS, SMEM, h->stream>>>(p);    \
-        else KERNEL<false, true, SUM_BPT, ##__VA_ARGS__><<<GRID, THREADS, SMEM, h->stream>>>(p);                 \
+#define SUM_DISPATCH(KERNEL, THREADS, GRID, SMEM, STREAM, ...)                                        \
+    do {                                                                                              \
+        if (write_h && like) KERNEL<true, true, SUM_BPT, ##__VA_ARGS__><<<GRID, THREADS, SMEM, STREAM>>>(p);  \
+        else if (write_h) KERNEL<true, false, SUM_BPT, ##__VA_ARGS__><<<GRID, THREADS, SMEM, STREAM>>>(p);    \
+        else KERNEL<false, true, SUM_BPT, ##__VA_ARGS__><<<GRID, THREADS, SMEM, STREAM>>>(p);                 \
     } while (0)
-    SUM_DISPATCH(empty_tile_kernel, EMPTY_THREADS, grid, 0);
-    h->launches++;
-    if (ev >= 0) cudaEventRecord(h->ev_m[ev], h->stream);
     int per_sm = 0;
     cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, mode_sum_kernel<true, true, SUM_BPT, true>, SUM_THREADS, smem);
     if (per_sm < 1) per_sm = 1;
-    int64_t pgrid = (int64_t)h->num_sms * per_sm;
-    if (ntiles * B <= 4 * pgrid) SUM_DISPATCH(mode_sum_kernel, SUM_THREADS, grid, smem, false); // about one wave: direct grid
-    else SUM_DISPATCH(mode_sum_kernel, SUM_THREADS, (unsigned)pgrid, smem, true);
+    const int64_t pgrid = (int64_t)h->num_sms * per_sm;
+    const bool persistent = ntiles * B > 4 * pgrid; // (about one wave or less: a plain grid, every CTA classifies its own tile)
+    {
+        dim3 cgrid((unsigned)((ntiles + CLASSIFY_THREADS - 1) / CLASSIFY_THREADS), (unsigned)B);
+        if (like) classify_tiles_kernel<true, SUM_BPT><<<cgrid, CLASSIFY_THREADS, 0, h->stream>>>(p);
+        else classify_tiles_kernel<false, SUM_BPT><<<cgrid, CLASSIFY_THREADS, 0, h->stream>>>(p);
+        h->launches++;
+        if (persistent) {
+            queue_build_kernel<<<1, QBUILD_THREADS, 0, h->stream>>>(p.tile_flag, (long long)ntiles * B, (int)ntiles, p.queue, p.qctl);
+            h->launches++;
+        }
+    }
+    // The zero-fill runs on a stream of its own underneath the sum (fork after the classification, join before the finalize);
+    // the sum is launched first so that its CTAs take their SMs and the zero-fill CTAs fill in around them.
+    // (EMRIFD_OVERLAP=0: same stream, after the sum -- for A/B runs.)
+    const bool overlap = h->overlap_mode != 0;
+    cudaStream_t zs = overlap ? h->aux : h->stream;
+    if (overlap) CUDA_TRY(h, cudaEventRecord(h->ev_fork, h->stream));
+    if (ev >= 0) cudaEventRecord(h->ev_m[ev], h->stream);
+    if (persistent) SUM_DISPATCH(mode_sum_kernel, SUM_THREADS, (unsigned)pgrid, smem, h->stream, true);
+    else SUM_DISPATCH(mode_sum_kernel, SUM_THREADS, grid, smem, h->stream, false);
+    if (ev >= 0) cudaEventRecord(h->ev_s[ev], h->stream);
+    if (overlap) CUDA_TRY(h, cudaStreamWaitEvent(h->aux, h->ev_fork, 0));
+    SUM_DISPATCH(empty_tile_kernel, EMPTY_THREADS, grid, 0, zs);
+    if (overlap) {
+        CUDA_TRY(h, cudaEventRecord(h->ev_join, h->aux));
+        CUDA_TRY(h, cudaStreamWaitEvent(h->stream, h->ev_join, 0)); // join: everything after this call sees both kernels' results
+    }
 #undef SUM_DISPATCH
+    h->launches++;
     if (ev >= 0) cudaEventRecord(h->ev_b[ev], h->stream);
     h->launches++;
     CUDA_TRY(h, cudaGetLastError());
@@ -3066,7 +3167,7 @@ int emrifd_sum_kernel_times(emrifd_handle_t *h, int enable, double *ms_pair, dou
     CUDA_TRY(h, cudaStreamSynchronize(h->stream));
     for (int i = 0; i < h->ev_n; i++) {
         float e = 0, m = 0;
-        if (cudaEventElapsedTime(&e, h->ev_a[i], h->ev_b[i]) == cudaSuccess && cudaEventElapsedTime(&m, h->ev_m[i], h->ev_b[i]) == cudaSuccess) {
+        if (cudaEventElapsedTime(&e, h->ev_a[i], h->ev_b[i]) == cudaSuccess && cudaEventElapsedTime(&m, h->ev_m[i], h->ev_s[i]) == cudaSuccess) {
             h->sum_ms += e; h->sum_ms_main += m; h->sum_launches++;
         }
     }

@@ -241,8 +241,8 @@ int emrifd_band_convolve(emrifd_handle_t *h, const double *taps, int H, const do
 int64_t emrifd_launch_count(emrifd_handle_t *h);
 /* CUDA-event time (ms) accumulated by the dominant kernel (mode-sum) since the last reset, and launches */
 int emrifd_sum_kernel_time(emrifd_handle_t *h, int enable, double *ms, int64_t *launches);
-/* the same with the split: ms_pair = empty_tile_kernel + mode_sum_kernel (one bracket), ms_mode_sum = mode_sum_kernel alone
- * (events recorded on the handle's stream around each launch while timing is enabled) */
+/* the same with the split: ms_pair = tile classification + mode_sum_kernel and the concurrent empty_tile_kernel, up to their
+ * join (one bracket), ms_mode_sum = mode_sum_kernel alone (events recorded on the handle's stream while timing is enabled) */
 int emrifd_sum_kernel_times(emrifd_handle_t *h, int enable, double *ms_pair, double *ms_mode_sum, int64_t *launches);
 
 #ifdef __cplusplus
