@@ -36,7 +36,7 @@ SYMBOLS = [
     "emrifd_sum_kernel_time", "emrifd_mode_select", "emrifd_ylm_batch", "emrifd_mode_compact_count",
     "emrifd_mode_compact_gather", "emrifd_tile_bins", "emrifd_batch_sum_cyclic",
     "emrifd_synth_amplitude", "emrifd_walker_status", "emrifd_walker_status_dev", "emrifd_set_k13_mode",
-    "emrifd_window_taps", "emrifd_band_energy", "emrifd_band_convolve", "emrifd_sum_kernel_times"]
+    "emrifd_window_taps", "emrifd_band_energy", "emrifd_band_convolve", "emrifd_sum_kernel_times", "emrifd_set_overlap"]
 
 _lib = None
 
@@ -74,6 +74,7 @@ def load():
     lib.emrifd_walker_status.argtypes = [vp, i64, vp]
     lib.emrifd_walker_status_dev.argtypes = [vp, i64, vp]
     lib.emrifd_set_k13_mode.argtypes = [vp, i32]
+    lib.emrifd_set_overlap.argtypes = [vp, i32]
     lib.emrifd_set_data.argtypes = [vp, vp, vp, i64]
     lib.emrifd_inner_product.argtypes = [vp, vp, vp, i64, i64, vp, vp, vp]
     lib.emrifd_loglike.argtypes = [vp, vp, i64, vp]

@@ -675,6 +675,54 @@ __device__ __forceinline__ void sincos_cycles_n(const double (&c)[W], double (&s
     }
 }
 
+__constant__ double c_rot64[128] = {
+    1.0, 0.0, 0.9951847266721969, 0.0980171403295606, 0.9807852804032304, 0.19509032201612828, 0.9569403357322088, 0.2902846772544624,
+    0.9238795325112867, 0.3826834323650898, 0.881921264348355, 0.47139673682599764, 0.8314696123025452, 0.5555702330196022, 0.773010453362737, 0.6343932841636455,
+    0.7071067811865476, 0.7071067811865476, 0.6343932841636455, 0.773010453362737, 0.5555702330196022, 0.8314696123025452, 0.47139673682599764, 0.881921264348355,
+    0.3826834323650898, 0.9238795325112867, 0.2902846772544624, 0.9569403357322088, 0.19509032201612828, 0.9807852804032304, 0.0980171403295606, 0.9951847266721969,
+    2.0670321098263988e-43, 1.0, -0.0980171403295606, 0.9951847266721969, -0.19509032201612828, 0.9807852804032304, -0.2902846772544624, 0.9569403357322088,
+    -0.3826834323650898, 0.9238795325112867, -0.47139673682599764, 0.881921264348355, -0.5555702330196022, 0.8314696123025452, -0.6343932841636455, 0.773010453362737,
+    -0.7071067811865476, 0.7071067811865476, -0.773010453362737, 0.6343932841636455, -0.8314696123025452, 0.5555702330196022, -0.881921264348355, 0.47139673682599764,
+    -0.9238795325112867, 0.3826834323650898, -0.9569403357322088, 0.2902846772544624, -0.9807852804032304, 0.19509032201612828, -0.9951847266721969, 0.0980171403295606,
+    -1.0, 4.1340642196527976e-43, -0.9951847266721969, -0.0980171403295606, -0.9807852804032304, -0.19509032201612828, -0.9569403357322088, -0.2902846772544624,
+    -0.9238795325112867, -0.3826834323650898, -0.881921264348355, -0.47139673682599764, -0.8314696123025452, -0.5555702330196022, -0.773010453362737, -0.6343932841636455,
+    -0.7071067811865476, -0.7071067811865476, -0.6343932841636455, -0.773010453362737, -0.5555702330196022, -0.8314696123025452, -0.47139673682599764, -0.881921264348355,
+    -0.3826834323650898, -0.9238795325112867, -0.2902846772544624, -0.9569403357322088, -0.19509032201612828, -0.9807852804032304, -0.0980171403295606, -0.9951847266721969,
+    2.2338764406549882e-41, -1.0, 0.0980171403295606, -0.9951847266721969, 0.19509032201612828, -0.9807852804032304, 0.2902846772544624, -0.9569403357322088,
+    0.3826834323650898, -0.9238795325112867, 0.47139673682599764, -0.881921264348355, 0.5555702330196022, -0.8314696123025452, 0.6343932841636455, -0.773010453362737,
+    0.7071067811865476, -0.7071067811865476, 0.773010453362737, -0.6343932841636455, 0.8314696123025452, -0.5555702330196022, 0.881921264348355, -0.47139673682599764,
+    0.9238795325112867, -0.3826834323650898, 0.9569403357322088, -0.2902846772544624, 0.9807852804032304, -0.19509032201612828, 0.9951847266721969, -0.0980171403295606};
+__constant__ double c_sin64[4] = {6.283185307179586, -41.34170224039976, 81.60524927607506, -76.70585975306139};
+__constant__ double c_cos64[4] = {-19.739208802178716, 64.9393940226683, -85.45681720669373, 60.24464137187666};
+// sin and cos of 2*pi*c by a 1/64-turn table (shared memory, filled from c_rot64) and degree-7/8 Taylor polynomials on the
+// remainder |rho| <= 1/128: e^{2 pi i c} = T[k] e^{2 pi i rho}, k = rint(64 c) mod 64, rho = c - k/64 (exact).  Four FP64
+// operations and all of the quadrant selects fewer than the quarter-turn reduction; the W arguments advance together.
+template <int W>
+__device__ __forceinline__ void sincos_cycles_tab(const double (&c)[W], const double2 *__restrict__ rot, double (&sn)[W], double (&cs)[W]) {
+    double rho[W], x2[W], ps[W], pc[W];
+    double2 T[W];
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const double kq = rint(64.0 * c[i]);
+        rho[i] = fma(-0.015625, kq, c[i]);
+        T[i] = rot[(int)kq & 63];
+        x2[i] = rho[i] * rho[i];
+        ps[i] = c_sin64[3]; pc[i] = c_cos64[3];
+    }
+#pragma unroll
+    for (int k = 2; k >= 0; k--) {
+#pragma unroll
+        for (int i = 0; i < W; i++) { ps[i] = fma(ps[i], x2[i], c_sin64[k]); pc[i] = fma(pc[i], x2[i], c_cos64[k]); }
+    }
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        ps[i] *= rho[i];                 // sin(2 pi rho)
+        pc[i] = fma(pc[i], x2[i], 1.0);  // cos(2 pi rho)
+        cs[i] = fma(T[i].x, pc[i], -T[i].y * ps[i]);
+        sn[i] = fma(T[i].x, ps[i], T[i].y * pc[i]);
+    }
+}
+
 // robust bracketed Newton (rare path: cold-start failures, turnover neighbourhood)
 __device__ __noinline__ double solve_bracketed(double c1, double c2, double c3, double delta, double xl, double xh,
                                                double sdir, double hj) {
@@ -1009,8 +1057,8 @@ __device__ __noinline__ double2 spa_fix(double fdot, double fddot, double s, dou
 //      copy of its neighbour) but not accumulated ----
 template <int W>
 __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)[W], const bool (&in)[W], const Piece &S,
-                                         const int fl, const int few, double (&ad_r)[W], double (&ad_i)[W], double (&ao_r)[W],
-                                         double (&ao_i)[W]) {
+                                         const int fl, const int few, const double2 *__restrict__ rot, double (&ad_r)[W],
+                                         double (&ad_i)[W], double (&ao_r)[W], double (&ao_i)[W]) {
     double er[W], ei[W];
     {
         double re[W], im[W], s[W], uu[W], fd[W], fdd[W], sn[W], cs[W], cyc[W];
@@ -1036,7 +1084,7 @@ __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)
             const double poly = fma(fi, xi, xi * fma(xi, fma(xi, p3, p2), p1));
             cyc[i] = ((p0 - mu_hi) + (e0 - mu_lo)) + poly;
         }
-        sincos_cycles_n<W>(cyc, sn, cs);
+        sincos_cycles_tab<W>(cyc, rot, sn, cs);
         bool slow = false; // one branch for all W bins: the rare path is taken by the whole group
 #pragma unroll
         for (int i = 0; i < W; i++) slow |= !(uu[i] <= 0.0009765625);
@@ -1555,6 +1603,7 @@ struct SumShared { // static shared memory of the mode-sum CTA
     unsigned long long full[SUM_RING], empty[SUM_RING]; // mbarriers: pass published and its pieces landed / pass released by all consumer warps
     int4 hdr[SUM_RING];                                 // (tile, walker, sub-entries in the pass, PASS_* flags)
     int list[64], rec[64];                              // producer: overlapping group records waiting for a fill round
+    double2 rot[64];                                    // (cos, sin)(2 pi k / 64): the consumers' sincos table
 };
 
 // ------------------------------------------------------------------------------------------------------------------
@@ -1903,8 +1952,8 @@ __device__ __forceinline__ void sum_consumer(const SumParams &p, SumShared &sh, 
                     x[0] = solve_slow(S.c1, S.c2, S.c3, f[0] - S.c0, xlo, xhi, tolr, sdir);
                     x[1] = solve_slow(S.c1, S.c2, S.c3, f[1] - S.c0, xlo, xhi, tolr, sdir);
                 }
-                if (fl & SE_SIDE) eval_sub<2>(x, f, in, S, fl, p.k13_few, wm_r, wm_i, wp_r, wp_i); // bins at -f: direct -> W(-f)
-                else eval_sub<2>(x, f, in, S, fl, p.k13_few, wp_r, wp_i, wm_r, wm_i);
+                if (fl & SE_SIDE) eval_sub<2>(x, f, in, S, fl, p.k13_few, sh.rot, wm_r, wm_i, wp_r, wp_i); // bins at -f: direct -> W(-f)
+                else eval_sub<2>(x, f, in, S, fl, p.k13_few, sh.rot, wp_r, wp_i, wm_r, wm_i);
             }
         }
         __syncwarp();
@@ -1933,6 +1982,7 @@ __global__ void SUM_BOUNDS mode_sum_kernel(SumParams p) {
     FillEntry *ent = reinterpret_cast<FillEntry *>(ring + SUM_RING * SUM_SUBCAP);
     RecC *sR = reinterpret_cast<RecC *>(ent + SUM_ECAP);
     double *sK = reinterpret_cast<double *>(sR + SUM_RCAP);
+    if (threadIdx.x < 64) sh.rot[threadIdx.x] = make_double2(c_rot64[2 * threadIdx.x], c_rot64[2 * threadIdx.x + 1]);
     if (threadIdx.x == 0) {
         for (int i = 0; i < SUM_RING; i++) { mbar_init(&sh.full[i], 1); mbar_init(&sh.empty[i], SUM_CW); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -2994,6 +3044,12 @@ int emrifd_walker_status_dev(emrifd_handle_t *h, int64_t B, int32_t *status_dev)
     if ((int64_t)sizeof(int) * B > h->wstatus_cap) return set_err(h, EMRIFD_ERR_INVALID, "walker_status_dev: no batch of that size has run on this handle");
     cudaSetDevice(h->device);
     CUDA_TRY(h, cudaMemcpyAsync(status_dev, h->d_wstatus, sizeof(int) * (size_t)B, cudaMemcpyDeviceToDevice, h->stream));
+    return 0;
+}
+
+int emrifd_set_overlap(emrifd_handle_t *h, int enable) {
+    if (!h) return EMRIFD_ERR_INVALID;
+    h->overlap_mode = enable ? 1 : 0;
     return 0;
 }
 

@@ -149,6 +149,10 @@ int emrifd_batch_status(emrifd_handle_t *h);
 int emrifd_walker_status(emrifd_handle_t *h, int64_t B, int32_t *status_host);
 /* same words copied to a DEVICE buffer on the handle's stream, no sync (pipelined callers read them back with the results) */
 int emrifd_walker_status_dev(emrifd_handle_t *h, int64_t B, int32_t *status_dev);
+/* 1 (default): the zero-fill of the empty tiles runs on an internal stream underneath mode_sum_kernel (joined before the call's
+ * results are used); 0: after it on the handle's stream (profiling: the sum's duration without the store stream beside it).
+ * Results are identical either way. */
+int emrifd_set_overlap(emrifd_handle_t *h, int enable);
 /* EMRIFD_K13_EXACT (default) or EMRIFD_K13_FEW for every later mode sum on this handle. */
 int emrifd_set_k13_mode(emrifd_handle_t *h, int mode);
 
