@@ -1072,7 +1072,8 @@ __device__ __forceinline__ void eval_sub(const double (&x)[W], const double (&f)
             // SPA factor, common path (X >= 1024): s = 1/sqrt|fdot|, u = 1/X = 3 fddot^2 s^6/(2 pi)
             s[i] = fast_rsqrt(fabs(fd[i]));
             const double s2 = s[i] * s[i];
-            uu[i] = 0.477464829275686 * (fdd[i] * fdd[i]) * (s2 * s2 * s2);
+            const double tq = (0.6909882989426709 * fdd[i]) * s2;         // sqrt(3 / 2 pi) fddot s^2
+            uu[i] = (tq * tq) * s2;
             const double w = uu[i] * uu[i];
             re[i] = fma(w, fma(w, k13_asym_re[2], k13_asym_re[1]), 1.0) * s[i];
             im[i] = uu[i] * fma(w, fma(w, k13_asym_im[2], k13_asym_im[1]), k13_asym_im[0]) * s[i];
