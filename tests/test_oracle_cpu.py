@@ -265,3 +265,26 @@ def test_fast_cpu_baseline_matches_oracle(name, generator, oracle_quad):
     assert np.allclose(like, ref, rtol=1e-9, atol=1e-9 * abs(ref[2]))
     _, _, like2, nev2 = fast.sum(it, N, val, data_w=d, wfac=w, want_h=False)            # likelihood only: same sums
     assert np.allclose(like2, like, rtol=1e-13) and nev2 == nev and 0 < nev <= oracle_quad.last_n_eval
+
+
+def test_walker_cost_estimate_tracks_the_work_list(generator, oracle_f64):
+    """engine.walker_cost_estimate (host-side, from the tracks alone: bins swept by every distinct (m, n) harmonic) against the
+    exact number of stationary points the oracle's work-list implies (one per (m, n) group and covered bin): within 10 % on
+    systems with and without turnovers -- good enough to balance walker shards across ranks (distributed.balanced_walker_assignment)."""
+    from emri_frequencydomainwaveforms_b200 import engine
+    gen, orc = generator, oracle_f64
+    for name in ("cfg1_like", "plunge", "ecc_many"):
+        it = make_item(gen, name, dt=10.0)
+        N = it["N"]
+        val = 1.0 / (N * it["dt"])
+        R = np.concatenate([it["teuk_modes"].real.T, it["teuk_modes"].imag.T, [it["f_phi"], it["f_r"], it["Phi_phi"], it["Phi_r"]]])
+        coeff = orc.spline_build(it["t"], R)
+        br, nbr = orc.segment_build(it["t"], coeff, it["m_arr"], it["n_arr"], N, val)
+        cnt = np.where(br["end"] >= br["start"], br["end"] - br["start"] + 1, 0).reshape(len(it["m_arr"]), -1).sum(axis=1)
+        seen, exact = set(), 0
+        for k, mn in enumerate(zip(it["m_arr"].tolist(), it["n_arr"].tolist())):
+            if mn not in seen:
+                seen.add(mn)
+                exact += int(cnt[k])
+        est = engine.walker_cost_estimate(it, val)
+        assert abs(est - exact) <= 0.10 * exact, (name, est, exact)
