@@ -132,7 +132,7 @@ def bench_batches(rank, B, nbatch=NBATCH, world=1):
     if world == 1:
         return own
     from emri_frequencydomainwaveforms_b200 import distributed as D, engine
-    pools = [own if g == rank else draw_pool(g, B, nbatch, wait_s=900.0) for g in range(world)]
+    pools = [own if g == rank else draw_pool(g, B, nbatch, wait_s=300.0) for g in range(world)]
     df = 1.0 / (grid_len() * DT)
     out = []
     for k in range(nbatch):
