@@ -1543,6 +1543,17 @@ __device__ __forceinline__ void mbar_wait(unsigned long long *bar, unsigned pari
                      : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
     } while (!ok);
 }
+// the producer warp's wait for a free slot: it is ahead of the consumers most of the time, so it sleeps between polls instead of
+// taking issue slots from the consumer warps that share its scheduler
+__device__ __forceinline__ void mbar_wait_relaxed(unsigned long long *bar, unsigned parity) {
+    unsigned ok;
+    for (;;) {
+        asm volatile("{\n\t.reg .pred p;\n\tmbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}"
+                     : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+        if (ok) break;
+        __nanosleep(400);
+    }
+}
 // global -> shared bulk copy by the TMA; completion is counted in bytes on `bar`
 __device__ __forceinline__ void tma_copy(void *dst_smem, const void *src_global, unsigned bytes, unsigned long long *bar) {
     asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];"
@@ -1717,7 +1728,7 @@ __device__ __forceinline__ void sum_producer(const SumParams &p, SumShared &sh, 
                     const int nsw = tot - w0 < SUM_SUBCAP ? tot - w0 : SUM_SUBCAP;
                     if (pending >= 0) { if (lane == 0) mbar_arrive(&sh.full[pending]); pending = -1; }
                     const int slot = it % SUM_RING;
-                    mbar_wait(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
+                    mbar_wait_relaxed(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
                     it++;
                     if (lane == 0) {
                         mbar_expect_tx(&sh.full[slot], (unsigned)(nsw * sizeof(Piece)));
@@ -1775,7 +1786,7 @@ __device__ __forceinline__ void sum_producer(const SumParams &p, SumShared &sh, 
             // ---- end of the tile: its last pass carries PASS_LAST (a tile without sub-entries gets an empty pass) ----
             if (pending < 0) {
                 const int slot = it % SUM_RING;
-                mbar_wait(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
+                mbar_wait_relaxed(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
                 it++;
                 if (lane == 0) { sh.hdr[slot] = make_int4(tile_x, walker_y, 0, PASS_FIRST | PASS_LAST); STAT_ADD(7, 1); mbar_arrive(&sh.full[slot]); }
             } else {
@@ -1787,7 +1798,7 @@ __device__ __forceinline__ void sum_producer(const SumParams &p, SumShared &sh, 
     }
     { // no more tiles
         const int slot = it % SUM_RING;
-        mbar_wait(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
+        mbar_wait_relaxed(&sh.empty[slot], ((it / SUM_RING) & 1) ^ 1);
         if (lane == 0) { sh.hdr[slot] = make_int4(0, 0, 0, PASS_QUIT); mbar_arrive(&sh.full[slot]); }
     }
 }
