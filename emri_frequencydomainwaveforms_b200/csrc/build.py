@@ -35,7 +35,7 @@ def build(force=False, verbose=False):
         return OUT
     nvcc = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
     cmd = [nvcc, "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-           "-Xcompiler", "-fPIC", "-shared", "-o", OUT, SRC]
+           "-Xcompiler", "-fPIC", "-Xcompiler", "-fopenmp", "-shared", "-o", OUT, SRC]
     if verbose:
         cmd.insert(1, "-Xptxas=-v")
     subprocess.check_call(cmd)
