@@ -616,7 +616,7 @@ def leg_from_parameters(args, h, batches, N, n, val, B, world, dist, barrier, de
         P = np.tile(P, (4, 1))              # configs[4]: 1024 walkers per likelihood call (16 chunks of 64: the pipeline reaches steady state)
         kw = dict(T=T_YR, dt=DT, eps=EPS, N=N)
         model.get_ll(P, **kw)               # warm-up of the pipelined path (side handles, allocator pools of the side streams)
-        reps = 2
+        reps = 6
         barrier()
         t0 = time.perf_counter()
         for _ in range(reps):

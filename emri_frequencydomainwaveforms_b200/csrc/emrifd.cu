@@ -99,6 +99,7 @@ struct emrifd_handle {
     int *d_gcount; int64_t gcount_cap;
     double *d_gq; int64_t gq_cap;
     void *d_pieces; int64_t pieces_cap; // piece table of the batch being summed
+    char *d_selovf; int64_t selovf_cap; // mode selection: samples left to the full-capacity launch
     int64_t tot_modes, tot_teuk; // packed sizes of the batch validated last (sum K, sum L*K)
     int k13_few;
     // kernel timing
@@ -2115,6 +2116,7 @@ __global__ void __launch_bounds__(256) loglike_partial_kernel(const double2 *__r
 // ==========================================================================================
 #define SEL_THREADS 256
 #define SEL_CAP 8192 /* >= M + Mneg (7137 for l <= 10, |n| <= 30) */
+#define SEL_CAP_SMALL 1024 /* sort capacity of the first launch */
 
 struct SelParams {
     const double2 *teuk;     // [nsamp][M]
@@ -2124,6 +2126,9 @@ struct SelParams {
     int M, Mneg, B;
     double eps;
     unsigned char *flags;    // [B][M], zero-initialised by the caller
+    int cap;                 // sort capacity of this launch (entries of shared memory)
+    int pass;                // 0: every sample, survivors beyond cap -> ovf[samp] = 1 and nothing written; 1: only the samples with ovf set
+    unsigned char *ovf;      // [nsamp]
 };
 
 __device__ __forceinline__ double sel_power(const SelParams &p, const double2 *A, const double2 *Y, int i) {
@@ -2136,13 +2141,14 @@ __device__ __forceinline__ double sel_power(const SelParams &p, const double2 *A
 
 __global__ void __launch_bounds__(SEL_THREADS) mode_select_kernel(SelParams p) {
     extern __shared__ __align__(16) unsigned char smraw[];
-    double *key = reinterpret_cast<double *>(smraw);                         // [SEL_CAP]
-    unsigned short *idx = reinterpret_cast<unsigned short *>(key + SEL_CAP); // [SEL_CAP]
+    double *key = reinterpret_cast<double *>(smraw);                       // [cap]
+    unsigned short *idx = reinterpret_cast<unsigned short *>(key + p.cap); // [cap]
     __shared__ double s_red[SEL_THREADS / 32];
     __shared__ double s_total;
     __shared__ int s_count, s_end;
     const int samp = blockIdx.x, w = p.samp_walker[samp], Mtot = p.M + p.Mneg;
     if (w < 0 || w >= p.B) return; // a sample that names no walker of the batch is ignored (never an out-of-bounds flag write)
+    if (p.pass == 1 && !p.ovf[samp]) return; // handled by the small-capacity launch
     const double2 *A = p.teuk + (long long)samp * p.M;
     const double2 *Y = p.ylm + (long long)w * Mtot;
     double part = 0.0;
@@ -2158,10 +2164,14 @@ __global__ void __launch_bounds__(SEL_THREADS) mode_select_kernel(SelParams p) {
     // survivors of the pre-filter, compacted in arbitrary order (the sort below is a total order)
     for (int i = threadIdx.x; i < Mtot; i += SEL_THREADS) {
         const double pw = sel_power(p, A, Y, i);
-        if (!(pw < cut)) { const int s = atomicAdd(&s_count, 1); key[s] = pw; idx[s] = (unsigned short)i; }
+        if (!(pw < cut)) { const int s = atomicAdd(&s_count, 1); if (s < p.cap) { key[s] = pw; idx[s] = (unsigned short)i; } }
     }
     __syncthreads();
     const int cnt = s_count;
+    if (p.pass == 0) { // more survivors than this launch can sort: leave the sample to the full-capacity launch
+        if (threadIdx.x == 0) p.ovf[samp] = cnt > p.cap ? 1 : 0;
+        if (cnt > p.cap) return;
+    }
     int n2 = 2;
     while (n2 < cnt) n2 <<= 1;
     for (int i = cnt + threadIdx.x; i < n2; i += SEL_THREADS) { key[i] = -1.0; idx[i] = 0xffff; } // padding sorts last
@@ -2606,7 +2616,7 @@ int emrifd_destroy(emrifd_handle_t *h) {
     cudaSetDevice(h->device);
     cudaStreamSynchronize(h->stream);
     cudaFree(h->d_status); cudaFree(h->d_walkers); cudaFree(h->d_queue); cudaFree(h->d_partial); cudaFree(h->d_ws); cudaFree(h->d_chunk); cudaFree(h->d_tiledd);
-    cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq); cudaFree(h->d_gmem); cudaFree(h->d_goff); cudaFree(h->d_pieces);
+    cudaFree(h->d_wstatus); cudaFree(h->d_leader); cudaFree(h->d_gcount); cudaFree(h->d_gq); cudaFree(h->d_gmem); cudaFree(h->d_goff); cudaFree(h->d_pieces); cudaFree(h->d_selovf);
     if (h->h_ws) cudaFreeHost(h->h_ws);
     for (int i = 0; i < 4; i++) { if (h->h_stage[i]) cudaFreeHost(h->h_stage[i]); if (h->stage_ev[i]) cudaEventDestroy(h->stage_ev[i]); }
     for (int i = 0; i < 64; i++) { if (h->ev_a[i]) cudaEventDestroy(h->ev_a[i]); if (h->ev_b[i]) cudaEventDestroy(h->ev_b[i]); if (h->ev_m[i]) cudaEventDestroy(h->ev_m[i]); if (h->ev_s[i]) cudaEventDestroy(h->ev_s[i]); }
@@ -3103,9 +3113,20 @@ int emrifd_mode_select(emrifd_handle_t *h, const double *teuk, int64_t nsamp, in
     p.teuk = (const double2 *)teuk; p.samp_walker = samp_walker; p.ylm = (const double2 *)ylm; p.neg_src = neg_src;
     p.M = (int)M; p.Mneg = (int)Mneg; p.B = (int)B; p.eps = eps; p.flags = flags;
     CUDA_TRY(h, cudaMemsetAsync(flags, 0, (size_t)(B * M), h->stream));
-    const size_t smem = SEL_CAP * (sizeof(double) + sizeof(unsigned short));
-    mode_select_kernel<<<(unsigned)nsamp, SEL_THREADS, smem, h->stream>>>(p);
-    h->launches++;
+    // Two launches: a small sort capacity first (10 KB of shared memory instead of 80: eight resident CTAs per SM instead of
+    // two -- at eps = 1e-2 a few hundred modes survive the pre-filter), then the full capacity for the samples that overflowed
+    // (every other CTA of that launch exits at once).  No host round trip, identical results.
+    int rc = ensure_bytes(h, (void **)&h->d_selovf, &h->selovf_cap, nsamp);
+    if (rc) return rc;
+    p.ovf = (unsigned char *)h->d_selovf;
+    auto launch = [&](int pass, int cap) {
+        p.pass = pass; p.cap = cap;
+        mode_select_kernel<<<(unsigned)nsamp, SEL_THREADS, (size_t)cap * (sizeof(double) + sizeof(unsigned short)), h->stream>>>(p);
+        h->launches++;
+    };
+    if (M + Mneg <= SEL_CAP_SMALL) launch(0, SEL_CAP_SMALL);   // cannot overflow
+    else if (eps < 1e-3) launch(0, SEL_CAP);                    // most modes survive the pre-filter: full capacity straight away
+    else { launch(0, SEL_CAP_SMALL); launch(1, SEL_CAP); }
     CUDA_TRY(h, cudaGetLastError());
     return 0;
 }
