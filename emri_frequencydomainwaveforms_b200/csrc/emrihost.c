@@ -74,16 +74,18 @@ static double carlson_rj(double x, double y, double z, double p) { /* p > 0 */
 
 static double carlson_rd(double x, double y, double z) { return carlson_rj(x, y, z, z); }
 
-static double ellip_k(double m) { return carlson_rf(0.0, 1.0 - m, 1.0); }
-static double ellip_e(double m) { return carlson_rf(0.0, 1.0 - m, 1.0) - m / 3.0 * carlson_rd(0.0, 1.0 - m, 1.0); }
-static double ellip_pi(double n, double m) { return carlson_rf(0.0, 1.0 - m, 1.0) + n / 3.0 * carlson_rj(0.0, 1.0 - m, 1.0, 1.0 - n); }
+/* K(m) = R_F(0, 1 - m, 1), E(m) = K - m/3 R_D(0, 1 - m, 1), Pi(n, m) = K + n/3 R_J(0, 1 - m, 1, 1 - n) */
 
 /* ---- A2: Schwarzschild Omega_phi, Omega_r (dimensionless) ----------------------------------- */
 static void schw_freqs(double p, double e, double *om_phi, double *om_r) {
     double m = 4.0 * e / (p - 6.0 + 2.0 * e);
-    double K = ellip_k(m), E = ellip_e(m);
-    double P1 = ellip_pi(16.0 * e / (12.0 + 8.0 * e - 4.0 * e * e - 8.0 * p + p * p), m);
-    double P2 = ellip_pi(2.0 * e * (p - 4.0) / ((1.0 + e) * (p - 6.0 + 2.0 * e)), m);
+    /* K, E, Pi(n1), Pi(n2) share R_F(0, 1 - m, 1): evaluated once (the same values as ellip_k / ellip_e / ellip_pi, bit for bit) */
+    const double K = carlson_rf(0.0, 1.0 - m, 1.0);
+    const double E = K - m / 3.0 * carlson_rd(0.0, 1.0 - m, 1.0);
+    const double n1 = 16.0 * e / (12.0 + 8.0 * e - 4.0 * e * e - 8.0 * p + p * p);
+    const double n2 = 2.0 * e * (p - 4.0) / ((1.0 + e) * (p - 6.0 + 2.0 * e));
+    const double P1 = K + n1 / 3.0 * carlson_rj(0.0, 1.0 - m, 1.0, 1.0 - n1);
+    const double P2 = K + n2 / 3.0 * carlson_rj(0.0, 1.0 - m, 1.0, 1.0 - n2);
     double p2 = p * p;
     double B = (-2.0 * P2 * (6.0 + 2.0 * e - p) * (3.0 + e * e - p) * p2) / ((-1.0 + e) * (1.0 + e) * (1.0 + e))
              - (E * (-4.0 + p) * p2 * (-6.0 + 2.0 * e + p)) / (-1.0 + e * e)
