@@ -466,18 +466,6 @@ __global__ void __launch_bounds__(SEG_THREADS) segment_kernel(SegParams p, int *
 // ==========================================================================================
 // SPA factor  R(X) = K_{1/3}(-iX) e^{-iX} sqrt(2X/pi) e^{-i pi/4}
 // ==========================================================================================
-__device__ __forceinline__ void k13_asym(double X, double &re, double &im) {
-    const double u = 1.0 / X, w = u * u;
-    if (X >= 1024.0) { // terms beyond a_5 are < 3e-19
-        re = fma(w, fma(w, k13_asym_re[2], k13_asym_re[1]), 1.0);
-        im = u * fma(w, fma(w, k13_asym_im[2], k13_asym_im[1]), k13_asym_im[0]);
-        return;
-    }
-    double pr = k13_asym_re[6], pi = k13_asym_im[6];
-#pragma unroll
-    for (int k = 5; k >= 0; k--) { pr = fma(pr, w, k13_asym_re[k]); pi = fma(pi, w, k13_asym_im[k]); }
-    re = pr; im = u * pi;
-}
 __device__ __noinline__ void k13_mid(double X, double &re, double &im) {
     // 1 <= X < 32: octave polynomial in s = 4/mant - 3
     int ex;
@@ -508,33 +496,8 @@ __device__ __noinline__ void k13_small_S(double X, double &re, double &im) {
     im = pref * (ure * sn + uim * cs);
 }
 // G(fdot, fddot) = i fdot/|fddot| (2/sqrt3) K_{1/3}(-iX) e^{-iX},  X = 2 pi fdot^3 / (3 fddot^2)
-//               = e^{+-i 3pi/4} R(|X|)/sqrt|fdot|   (conjugated for fdot < 0)
-__device__ __forceinline__ void spa_G(double fdot, double fddot, double &gre, double &gim) {
-    const double af = fabs(fdot);
-    double re, im;
-    if (fddot == 0.0) { re = rsqrt(af); im = 0.0; }
-    else {
-        const double X = 2.0943951023931953 * af * af * af / (fddot * fddot); // 2pi/3
-        if (X >= 32.0) {
-            k13_asym(X, re, im);
-            const double sc = rsqrt(af);
-            re *= sc; im *= sc;
-        } else if (X >= 1.0) {
-            k13_mid(X, re, im);
-            const double sc = rsqrt(af);
-            re *= sc; im *= sc;
-        } else {
-            k13_small_S(X, re, im);
-            const double sc = cbrt(1.4472025091165353 / fabs(fddot));
-            re *= sc; im *= sc;
-        }
-    }
-    const double r2 = 0.7071067811865476;
-    gre = (-re - im) * r2;
-    gim = (re - im) * r2;
-    if (fdot < 0.0) gim = -gim;
-}
-
+//               = e^{+-i 3pi/4} R(|X|)/sqrt|fdot|   (conjugated for fdot < 0): evaluated inside eval_sub (common path) and
+// spa_fix (X < 1024); k13_mid / k13_small_S are its rarer ranges.
 // ==========================================================================================
 // A5-A7 (+A11): bin-owner mode sum
 // ==========================================================================================
@@ -647,35 +610,6 @@ __device__ __forceinline__ void sincos_cycles(double c, double &sn, double &cs) 
     cs = ((qi + 1) & 2) ? -b : b;
 }
 
-// the same for W arguments at once, the W pairs of Horner chains advanced together (2 W independent dependency chains)
-template <int W>
-__device__ __forceinline__ void sincos_cycles_n(const double (&c)[W], double (&sn)[W], double (&cs)[W]) {
-    double r[W], r2[W], ps[W], pc[W];
-    int qi[W];
-#pragma unroll
-    for (int i = 0; i < W; i++) {
-        const double q = rint(4.0 * c[i]);
-        qi[i] = (int)q;
-        r[i] = fma(-0.25, q, c[i]);
-        r2[i] = r[i] * r[i];
-        ps[i] = c_sin[7]; pc[i] = c_cos[8];
-    }
-#pragma unroll
-    for (int k = 6; k >= 0; k--) {
-#pragma unroll
-        for (int i = 0; i < W; i++) { ps[i] = fma(ps[i], r2[i], c_sin[k]); pc[i] = fma(pc[i], r2[i], c_cos[k + 1]); }
-    }
-#pragma unroll
-    for (int i = 0; i < W; i++) {
-        ps[i] *= r[i];
-        pc[i] = fma(pc[i], r2[i], c_cos[0]);
-        const bool swap = qi[i] & 1;
-        const double a = swap ? pc[i] : ps[i], b = swap ? ps[i] : pc[i];
-        sn[i] = (qi[i] & 2) ? -a : a;
-        cs[i] = ((qi[i] + 1) & 2) ? -b : b;
-    }
-}
-
 __constant__ double c_rot64[128] = {
     1.0, 0.0, 0.9951847266721969, 0.0980171403295606, 0.9807852804032304, 0.19509032201612828, 0.9569403357322088, 0.2902846772544624,
     0.9238795325112867, 0.3826834323650898, 0.881921264348355, 0.47139673682599764, 0.8314696123025452, 0.5555702330196022, 0.773010453362737, 0.6343932841636455,
@@ -761,41 +695,6 @@ __device__ __noinline__ double solve_slow(double c1, double c2, double c3, doubl
         }
     }
     return solve_bracketed(c1, c2, c3, delta, xlo, xhi, sdir, tol * 1e6);
-}
-
-// SPA factor from fdot, fddot without divisions on the common path:
-//   s = 1/sqrt|fdot|,  u = 1/X = 3 fddot^2 s^6 / (2 pi)
-__device__ __forceinline__ void spa_G2(double fdot, double fddot, double &gre, double &gim) {
-    const double af = fabs(fdot);
-    const double s = fast_rsqrt(af);
-    const double s2 = s * s;
-    const double u = 0.477464829275686 * (fddot * fddot) * (s2 * s2 * s2); // 3/(2 pi)
-    double re, im;
-    if (u <= 0.03125) { // X >= 32 (covers fddot == 0)
-        const double w = u * u;
-        if (u <= 0.0009765625) {
-            re = fma(w, fma(w, k13_asym_re[2], k13_asym_re[1]), 1.0);
-            im = u * fma(w, fma(w, k13_asym_im[2], k13_asym_im[1]), k13_asym_im[0]);
-        } else {
-            double pr = k13_asym_re[6], pi = k13_asym_im[6];
-#pragma unroll
-            for (int k = 5; k >= 0; k--) { pr = fma(pr, w, k13_asym_re[k]); pi = fma(pi, w, k13_asym_im[k]); }
-            re = pr; im = u * pi;
-        }
-        re *= s; im *= s;
-    } else if (u <= 1.0) { // 1 <= X < 32
-        k13_mid(1.0 / u, re, im);
-        re *= s; im *= s;
-    } else {               // X < 1: turnover regime, finite as fdot -> 0
-        const double X = 2.0943951023931953 * af * af * af / (fddot * fddot);
-        k13_small_S(X, re, im);
-        const double sc = cbrt(1.4472025091165353 / fabs(fddot));
-        re *= sc; im *= sc;
-    }
-    const double r2 = 0.7071067811865476;
-    gre = (-re - im) * r2;
-    gim = (re - im) * r2;
-    if (fdot < 0.0) gim = -gim;
 }
 
 // ==========================================================================================
