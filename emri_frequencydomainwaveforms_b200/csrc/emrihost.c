@@ -5,7 +5,7 @@
  * integrator" (FastEMRIWaveforms integrates in C++: upstream src/Inspiral.cc, src/Utility.cc; SURVEY.md
  * section 2.2, section 8f rank 3).  This file is the native stand-in for that producer:
  *   - Schwarzschild fundamental frequencies Omega_phi, Omega_r from complete elliptic integrals
- *     (Carlson R_F, R_D, R_J duplication algorithms) -- row A2 of the scope table, called inside
+ *     (K, E by the arithmetic-geometric mean, Pi by Carlson's R_J duplication algorithm) -- row A2 of the scope table, called inside
  *     FDInterpolatedModeSum.sum for the L sparse points;
  *   - an adaptive Dormand-Prince 5(4) integrator of (p, e, Phi_phi, Phi_r) with the step control and dense
  *     output of SciPy's RK45, whose accepted steps ARE the sparse trajectory, stopping 0.1 outside the
@@ -23,23 +23,7 @@
 
 #define DIST_TO_SEP 0.1
 
-/* ---- Carlson symmetric forms (duplication; Carlson 1995) ------------------------------------ */
-static double carlson_rf(double x, double y, double z) {
-    double A0 = (x + y + z) / 3.0, A = A0;
-    const double Q = fmax(fmax(fabs(A0 - x), fabs(A0 - y)), fabs(A0 - z)) / pow(3.0e-17, 1.0 / 6.0);
-    double p4 = 1.0;
-    for (int n = 0; n < 60 && p4 * Q >= fabs(A); n++) {
-        const double sx = sqrt(x), sy = sqrt(y), sz = sqrt(z);
-        const double lam = sx * sy + sy * sz + sz * sx;
-        A = (A + lam) * 0.25; x = (x + lam) * 0.25; y = (y + lam) * 0.25; z = (z + lam) * 0.25;
-        p4 *= 0.25;
-    }
-    /* (A_n - x_n) = (A_0 - x_0)/4^n, so the scaled differences can be read off the iterates */
-    const double X = 1.0 - x / A, Y = 1.0 - y / A, Z = -X - Y;
-    const double E2 = X * Y - Z * Z, E3 = X * Y * Z;
-    return (1.0 - E2 / 10.0 + E3 / 14.0 + E2 * E2 / 24.0 - 3.0 * E2 * E3 / 44.0) / sqrt(A);
-}
-
+/* ---- Carlson symmetric forms R_C, R_J (duplication; Carlson 1995) ----------------------------- */
 static double carlson_rc(double x, double y) { /* y > 0 */
     if (x == y) return 1.0 / sqrt(x);
     if (x < y) { double d = sqrt((y - x) / x); return atan(d) / sqrt(y - x); }
@@ -83,16 +67,27 @@ static double carlson_rj(double x, double y, double z, double p) { /* p > 0 */
     return p4 * ser / (A * sqrt(A)) + 6.0 * sum;
 }
 
-static double carlson_rd(double x, double y, double z) { return carlson_rj(x, y, z, z); }
 
-/* K(m) = R_F(0, 1 - m, 1), E(m) = K - m/3 R_D(0, 1 - m, 1), Pi(n, m) = K + n/3 R_J(0, 1 - m, 1, 1 - n) */
+/* Pi(n, m) = K(m) + n/3 R_J(0, 1 - m, 1, 1 - n); K and E come from the AGM in schw_freqs */
 
 /* ---- A2: Schwarzschild Omega_phi, Omega_r (dimensionless) ----------------------------------- */
 static void schw_freqs(double p, double e, double *om_phi, double *om_r) {
     double m = 4.0 * e / (p - 6.0 + 2.0 * e);
-    /* K, E, Pi(n1), Pi(n2) share R_F(0, 1 - m, 1): evaluated once (the same values as ellip_k / ellip_e / ellip_pi, bit for bit) */
-    const double K = carlson_rf(0.0, 1.0 - m, 1.0);
-    const double E = K - m / 3.0 * carlson_rd(0.0, 1.0 - m, 1.0);
+    /* complete K(m), E(m) by the arithmetic-geometric mean (quadratic convergence: five or six square roots in all, against
+       ~35 for R_F + R_D): K = pi / (2 agm(1, sqrt(1 - m))), E = K (1 - sum_n 2^(n-1) c_n^2), c_0^2 = m */
+    double K, E;
+    {
+        double a = 1.0, b = sqrt(1.0 - m), c2sum = 0.5 * m, pw = 0.5;
+        for (int it = 0; it < 12; it++) {
+            const double c = 0.5 * (a - b);
+            if (fabs(c) <= 4e-16 * a) break; /* (c enters the next a only at second order) */
+            const double an = 0.5 * (a + b);
+            b = sqrt(a * b); a = an;
+            pw *= 2.0; c2sum += pw * c * c;
+        }
+        K = M_PI / (a + b);           /* a = b to rounding: 2 agm = a + b */
+        E = K * (1.0 - c2sum);
+    }
     const double n1 = 16.0 * e / (12.0 + 8.0 * e - 4.0 * e * e - 8.0 * p + p * p);
     const double n2 = 2.0 * e * (p - 4.0) / ((1.0 + e) * (p - 6.0 + 2.0 * e));
     const double P1 = K + n1 / 3.0 * carlson_rj(0.0, 1.0 - m, 1.0, 1.0 - n1);
