@@ -141,3 +141,38 @@ def test_balanced_walker_assignment():
         assert tot.max() / tot.mean() < 1.02 and tot.max() / tot.mean() < blocks.max() / blocks.mean()
     assert D.balanced_walker_assignment([3.0, 1.0, 2.0], 1) == [[0, 2, 1]]
     assert [len(s) for s in D.balanced_walker_assignment(np.ones(10), 4)] == [3, 3, 2, 2]
+
+
+def test_bench_deals_every_pooled_walker_exactly_once(monkeypatch):
+    """bench.bench_batches for N > 1: the pools of all ranks are dealt per batch index by estimated cost -- every pooled walker goes
+    to exactly one rank, every rank gets B walkers per batch, and the per-rank work estimates are balanced to a few per cent."""
+    import sys, os
+    sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+    import bench
+    rng = np.random.default_rng(11)
+    B, nbatch, world = 6, 2, 4
+
+    def fake_pool(g, B_, nbatch_=bench.NBATCH, wait_s=0.0):
+        r = np.random.default_rng(100 + g)
+        pool = []
+        for k in range(nbatch_):
+            items = []
+            for w in range(B_):
+                L = 12
+                scale = np.exp(r.normal())
+                items.append({"f_phi": np.linspace(1e-3, 1e-3 * (1 + scale), L), "f_r": np.linspace(7e-4, 7e-4 * (1 + 0.5 * scale), L),
+                              "m_arr": np.array([2, 2, 1]), "n_arr": np.array([0, 1, -1]), "tag": (g, k, w)})
+            pool.append(items)
+        return pool
+
+    monkeypatch.setattr(bench, "draw_pool", fake_pool)
+    shares = [bench.bench_batches(r, B, nbatch, world=world) for r in range(world)]
+    from emri_frequencydomainwaveforms_b200 import engine
+    df = 1.0 / (bench.grid_len() * bench.DT)
+    for k in range(nbatch):
+        tags = [it["tag"] for r in range(world) for it in shares[r][k]]
+        assert len(tags) == world * B and len(set(tags)) == world * B and all(t[1] == k for t in tags)
+        assert all(len(shares[r][k]) == B for r in range(world))
+        tot = np.array([sum(engine.walker_cost_estimate(it, df) for it in shares[r][k]) for r in range(world)])
+        assert tot.max() / tot.mean() < 1.10
+    assert bench.bench_batches(0, B, nbatch, world=1)[0][0]["tag"] == (0, 0, 0)     # one GPU: pool 0 as drawn
