@@ -132,7 +132,10 @@ def bench_batches(rank, B, nbatch=NBATCH, world=1):
     if world == 1:
         return own
     from emri_frequencydomainwaveforms_b200 import distributed as D, engine
-    pools = [own if g == rank else draw_pool(g, B, nbatch, wait_s=300.0) for g in range(world)]
+    # the other ranks draw their pools at this very moment (torchrun): poll for their files; without them (a single process asked
+    # for --gpus N) draw everything here
+    wait = 300.0 if int(os.environ.get("WORLD_SIZE", "1")) > 1 else 0.0
+    pools = [own if g == rank else draw_pool(g, B, nbatch, wait_s=wait) for g in range(world)]
     df = 1.0 / (grid_len() * DT)
     out = []
     for k in range(nbatch):
